@@ -1,0 +1,310 @@
+// Batched enclosing-subgraph extraction (h = 1) over the device-resident rating CSR/CSC.
+//
+// Replaces, for a whole mini-batch in two launches, the reference's per-pair Python path
+//   MyDynamicDataset.get            util_functions.py:138-145
+//   subgraph_extraction_labeling    util_functions.py:208-247   (BFS, sampling, labels, induced sub-matrix)
+//   construct_pyg_graph / one_hot   util_functions.py:280-297, 307-311
+//   PyG Batch.from_data_list        (third party)
+// and emits the already-collated batch in canonical form: per side the target
+// first, then the fringe in ascending global id; undirected edges sorted by (u_local, v_local).
+//
+// Layout: one CTA per (user,item) pair.
+//   k_extract_select_count : fringe discovery from CSC column j / CSR row i (coalesced int32
+//       loads), uniform k-subset sampling by 4-pass radix-select over counter-hash keys
+//       (no storage, any degree), item-id -> local-id table in shared memory, per-user-row
+//       match count (warp per row).
+//   k_extract_fill         : cross-graph prefix (each CTA sums its predecessors' counts),
+//       second row scan with warp-ballot ordered compaction, writes x / labels / batch / y /
+//       edge_index (int64, PyG order [u|v ; v|u]) / edge_type / node_ptr / edge_ptr.
+// HBM-bound integer work: no tensor cores; int32 index + uint8 rating per nonzero.
+#include "common.cuh"
+#include "../../include/igmc_b200.h"
+
+namespace {
+
+constexpr int EX_THREADS = 256;
+constexpr uint16_t NONE16 = 0xFFFF;
+
+// Select the node list of one side: out[0] = target, out[1..] = (sampled) fringe ascending.
+__device__ void select_side(const int32_t* __restrict__ nbr, int len, int target, int mnph, double ratio,
+                            uint64_t state, int32_t* __restrict__ out, int cap, int* n_out,
+                            int* hist, int* ws, int* sh, int* err) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  if (tid == 0) sh[0] = -1;
+  __syncthreads();
+  for (int p = tid; p < len; p += nt)
+    if (nbr[p] == target) sh[0] = p;  // sorted, duplicate-free list: at most one hit
+  __syncthreads();
+  const int pos = sh[0];
+  const int d = len - (pos >= 0 ? 1 : 0);
+  int k = d;
+  if (ratio < 1.0) k = (int)(ratio * (double)d);   // int(sample_ratio*len(fringe)), ref :223-224
+  if (mnph >= 0 && mnph < k) k = mnph;             // strict '<', ref :226,:228
+  if (k + 1 > cap) {
+    if (tid == 0) { igmc_set_err(err, IGMC_ERR_NODE_CAP); out[0] = target; *n_out = 1; }
+    __syncthreads();
+    return;
+  }
+  if (tid == 0) { out[0] = target; *n_out = 1 + k; }
+  if (k == d) {  // no sampling: ordered copy minus the target
+    for (int p = tid; p < len; p += nt) {
+      if (p == pos) continue;
+      out[1 + p - ((pos >= 0 && p > pos) ? 1 : 0)] = nbr[p];
+    }
+    __syncthreads();
+    return;
+  }
+  if (k == 0) { __syncthreads(); return; }
+
+  // ---- radix-select the k-th smallest 32-bit key (ties resolved by ascending node id) ----
+  uint32_t prefix = 0, mask = 0;
+  int remaining = k;
+  for (int pass = 3; pass >= 0; --pass) {
+    for (int b = tid; b < 256; b += nt) hist[b] = 0;
+    __syncthreads();
+    for (int p = tid; p < len; p += nt) {
+      if (p == pos) continue;
+      uint32_t key = sample_key(state, nbr[p]);
+      if ((key & mask) == prefix) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      int s = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += hist[8 * tid + i];
+      int incl = warp_incl_scan_i(s, tid);
+      int excl = incl - s;
+      if (excl < remaining && remaining <= incl) {
+        int c = excl, b = 8 * tid + 7;
+        for (int i = 0; i < 8; ++i) {
+          int hc = hist[8 * tid + i];
+          if (c + hc >= remaining) { b = 8 * tid + i; break; }
+          c += hc;
+        }
+        sh[1] = b;
+        sh[2] = remaining - c;
+      }
+    }
+    __syncthreads();
+    prefix |= (uint32_t)sh[1] << (8 * pass);
+    mask |= 255u << (8 * pass);
+    remaining = sh[2];
+    __syncthreads();
+  }
+  const uint32_t tau = prefix;  // keys < tau are all taken; `remaining` ties (key == tau) are taken
+  int run_strict = 0, run_tie = 0;
+  for (int base = 0; base < len; base += nt) {
+    const int p = base + tid;
+    int strict = 0, tie = 0, node = 0;
+    if (p < len && p != pos) {
+      node = nbr[p];
+      uint32_t key = sample_key(state, node);
+      strict = key < tau;
+      tie = key == tau;
+    }
+    int tot;
+    int ex = block_excl_scan_i(strict | (tie << 16), ws, &tot);
+    const int sb = run_strict + (ex & 0xFFFF), tb = run_tie + (ex >> 16);
+    if (strict || (tie && tb < remaining)) out[1 + sb + min(tb, remaining)] = node;
+    run_strict += tot & 0xFFFF;
+    run_tie += tot >> 16;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ void resolve_pair(const igmc_pairs_t& P, int g, int* i, int* j, int* lab, int64_t* pid) {
+  const int64_t src = P.idx ? P.idx[g] : (int64_t)g;
+  *i = P.links_u[src];
+  *j = P.links_v[src];
+  *lab = P.links_label ? P.links_label[src] : 0;
+  *pid = P.pair_id ? P.pair_id[g] : src;
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint64_t seed_val,
+                       const uint64_t* __restrict__ seed_dev, int cap,
+                       const int32_t* __restrict__ inj_nodes_u, const int32_t* __restrict__ inj_nodes_v,
+                       const int32_t* __restrict__ inj_n_u, const int32_t* __restrict__ inj_n_v,
+                       int32_t* __restrict__ nodes_u, int32_t* __restrict__ nodes_v,
+                       int32_t* __restrict__ n_u, int32_t* __restrict__ n_v,
+                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ m_cnt, int* err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw);
+  __shared__ int hist[256];
+  __shared__ int ws[34];
+  __shared__ int sh[4];
+  __shared__ int s_nu, s_nv, s_m;
+  const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const uint64_t seed = seed_dev ? *seed_dev : seed_val;
+  int i, j, lab;
+  int64_t pid;
+  resolve_pair(P, g, &i, &j, &lab, &pid);
+  int32_t* gu = nodes_u + (size_t)g * cap;
+  int32_t* gv = nodes_v + (size_t)g * cap;
+  if (tid == 0) s_m = 0;
+  if (inj_nodes_u) {  // test hook: node lists supplied (the reference's own draw)
+    const int nu = inj_n_u[g], nv = inj_n_v[g];
+    if (nu > cap || nv > cap) {
+      if (tid == 0) { igmc_set_err(err, IGMC_ERR_NODE_CAP); s_nu = 1; s_nv = 1; gu[0] = i; gv[0] = j; }
+    } else {
+      for (int t = tid; t < nu; t += nt) gu[t] = inj_nodes_u[(size_t)g * cap + t];
+      for (int t = tid; t < nv; t += nt) gv[t] = inj_nodes_v[(size_t)g * cap + t];
+      if (tid == 0) { s_nu = nu; s_nv = nv; }
+    }
+    __syncthreads();
+  } else {
+    // user fringe = users who rated item j (CSC column j); item fringe = items rated by user i (CSR row i)
+    select_side(G.row_idx + G.col_ptr[j], G.col_ptr[j + 1] - G.col_ptr[j], i, mnph, ratio,
+                sample_state(seed, pid, 0, 1), gu, cap, &s_nu, hist, ws, sh, err);
+    select_side(G.col_idx + G.row_ptr[i], G.row_ptr[i + 1] - G.row_ptr[i], j, mnph, ratio,
+                sample_state(seed, pid, 1, 1), gv, cap, &s_nv, hist, ws, sh, err);
+  }
+  __syncthreads();
+  const int nu = s_nu, nv = s_nv;
+  // item-id -> local-id table
+  for (int t = tid; t < G.num_items; t += nt) tab[t] = NONE16;
+  __syncthreads();
+  for (int b = tid; b < nv; b += nt) tab[gv[b]] = (uint16_t)b;
+  __syncthreads();
+  // per-row match count (warp per user row); bit31 = row contains the target item j
+  for (int a = warp; a < nu; a += nwarps) {
+    const int u = gu[a];
+    const int s = G.row_ptr[u], e = G.row_ptr[u + 1];
+    int cnt = 0, hasj = 0;
+    for (int p = s + lane; p < e; p += 32) {
+      const uint16_t b = tab[G.col_idx[p]];
+      if (b != NONE16) {
+        if (b == 0) { hasj = 1; if (a != 0) ++cnt; }   // (0,0) is the target edge: dropped (ref :238)
+        else ++cnt;
+      }
+    }
+    cnt = warp_sum_i(cnt);
+    hasj = __any_sync(IGMC_FULL, hasj);
+    if (lane == 0) {
+      row_cnt[(size_t)g * cap + a] = cnt | (hasj ? (int)0x80000000 : 0);
+      atomicAdd(&s_m, cnt);
+    }
+  }
+  __syncthreads();
+  if (tid == 0) { n_u[g] = nu; n_v[g] = nv; m_cnt[g] = s_m; }
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
+k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
+               const int32_t* __restrict__ nodes_u, const int32_t* __restrict__ nodes_v,
+               const int32_t* __restrict__ n_u, const int32_t* __restrict__ n_v,
+               const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ m_cnt,
+               const float* __restrict__ class_values, igmc_batch_out_t O, int* err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int* rowoff = reinterpret_cast<int*>(smem_raw);                 // [cap]
+  uint16_t* tab = reinterpret_cast<uint16_t*>(rowoff + cap);      // [num_items]
+  __shared__ int ws[34];
+  const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  int nsum = 0, msum = 0;
+  for (int q = tid; q < g; q += nt) { nsum += n_u[q] + n_v[q]; msum += m_cnt[q]; }
+  const int Nbase = block_sum_i(nsum, ws);
+  const int Mbase = block_sum_i(msum, ws);
+  const int nu = n_u[g], nv = n_v[g], m = m_cnt[g], n = nu + nv;
+  const int32_t* gu = nodes_u + (size_t)g * cap;
+  const int32_t* gv = nodes_v + (size_t)g * cap;
+  const bool overflow = (Nbase + n > O.node_cap) || (2 * (Mbase + m) > O.edge_cap);
+  if (g == B - 1 && tid == 0) {
+    O.counts[0] = Nbase + n;
+    O.counts[1] = 2 * (Mbase + m);
+    O.node_ptr[B] = Nbase + n;
+    O.edge_ptr[B] = 2 * (Mbase + m);
+  }
+  if (tid == 0) { O.node_ptr[g] = Nbase; O.edge_ptr[g] = 2 * Mbase; }
+  if (overflow) {
+    if (tid == 0) igmc_set_err(err, (Nbase + n > O.node_cap) ? IGMC_ERR_NODE_TOTAL : IGMC_ERR_EDGE_CAP);
+    return;
+  }
+  int i, j, lab;
+  int64_t pid;
+  resolve_pair(P, g, &i, &j, &lab, &pid);
+  if (tid == 0) {
+    O.y[g] = class_values[lab];
+    O.graph_nu[g] = nu;
+  }
+  // node labels (h=1): target user 0, target item 1, other users 2, other items 3 (ref :245)
+  for (int t = tid; t < n; t += nt) {
+    const int label = t < nu ? (t == 0 ? 0 : 2) : (t == nu ? 1 : 3);
+    const size_t row = (size_t)Nbase + t;
+    O.node_label[row] = (uint8_t)label;
+    O.batch[row] = g;
+    O.node_gid[row] = t < nu ? gu[t] : gv[t - nu];
+    if (O.x) {
+      for (int f = 0; f < O.feat_dim; ++f) O.x[row * O.feat_dim + f] = (f == label) ? 1.0f : 0.0f;
+    }
+  }
+  // exclusive scan of the per-row match counts
+  int running = 0;
+  for (int base = 0; base < nu; base += nt) {
+    const int a = base + tid;
+    const int c = a < nu ? (row_cnt[(size_t)g * cap + a] & 0x7fffffff) : 0;
+    int tot;
+    const int ex = block_excl_scan_i(c, ws, &tot);
+    if (a < nu) rowoff[a] = running + ex;
+    running += tot;
+  }
+  for (int t = tid; t < G.num_items; t += nt) tab[t] = NONE16;
+  __syncthreads();
+  for (int b = tid; b < nv; b += nt) tab[gv[b]] = (uint16_t)b;
+  __syncthreads();
+  int64_t* ei0 = O.edge_index;
+  int64_t* ei1 = O.edge_index + O.edge_cap;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  for (int a = warp; a < nu; a += nwarps) {
+    const int u = gu[a];
+    const int s = G.row_ptr[u], e = G.row_ptr[u + 1];
+    const int jfirst = (a != 0 && (row_cnt[(size_t)g * cap + a] < 0)) ? 1 : 0;  // j sorts first (v_local 0)
+    const int base = rowoff[a];
+    int seen = 0;
+    for (int p0 = s; p0 < e; p0 += 32) {
+      const int p = p0 + lane;
+      uint16_t b = NONE16;
+      if (p < e) b = tab[G.col_idx[p]];
+      const bool match = (b != NONE16) && !(a == 0 && b == 0);
+      const bool isj = match && b == 0;
+      const unsigned bal = __ballot_sync(IGMC_FULL, match && !isj);
+      if (match) {
+        const int rank = isj ? 0 : (jfirst + seen + __popc(bal & lt_mask));
+        const int64_t r = G.rating[p];
+        const size_t e1 = (size_t)2 * Mbase + base + rank, e2 = e1 + m;
+        const int64_t un = Nbase + a, vn = Nbase + nu + b;
+        ei0[e1] = un; ei1[e1] = vn; O.edge_type[e1] = r;
+        ei0[e2] = vn; ei1[e2] = un; O.edge_type[e2] = r;
+      }
+      seen += __popc(bal);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int max_nodes_per_hop,
+                                  double sample_ratio, uint64_t seed, const uint64_t* seed_dev, int cap,
+                                  const int32_t* inj_nodes_u, const int32_t* inj_nodes_v,
+                                  const int32_t* inj_n_u, const int32_t* inj_n_v,
+                                  const igmc_extract_ws_t* W, const float* class_values,
+                                  const igmc_batch_out_t* O, int* err, void* stream) {
+  if (B <= 0) return 0;
+  if (cap < 1 || cap > 65534) return -2;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smemA = (size_t)G->num_items * sizeof(uint16_t);
+  const size_t smemB = (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
+  if (smemB > 220 * 1024) return -3;  // item table does not fit in shared memory
+  cudaFuncSetAttribute(k_extract_select_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
+  cudaFuncSetAttribute(k_extract_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
+  k_extract_select_count<<<B, EX_THREADS, smemA, st>>>(*G, *P, B, max_nodes_per_hop, sample_ratio, seed, seed_dev, cap,
+                                                       inj_nodes_u, inj_nodes_v, inj_n_u, inj_n_v,
+                                                       W->nodes_u, W->nodes_v, W->n_u, W->n_v, W->row_cnt, W->m_cnt,
+                                                       err);
+  IGMC_CUDA_CHECK_LAUNCH();
+  k_extract_fill<<<B, EX_THREADS, smemB, st>>>(*G, *P, B, cap, W->nodes_u, W->nodes_v, W->n_u, W->n_v,
+                                               W->row_cnt, W->m_cnt, class_values, *O, err);
+  IGMC_CUDA_CHECK_LAUNCH();
+  return 0;
+}

@@ -1,0 +1,373 @@
+"""Drop-in for the reference's ``models.IGMC`` (models.py:170-217) on the fused sm_100a kernels.
+
+``IGMC(dataset, gconv, latent_dim, num_relations, num_bases, regression, adj_dropout, ...)`` keeps the
+reference constructor, ``forward(data) -> Tensor[B]``, ``reset_parameters()``, the attribute surface
+``convs[l].{att, basis, root, bias, num_bases, num_relations, in_channels, out_channels}``, ``lin1``,
+``lin2`` and therefore the reference's ``state_dict`` keys, so its checkpoints load.
+
+All parameters are views into ONE flat fp32 buffer (``flat_params``), gradients into ``flat_grad``:
+that buffer is what the kernels read, what the single NCCL all-reduce per step moves and what the fused
+Adam updates.  ``forward`` is autograd-capable (custom Function over the C-ABI); the training loop in
+``train_eval`` uses ``fused_step`` which skips autograd altogether.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .util_functions import Batch, _stream_ptr
+
+HID = _lib.HIDDEN
+SMEM_LIMIT = 227 * 1024
+
+
+def _align4(x):
+    return (x + 3) & ~3
+
+
+def splitmix64(x):
+    M = (1 << 64) - 1
+    x = (x + 0x9E3779B97F4A7C15) & M
+    x = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & M
+    x = ((x ^ (x >> 27)) * 0x94D049BB133111EB) & M
+    return x ^ (x >> 31)
+
+
+def edge_keep_reference(seed, num_edges, p):
+    """Host twin of ``edge_keep`` in csrc/common.cuh: bool keep mask for directed edges 0..E-1."""
+    import numpy as np
+    thresh = min(int(float(np.float32(p)) * 4294967296.0), 0xFFFFFFFF)   # the kernel sees p as fp32
+    return torch.tensor([(splitmix64((seed + e) & ((1 << 64) - 1)) >> 32) >= thresh for e in range(num_edges)])
+
+
+class RGCNConv(nn.Module):
+    """Parameter holder with PyG 1.4.2 ``RGCNConv`` names/shapes/init.  The arithmetic
+    lives in the fused kernels of the owning ``IGMC``."""
+
+    def __init__(self, in_channels, out_channels, num_relations, num_bases):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases = num_relations, num_bases
+        self.basis = nn.Parameter(torch.empty(num_bases, in_channels, out_channels))
+        self.att = nn.Parameter(torch.empty(num_relations, num_bases))
+        self.root = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.num_bases * self.in_channels)   # PyG inits.uniform(size, tensor)
+        with torch.no_grad():
+            for p in (self.basis, self.att, self.root, self.bias):
+                p.uniform_(-bound, bound)
+
+    def __repr__(self):
+        return "RGCNConv(%d, %d, num_relations=%d, num_bases=%d)" % (
+            self.in_channels, self.out_channels, self.num_relations, self.num_bases)
+
+
+class _IGMCFunction(torch.autograd.Function):
+    """autograd bridge: forward/backward kernels behind ``IGMC.forward``."""
+
+    @staticmethod
+    def forward(ctx, model, batch, training, drop, *params):
+        out, saved = model._launch_forward(batch, training, drop, y=None)
+        ctx.model, ctx.batch, ctx.saved, ctx.drop = model, batch, saved, drop
+        return out.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model = ctx.model
+        if not ctx.saved["train"]:
+            raise RuntimeError("igmc_b200: backward through an eval-mode forward (zsave not kept); "
+                               "call model.train() or use torch.no_grad()")
+        model._launch_backward(ctx.batch, ctx.drop, ctx.saved,
+                               (grad_out.float() * float(model.multiply_by)).contiguous())
+        model._launch_grad_reduce(ctx.batch, ctx.saved, loss_scale=0.0, arr=0.0, with_loss=False)
+        grads = [model.flat_grad[o:o + n].view(s).clone() for (o, n, s) in model._layout]
+        return (None, None, None, None) + tuple(grads)
+
+
+class IGMC(nn.Module):
+    def __init__(self, dataset, gconv=RGCNConv, latent_dim=[32, 32, 32, 32], num_relations=5, num_bases=2,
+                 regression=False, adj_dropout=0.2, force_undirected=False, side_features=False,
+                 n_side_features=0, multiply_by=1):
+        super().__init__()
+        if not regression:
+            raise NotImplementedError("igmc_b200.IGMC implements the regression head Main.py uses (Main.py:396)")
+        if force_undirected:
+            raise NotImplementedError("force_undirected edge dropout is not on the hot path")
+        if side_features:
+            raise NotImplementedError("side features are outside the hot path (SURVEY.md §2)")
+        if any(int(d) != HID for d in latent_dim) or not (1 <= len(latent_dim) <= _lib.MAX_LAYERS):
+            raise NotImplementedError("latent_dim entries must be 32 (Main.py:391 hard-codes [32,32,32,32])")
+        if num_bases not in (2, 4):
+            raise NotImplementedError("num_bases must be 2 or 4")
+        self.regression, self.adj_dropout, self.force_undirected = regression, adj_dropout, force_undirected
+        self.side_features, self.multiply_by = side_features, multiply_by
+        num_features = dataset if isinstance(dataset, int) else dataset.num_features
+        self.num_features = int(num_features)
+        if self.num_features > HID:
+            raise NotImplementedError("node feature width > 32")
+        self.num_relations, self.num_bases = int(num_relations), int(num_bases)
+        dims = [self.num_features] + [int(d) for d in latent_dim]
+        self.convs = nn.ModuleList([RGCNConv(dims[l], dims[l + 1], num_relations, num_bases)
+                                    for l in range(len(latent_dim))])
+        self.lin1 = nn.Linear(2 * sum(latent_dim), 128)
+        self.lin2 = nn.Linear(128, 1)
+        self.drop_seed = 0x1234ABCD
+        self._step = 0
+        self._ws = {}
+        self._flatten()
+
+    # ---- flat parameter bucket ---------------------------------------------------------------------
+    def _named_order(self):
+        for l, c in enumerate(self.convs):
+            yield ("att", l, c.att)
+            yield ("basis", l, c.basis)
+            yield ("root", l, c.root)
+            yield ("bias", l, c.bias)
+        yield ("lin1_w", 0, self.lin1.weight)
+        yield ("lin1_b", 0, self.lin1.bias)
+        yield ("lin2_w", 0, self.lin2.weight)
+        yield ("lin2_b", 0, self.lin2.bias)
+
+    def _flatten(self):
+        """(re)create flat_params / flat_grad on the parameters' device and alias every parameter."""
+        items = list(self._named_order())
+        dev = items[0][2].device
+        off, layout, m = 0, [], _lib.Model()
+        m.num_layers, m.num_relations, m.num_bases, m.in_dim0 = len(self.convs), self.num_relations, \
+            self.num_bases, self.num_features
+        for kind, l, p in items:
+            n = p.numel()
+            if kind == "lin1_w":
+                m.conv_param_count = off
+            layout.append((off, n, tuple(p.shape)))
+            if kind == "att":
+                m.off_att[l] = off
+            elif kind == "basis":
+                m.off_basis[l] = off
+            elif kind == "root":
+                m.off_root[l] = off
+            elif kind == "bias":
+                m.off_bias[l] = off
+            else:
+                setattr(m, "off_" + kind, off)
+            off = _align4(off + n)
+        m.param_count = off
+        m.multiply_by = float(self.multiply_by)
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for (o, n, s), (_, _, p) in zip(layout, items):
+                flat[o:o + n].copy_(p.data.reshape(-1).float())
+                p.data = flat[o:o + n].view(s)
+                p.grad = None
+        self.flat_params, self.flat_grad = flat, grad
+        self._layout, self._cmodel = layout, m
+        self._ws = {}
+
+    def alias_grads(self):
+        """point every ``p.grad`` at its slice of ``flat_grad`` (for stock torch optimizers)."""
+        for (o, n, s), (_, _, p) in zip(self._layout, self._named_order()):
+            p.grad = self.flat_grad[o:o + n].view(s)
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        self._flatten()
+        return out
+
+    def reset_parameters(self):
+        for c in self.convs:
+            c.reset_parameters()
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+
+    # ---- kernel launches ---------------------------------------------------------------------------------
+    def _check_fit(self, n_cap, backward):
+        lib = _lib.load()
+        need = lib.igmc_model_smem_bytes(n_cap, self.num_relations, self.num_bases, len(self.convs), int(backward))
+        if need > SMEM_LIMIT:
+            raise RuntimeError("igmc_b200: subgraphs of up to %d nodes need %d B of shared memory per CTA "
+                               "(limit %d); lower --max-nodes-per-hop" % (n_cap, need, SMEM_LIMIT))
+
+    def _workspace(self, batch, train):
+        p = batch._priv
+        key = (p["node_cap"], batch.num_graphs, bool(train))
+        ws = self._ws.get(key)
+        if ws is None:
+            dev, L, NB, B, ncap = self.flat_params.device, len(self.convs), self.num_bases, batch.num_graphs, \
+                p["node_cap"]
+            f32 = dict(dtype=torch.float32, device=dev)
+            ws = dict(states=torch.empty(ncap, HID * L, **f32), inv_deg=torch.empty(ncap, **f32),
+                      feat=torch.empty(B, 2 * HID * L, **f32), hid=torch.empty(B, 128, **f32),
+                      hid_gscale=torch.empty(B, 128, **f32), pred=torch.empty(B, **f32),
+                      target=torch.empty(B, 2, dtype=torch.int32, device=dev),
+                      dpred=torch.zeros(B, **f32), sqerr=torch.zeros(B, **f32), loss=torch.zeros(1, **f32))
+            if train:
+                ws.update(zsave=torch.empty(L, ncap, NB * HID, **f32),
+                          gpart=torch.zeros(B, self._cmodel.conv_param_count, **f32),
+                          dhid=torch.empty(B, 128, **f32))
+            if len(self._ws) > 8:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    def _saved_struct(self, ws, ncap):
+        return _lib.Saved(ws["states"].data_ptr(), _lib.ptr(ws.get("zsave")), ws["inv_deg"].data_ptr(),
+                          ws["feat"].data_ptr(), ws["hid"].data_ptr(), ws["hid_gscale"].data_ptr(),
+                          ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap)
+
+    def make_dropout(self, training, edge_keep=None, hidden_keep=None, seed=None, seed_dev=None):
+        """dropout descriptor of one step (+ the tensors it references, to keep them alive)."""
+        d = _lib.Dropout()
+        d.adj_dropout = float(self.adj_dropout) if training else 0.0
+        d.hidden_dropout = 0.5 if training else 0.0
+        if seed is None:
+            seed = splitmix64(self.drop_seed + self._step)
+        d.seed = int(seed) & ((1 << 64) - 1)
+        keep = []
+        if seed_dev is not None:
+            d.seed_dev = seed_dev.data_ptr()
+            keep.append(seed_dev)
+        if edge_keep is not None:
+            ek = torch.as_tensor(edge_keep).to(self.flat_params.device).to(torch.uint8).contiguous()
+            d.edge_keep = ek.data_ptr()
+            keep.append(ek)
+        if hidden_keep is not None:
+            hk = torch.as_tensor(hidden_keep).to(self.flat_params.device).to(torch.uint8).contiguous()
+            d.hidden_keep = hk.data_ptr()
+            keep.append(hk)
+        return d, keep
+
+    def _launch_forward(self, batch, training, drop, y=None, loss_scale=0.0):
+        lib = _lib.load()
+        p = batch._priv
+        self._check_fit(p["n_cap"], False)
+        adj_c, _ = batch.adjacency()
+        ws = self._workspace(batch, training)
+        S = self._saved_struct(ws, p["node_cap"])
+        d, keep = drop
+        _lib.check(lib.igmc_forward(C.byref(self._cmodel), self.flat_params.data_ptr(), p["node_label"].data_ptr(),
+                                    p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
+                                    batch.num_graphs, p["n_cap"], C.byref(d), int(training), C.byref(S),
+                                    _lib.ptr(y), float(loss_scale), ws["dpred"].data_ptr() if y is not None else None,
+                                    ws["sqerr"].data_ptr() if y is not None else None, batch._err.data_ptr(),
+                                    _stream_ptr()), "igmc_forward")
+        return ws["pred"], dict(ws=ws, S=S, train=bool(training))
+
+    def _launch_backward(self, batch, drop, saved, dpred):
+        lib = _lib.load()
+        p = batch._priv
+        self._check_fit(p["n_cap"], True)
+        adj_c, _ = batch.adjacency()
+        ws = saved["ws"]
+        d, keep = drop
+        saved["dpred_used"] = dpred
+        _lib.check(lib.igmc_backward(C.byref(self._cmodel), self.flat_params.data_ptr(), p["node_label"].data_ptr(),
+                                     p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
+                                     batch.num_graphs, p["n_cap"], C.byref(d), C.byref(saved["S"]),
+                                     dpred.data_ptr(), ws["gpart"].data_ptr(), ws["dhid"].data_ptr(),
+                                     batch._err.data_ptr(), _stream_ptr()), "igmc_backward")
+
+    def _launch_grad_reduce(self, batch, saved, loss_scale, arr, with_loss=True):
+        lib = _lib.load()
+        ws = saved["ws"]
+        _lib.check(lib.igmc_grad_reduce(C.byref(self._cmodel), self.flat_params.data_ptr(), batch.num_graphs,
+                                        ws["gpart"].data_ptr(), ws["dhid"].data_ptr(), ws["feat"].data_ptr(),
+                                        ws["hid"].data_ptr(), saved["dpred_used"].data_ptr(),
+                                        ws["sqerr"].data_ptr() if with_loss else None, float(loss_scale),
+                                        float(arr), 1.0, self.flat_grad.data_ptr(),
+                                        ws["loss"].data_ptr() if with_loss else None, _stream_ptr()),
+                   "igmc_grad_reduce")
+
+    # ---- public API ------------------------------------------------------------------------------------------
+    def _as_batch(self, data):
+        if isinstance(data, Batch):
+            return data
+        if getattr(data, "batch", None) is None:
+            raise ValueError("IGMC.forward expects a collated Batch")
+        return Batch.from_arrays(data.x, data.edge_index, data.edge_type, data.batch, data.y,
+                                 getattr(data, "num_graphs", None), self.flat_params.device)
+
+    def forward(self, data, edge_keep=None, hidden_keep=None):
+        batch = self._as_batch(data)
+        drop = self.make_dropout(self.training, edge_keep, hidden_keep)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            self._step += 1
+            params = [p for (_, _, p) in self._named_order()]
+            return _IGMCFunction.apply(self, batch, self.training, drop, *params)
+        out, _ = self._launch_forward(batch, False if not self.training else True, drop)
+        return out.clone()
+
+    def fused_step(self, batch, ARR=0.0, global_num_graphs=None, edge_keep=None, hidden_keep=None,
+                   seed_dev=None):
+        """forward + MSE (+ARR) + backward + gradient assembly, no autograd, no host sync.
+
+        Equivalent to the body of the reference's ``train`` loop up to ``loss.backward()``
+        (train_eval.py:158-175).  ``flat_grad`` then holds d loss / d params where the MSE mean is taken
+        over ``global_num_graphs`` (defaults to this batch; under data parallelism pass B*world so that an
+        NCCL SUM of flat_grad is the gradient of the global-batch mean).  Returns the device scalar
+        ``sum_g (out_g-y_g)^2 / global_num_graphs + ARR*reg``.
+        """
+        self._step += 1
+        drop = self.make_dropout(True, edge_keep, hidden_keep, seed_dev=seed_dev)
+        G = batch.num_graphs if global_num_graphs is None else int(global_num_graphs)
+        out, saved = self._launch_forward(batch, True, drop, y=batch.y, loss_scale=1.0 / G)
+        self._launch_backward(batch, drop, saved, saved["ws"]["dpred"])
+        self._launch_grad_reduce(batch, saved, loss_scale=1.0 / G, arr=ARR, with_loss=True)
+        return saved["ws"]["loss"]
+
+    def __repr__(self):
+        return self.__class__.__name__
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """``torch.optim.Adam`` semantics (train_eval.py:54) as ONE kernel over the flat bucket.
+
+    ``state_dict()`` has the stock Adam structure (per-parameter ``step/exp_avg/exp_avg_sq`` that are
+    views of the flat moments), so optimizer checkpoints interchange with the reference's
+    (Main.py:45, train_eval.py:60-62)."""
+
+    def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
+        self.model = model
+        params = [p for (_, _, p) in model._named_order()]
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False))
+        dev = model.flat_params.device
+        n = model.flat_params.numel()
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        for (o, k, s), p in zip(model._layout, params):
+            self.state[p] = dict(step=self.step_count[0], exp_avg=self.exp_avg[o:o + k].view(s),
+                                 exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        params = [p for (_, _, p) in self.model._named_order()]
+        with torch.no_grad():
+            for (o, k, s), p in zip(self.model._layout, params):
+                st = self.state[p]
+                self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                self.step_count.fill_(int(st["step"]))
+                self.state[p] = dict(step=self.step_count[0], exp_avg=self.exp_avg[o:o + k].view(s),
+                                     exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
+
+    @torch.no_grad()
+    def step(self, grad_mul=1.0, lr_dev=None):
+        lib = _lib.load()
+        g = self.param_groups[0]
+        m = self.model
+        _lib.check(lib.igmc_adam_step(m.flat_params.data_ptr(), m.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
+                                      self.exp_avg_sq.data_ptr(), self.step_count.data_ptr(),
+                                      m.flat_params.numel(), float(g["lr"]), _lib.ptr(lr_dev),
+                                      float(g["betas"][0]),
+                                      float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
+                                      float(grad_mul), _stream_ptr()), "igmc_adam_step")
+
+    def zero_grad(self, set_to_none=False):
+        pass  # flat_grad is fully overwritten by every fused_step

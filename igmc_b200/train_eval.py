@@ -1,0 +1,303 @@
+"""Drop-in for the reference's ``train_eval.py`` (train loop / eval) on the fused kernels.
+
+``train_multiple_epochs`` / ``test_once`` / ``train`` / ``eval_loss`` / ``eval_rmse`` /
+``eval_rmse_ensemble`` keep the reference signatures (train_eval.py:23-36,114-119,149-245) and
+semantics (MSE mean + ARR regulariser, Adam, LR x factor every ``lr_decay_step_size`` epochs,
+``logger(eval_info, model, optimizer)`` once per epoch, ``continue_from`` checkpoints).
+
+What changed underneath:
+* no DataLoader workers: a step is  H2D(indices) -> extract -> adjacency -> fused forward+loss ->
+  backward -> gradient assembly (+ARR) -> [NCCL all-reduce] -> fused Adam, captured ONCE as a CUDA graph
+  per batch size and replayed; the host never synchronises inside an epoch;
+* data parallel: every rank holds the rating CSR, draws the same epoch permutation and takes its
+  slice of every global batch; the only collective is one all-reduce(SUM) of the flat gradient
+  (49 k floats) per step, plus one scalar all-reduce per epoch for the reported loss / RMSE.
+"""
+import math
+import os
+import time
+
+import numpy as np
+import torch
+
+from .models import FusedAdam, splitmix64
+from .util_functions import MyDynamicDataset  # noqa: F401  (re-export, Main.py star-imports)
+
+try:
+    import torch.distributed as dist
+except Exception:  # pragma: no cover
+    dist = None
+
+device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+
+
+def _dist_info():
+    if dist is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
+def shard_batches(perm, batch_size, rank, world):
+    """Split an epoch permutation into global batches of ``batch_size*world`` and return, per step,
+    (this rank's indices, global batch size).  The last global batch may be short (the reference's
+    DataLoader keeps the partial batch, drop_last=False); it is split as evenly as possible and a rank
+    may then receive an empty slice.  Pure host logic (covered by CPU tests)."""
+    n = len(perm)
+    gb = batch_size * world
+    out = []
+    for s in range(0, n, gb):
+        chunk = perm[s:s + gb]
+        g = len(chunk)
+        if g == gb:
+            mine = chunk[rank * batch_size:(rank + 1) * batch_size]
+        else:
+            base, extra = divmod(g, world)
+            lo = rank * base + min(rank, extra)
+            mine = chunk[lo:lo + base + (1 if rank < extra else 0)]
+        out.append((mine, g))
+    return out
+
+
+def _u64_as_i64(x):
+    return int(np.array([x & ((1 << 64) - 1)], dtype=np.uint64).view(np.int64)[0])
+
+
+class TrainEngine(object):
+    """One training step as a replayable CUDA graph (see module docstring)."""
+
+    RING = 16
+
+    def __init__(self, dataset, model, optimizer, batch_size, ARR=0.0, use_graph=True, sample_seed=0):
+        self.dataset, self.model, self.opt = dataset, model, optimizer
+        self.B, self.ARR = int(batch_size), float(ARR)
+        self.rank, self.world = _dist_info()
+        self.dev = model.flat_params.device
+        self.use_graph = bool(use_graph) and hasattr(dataset, "extractor") and not hasattr(dataset, "slices")
+        self.sample_seed = int(sample_seed)
+        self.graphs = {}
+        self.eager_done = set()
+        # [idx(B) | sample_seed | drop_seed | global batch size]  per step, pinned ring + one device copy
+        self.stepbuf_dev = torch.zeros(self.B + 3, dtype=torch.int64, device=self.dev)
+        self.ring = [torch.zeros(self.B + 3, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+        self.ring_ev = [None] * self.RING
+        self.ring_pos = 0
+        self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.dev)   # sum_steps loss*G (this rank)
+        self.last_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self.steps = 0
+        self.sync_lr()
+
+    def sync_lr(self):
+        self.lr_dev.fill_(float(self.opt.param_groups[0]["lr"]))
+
+    # ---- the launches of one step, reading everything from stepbuf_dev ----------------------------
+    def _launch(self, nb, G):
+        B = self.B
+        buf = self.stepbuf_dev
+        if nb > 0:
+            batch = self.dataset.extractor.extract(idx=buf[:nb], seed_dev=buf[B:B + 1], reuse=True)
+            loss = self.model.fused_step(batch, ARR=self.ARR / self.world, global_num_graphs=G,
+                                         seed_dev=buf[B + 1:B + 2])
+        else:  # this rank got no graph of a short tail batch: contribute zeros
+            self.model.flat_grad.zero_()
+            loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(self.model.flat_grad)
+        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev)
+        self.last_loss.copy_(loss)
+        self.loss_acc.add_(loss * float(G))
+
+    def _launch_static(self, idx, G):
+        batch = self.dataset.extract_batch(idx)
+        loss = self.model.fused_step(batch, ARR=self.ARR / self.world, global_num_graphs=G)
+        if self.world > 1:
+            dist.all_reduce(self.model.flat_grad)
+        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev)
+        self.last_loss.copy_(loss)
+        self.loss_acc.add_(loss * float(G))
+
+    def stage(self, idx, epoch, G):
+        """fill the next pinned slot with this step's inputs and enqueue its H2D copy."""
+        slot = self.ring_pos
+        self.ring_pos = (slot + 1) % self.RING
+        if self.ring_ev[slot] is not None:
+            self.ring_ev[slot].synchronize()   # the copy that last used this slot has finished
+        host = self.ring[slot]
+        nb = len(idx)
+        host[:nb] = torch.as_tensor(idx, dtype=torch.int64)
+        host[self.B] = _u64_as_i64(splitmix64(self.sample_seed + epoch))
+        host[self.B + 1] = _u64_as_i64(splitmix64(self.model.drop_seed + self.steps))
+        host[self.B + 2] = G
+        self.stepbuf_dev.copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.ring_ev[slot] = ev
+        return nb
+
+    def step(self, idx, epoch=0, G=None, staged=False):
+        """One optimisation step on this rank's ``idx`` (host int array).  H2D copy + graph replay."""
+        G = len(idx) * self.world if G is None else int(G)
+        self.steps += 1
+        if not hasattr(self.dataset, "extractor") or hasattr(self.dataset, "slices"):
+            return self._launch_static(np.asarray(idx), G)
+        nb = len(idx) if staged else self.stage(idx, epoch, G)
+        key = (nb, G)
+        if self.use_graph and key in self.graphs:
+            self.graphs[key].replay()
+        elif self.use_graph and key in self.eager_done and nb > 0:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch(nb, G)
+            self.graphs[key] = g
+            g.replay()
+        else:
+            self._launch(nb, G)
+            self.eager_done.add(key)
+
+    def check(self):
+        code = int(self.dataset.extractor.err.item()) if hasattr(self.dataset, "extractor") else 0
+        if code:
+            from . import _lib
+            raise RuntimeError("igmc_b200 kernel error %d: %s" % (code, _lib.ERR_NAMES.get(code, "?")))
+
+
+def train_multiple_epochs(train_dataset, test_dataset, model, epochs, batch_size, lr, lr_decay_factor,
+                          lr_decay_step_size, weight_decay, ARR=0, test_freq=1, logger=None,
+                          continue_from=None, res_dir=None, use_graph=True, seed=1):
+    """Reference train_eval.py:23-111.  Returns the last test RMSE."""
+    rank, world = _dist_info()
+    rmses = []
+    model.to(device).reset_parameters()
+    if world > 1:  # identical initial weights on every rank
+        dist.broadcast(model.flat_params, 0)
+    optimizer = FusedAdam(model, lr=lr, weight_decay=weight_decay)
+    start_epoch = 1
+    if continue_from is not None:
+        model.load_state_dict(torch.load(os.path.join(res_dir, "model_checkpoint{}.pth".format(continue_from))))
+        optimizer.load_state_dict(
+            torch.load(os.path.join(res_dir, "optimizer_checkpoint{}.pth".format(continue_from))))
+        start_epoch = continue_from + 1
+        epochs -= continue_from
+    engine = TrainEngine(train_dataset, model, optimizer, batch_size, ARR, use_graph, sample_seed=seed)
+    torch.cuda.synchronize()
+    t_start = time.perf_counter()
+    gen = torch.Generator().manual_seed(int(seed))
+    for epoch in range(start_epoch, epochs + start_epoch):
+        train_loss = train(model, optimizer, train_dataset, device, regression=True, ARR=ARR, epoch=epoch,
+                           engine=engine, generator=gen)
+        if epoch % test_freq == 0:
+            rmses.append(eval_rmse(model, test_dataset, device, batch_size=batch_size))
+        else:
+            rmses.append(np.nan)
+        eval_info = {"epoch": epoch, "train_loss": train_loss, "test_rmse": rmses[-1]}
+        if rank == 0:
+            print("Epoch {}, train loss {:.6f}, test rmse {:.6f}".format(*eval_info.values()))
+        if epoch % lr_decay_step_size == 0:
+            for param_group in optimizer.param_groups:
+                param_group["lr"] = lr_decay_factor * param_group["lr"]
+            engine.sync_lr()
+        if logger is not None and rank == 0:
+            logger(eval_info, model, optimizer)
+    torch.cuda.synchronize()
+    duration = time.perf_counter() - t_start
+    if rank == 0:
+        print("Final Test RMSE: {:.6f}, Duration: {:.6f}".format(rmses[-1], duration))
+    return rmses[-1]
+
+
+def train(model, optimizer, loader, device, regression=False, ARR=0, show_progress=False, epoch=None,
+          engine=None, generator=None, batch_size=50):
+    """One epoch (reference train_eval.py:149-179).  ``loader`` is the train dataset; mini-batches are
+    drawn from a seeded permutation identical on every rank.  Returns sum(loss*num_graphs)/len(dataset)
+    (global under data parallelism)."""
+    dataset = loader
+    model.train()
+    if engine is None:
+        engine = TrainEngine(dataset, model, optimizer, batch_size, ARR)
+    rank, world = _dist_info()
+    perm = torch.randperm(len(dataset), generator=generator).numpy()
+    engine.loss_acc.zero_()
+    for idx, G in shard_batches(perm, engine.B, rank, world):
+        engine.step(idx, epoch=0 if epoch is None else int(epoch), G=G)
+    acc = engine.loss_acc.clone()
+    if world > 1:
+        dist.all_reduce(acc)
+    engine.check()
+    return float(acc.item()) / len(dataset)
+
+
+def _eval_sqerr_sum(model, dataset, batch_size):
+    """sum of squared errors of this rank's share of ``dataset`` (device scalar), eval mode, no grad."""
+    rank, world = _dist_info()
+    dev = model.flat_params.device
+    acc = torch.zeros(1, dtype=torch.float32, device=dev)
+    order = np.arange(len(dataset), dtype=np.int64)
+    drop = model.make_dropout(False)
+    for idx, _ in shard_batches(order, batch_size, rank, world):
+        if len(idx) == 0:
+            continue
+        batch = dataset.extract_batch(idx)
+        _, saved = model._launch_forward(batch, False, drop, y=batch.y, loss_scale=0.0)
+        acc += saved["ws"]["sqerr"].sum()
+    if world > 1:
+        dist.all_reduce(acc)
+    return acc
+
+
+def eval_loss(model, loader, device, regression=False, show_progress=False, batch_size=50):
+    """Reference train_eval.py:182-199: mean squared error over the dataset (sum reduction / N)."""
+    model.eval()
+    with torch.no_grad():
+        s = _eval_sqerr_sum(model, loader, batch_size)
+    return float(s.item()) / len(loader)
+
+
+def eval_rmse(model, loader, device, show_progress=False, batch_size=50):
+    return math.sqrt(eval_loss(model, loader, device, True, show_progress, batch_size))
+
+
+def eval_loss_ensemble(model, checkpoints, loader, device, regression=False, show_progress=False, batch_size=50):
+    """Reference train_eval.py:208-238: average the predictions of several checkpoints, then MSE."""
+    dataset = loader
+    outs, ys = [], None
+    for i, checkpoint in enumerate(checkpoints):
+        model.load_state_dict(torch.load(checkpoint))
+        model.eval()
+        o, y = [], []
+        drop = model.make_dropout(False)
+        with torch.no_grad():
+            for s in range(0, len(dataset), batch_size):
+                batch = dataset.extract_batch(np.arange(s, min(s + batch_size, len(dataset)), dtype=np.int64))
+                pred, _ = model._launch_forward(batch, False, drop)
+                o.append(pred.clone())
+                if i == 0:
+                    y.append(batch.y.clone())
+        outs.append(torch.cat(o).view(-1, 1))
+        if i == 0:
+            ys = torch.cat(y)
+    mean = torch.cat(outs, 1).mean(1)
+    return float(((mean - ys) ** 2).sum().item()) / len(dataset)
+
+
+def eval_rmse_ensemble(model, checkpoints, loader, device, show_progress=False, batch_size=50):
+    return math.sqrt(eval_loss_ensemble(model, checkpoints, loader, device, True, show_progress, batch_size))
+
+
+def test_once(test_dataset, model, batch_size, logger=None, ensemble=False, checkpoints=None):
+    """Reference train_eval.py:114-139."""
+    model.to(device)
+    t_start = time.perf_counter()
+    if ensemble and checkpoints:
+        rmse = eval_rmse_ensemble(model, checkpoints, test_dataset, device, batch_size=batch_size)
+    else:
+        rmse = eval_rmse(model, test_dataset, device, batch_size=batch_size)
+    duration = time.perf_counter() - t_start
+    print("Test Once RMSE: {:.6f}, Duration: {:.6f}".format(rmse, duration))
+    eval_info = {"epoch": "test_once" if not ensemble else "ensemble", "train_loss": 0, "test_rmse": rmse}
+    if logger is not None:
+        logger(eval_info, None, None)
+    return rmse
+
+
+def visualize(*args, **kwargs):
+    raise NotImplementedError("visualisation (train_eval.py:248-322) is reporting code outside the hot path")

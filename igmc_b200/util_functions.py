@@ -1,0 +1,488 @@
+"""Drop-in for the hot-path half of the reference's ``util_functions.py``.
+
+Same public names and signatures as the reference (``MyDynamicDataset`` util_functions.py:113-145,
+``MyDataset`` :69-110, ``SparseRowIndexer``/``SparseColIndexer`` :20-66 replaced by ``RatingGraph``),
+but ``get``/batching run as CUDA kernels over a device-resident CSR/CSC through the C-ABI in
+include/igmc_b200.h.  The ``Data``/``Batch`` objects expose the PyG attribute surface the reference's
+model and train loop touch (``x, edge_index, edge_type, y, batch, num_graphs, to()``).
+
+No CPU fallback: constructing a dataset or extracting without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+
+__all__ = ["RatingGraph", "Data", "Batch", "SubgraphExtractor", "MyDynamicDataset", "MyDataset"]
+
+
+def _require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise RuntimeError("igmc_b200 needs a CUDA device (B200); there is no CPU path")
+    return torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+
+def _stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class RatingGraph(object):
+    """Flat device CSR + CSC of ``adj_train`` (scipy CSR, stored value = rating label + 1,
+    preprocessing.py:190-197).  Replaces SparseRowIndexer/SparseColIndexer (util_functions.py:20-66)."""
+
+    def __init__(self, A, device=None):
+        import scipy.sparse as ssp
+        A = ssp.csr_matrix(A)
+        A.sum_duplicates()
+        A.sort_indices()
+        self.shape = A.shape
+        self.nnz = int(A.nnz)
+        self.num_users, self.num_items = int(A.shape[0]), int(A.shape[1])
+        lab = np.rint(A.data).astype(np.int64) - 1
+        if self.nnz and (lab.min() < 0 or lab.max() > 255):
+            raise ValueError("rating labels must lie in 0..255")
+        Cc = A.tocsc()
+        Cc.sort_indices()
+        self.max_row_deg = int(np.diff(A.indptr).max()) if self.nnz else 0
+        self.max_col_deg = int(np.diff(Cc.indptr).max()) if self.nnz else 0
+        self.host = dict(row_ptr=A.indptr.astype(np.int32), col_idx=A.indices.astype(np.int32),
+                         rating=lab.astype(np.uint8), col_ptr=Cc.indptr.astype(np.int32),
+                         row_idx=Cc.indices.astype(np.int32))
+        self.device = None
+        self.dev = {}
+        if device is not None or torch.cuda.is_available():
+            self.to(_require_cuda(device))
+
+    def to(self, device):
+        self.device = torch.device(device)
+        self.dev = {k: torch.from_numpy(v).to(self.device) for k, v in self.host.items()}
+        # a zero-length index array still needs a valid pointer
+        for k, v in self.dev.items():
+            if v.numel() == 0:
+                self.dev[k] = torch.zeros(1, dtype=v.dtype, device=self.device)
+        self._c = _lib.CSR(self.dev["row_ptr"].data_ptr(), self.dev["col_idx"].data_ptr(),
+                           self.dev["rating"].data_ptr(), self.dev["col_ptr"].data_ptr(),
+                           self.dev["row_idx"].data_ptr(), self.num_users, self.num_items)
+        return self
+
+    def node_cap(self, max_nodes_per_hop):
+        """capacity of one side's node list: target + min(mnph, largest possible fringe)."""
+        d = max(self.max_row_deg, self.max_col_deg)
+        if max_nodes_per_hop is not None:
+            d = min(d, int(max_nodes_per_hop))
+        return 1 + d
+
+
+class Data(object):
+    """Minimal stand-in for ``torch_geometric.data.Data`` (reference util_functions.py:13,287)."""
+
+    def __init__(self, x=None, edge_index=None, edge_type=None, y=None, **kw):
+        self.x, self.edge_index, self.edge_type, self.y = x, edge_index, edge_type, y
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    @property
+    def num_nodes(self):
+        return int(self.x.shape[0])
+
+    @property
+    def num_features(self):
+        return int(self.x.shape[1])
+
+    def keys(self):
+        return [k for k, v in self.__dict__.items() if not k.startswith("_") and torch.is_tensor(v)]
+
+    def to(self, device):
+        for k in self.keys():
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class Batch(Data):
+    """A collated mini-batch (PyG ``Batch.from_data_list`` semantics) plus the private
+    device structures the fused kernels consume (graph offsets, labels, message-passing adjacency).
+
+    Batches produced by ``SubgraphExtractor`` live in capacity-sized buffers; the public tensors
+    (``x``, ``edge_index`` ...) are views cut to the true sizes, which costs one host sync the first
+    time one of them is touched (the training loop never touches them).
+    """
+
+    def __init__(self, num_graphs, device, **kw):
+        super().__init__(**kw)
+        self.num_graphs = int(num_graphs)
+        self.device = device
+        self.batch = None
+        self._priv = {}      # node_label, node_ptr, edge_ptr, node_cap, edge_cap, n_cap, symmetric ...
+        self._adj = None
+        self._lazy = None    # capacity buffers of an extracted batch
+        self._err = None
+
+    # ---- lazily cut public views of an extracted batch -------------------------------------------
+    def _materialize(self):
+        if self._lazy is None:
+            return
+        lz, self._lazy = self._lazy, None
+        counts = lz["counts"].cpu()
+        self.check()
+        N, E = int(counts[0]), int(counts[1])
+        self.__dict__["x"] = lz["x"][:N]
+        self.__dict__["edge_index"] = lz["edge_index"][:, :E]
+        self.__dict__["edge_type"] = lz["edge_type"][:E]
+        self.__dict__["batch"] = lz["batch"][:N]
+        self.__dict__["node_label"] = lz["node_label"][:N]
+        self.__dict__["node_gid"] = lz["node_gid"][:N]
+
+    def __getattribute__(self, name):
+        if name in ("x", "edge_index", "edge_type", "batch", "node_label", "node_gid"):
+            d = object.__getattribute__(self, "__dict__")
+            if d.get("_lazy") is not None:
+                object.__getattribute__(self, "_materialize")()
+        return object.__getattribute__(self, name)
+
+    def check(self):
+        """raise if a kernel flagged a data-dependent error (host sync)."""
+        if self._err is not None:
+            code = int(self._err.item())
+            if code != 0:
+                raise RuntimeError("igmc_b200 kernel error %d: %s" % (code, _lib.ERR_NAMES.get(code, "?")))
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("igmc_b200 batches live on the GPU")
+        return self
+
+    # ---- foreign batches (PyG-collated tensors from anywhere) ------------------------------------
+    @staticmethod
+    def from_arrays(x, edge_index, edge_type, batch, y, num_graphs=None, device=None):
+        """Wrap already-collated arrays (e.g. the oracle's) and derive graph offsets on the GPU."""
+        device = _require_cuda(device)
+        lib = _lib.load()
+        x = torch.as_tensor(x, dtype=torch.float32).to(device).contiguous()
+        edge_index = torch.as_tensor(edge_index, dtype=torch.int64).to(device).contiguous()
+        edge_type = torch.as_tensor(edge_type, dtype=torch.int64).to(device).contiguous()
+        batch = torch.as_tensor(batch, dtype=torch.int64).to(device).contiguous()
+        y = torch.as_tensor(y, dtype=torch.float32).to(device).contiguous().view(-1)
+        B = int(num_graphs) if num_graphs is not None else int(y.numel())
+        N, E = int(x.shape[0]), int(edge_index.shape[1])
+        b = Batch(B, device, x=x, edge_index=edge_index, edge_type=edge_type, y=y)
+        b.batch = batch
+        lab = torch.argmax(x, 1).to(torch.uint8)
+        node_ptr = torch.zeros(B + 1, dtype=torch.int32, device=device)
+        edge_ptr = torch.zeros(B + 1, dtype=torch.int32, device=device)
+        err = torch.zeros(1, dtype=torch.int32, device=device)
+        src = edge_index[0] if E else torch.zeros(1, dtype=torch.int64, device=device)
+        _lib.check(lib.igmc_batch_ptrs(batch.data_ptr() if N else None, src.data_ptr(), N, E, B,
+                                       node_ptr.data_ptr(), edge_ptr.data_ptr(), err.data_ptr(), _stream_ptr()),
+                   "igmc_batch_ptrs")
+        n_max = int((node_ptr[1:] - node_ptr[:-1]).max().item()) if B else 0
+        b._err = err
+        b._priv = dict(node_label=lab, node_ptr=node_ptr, edge_ptr=edge_ptr, node_cap=max(N, 1),
+                       edge_cap=max(E, 1), n_cap=max(n_max, 2), symmetric=0, edge_row_stride=E)
+        b.__dict__["node_label"] = lab
+        b.check()
+        return b
+
+    @staticmethod
+    def from_data_list(data_list, device=None):
+        """PyG collate of ``Data`` objects (offset-concat edge_index, concat the rest)."""
+        xs, eis, ets, ys, bs = [], [], [], [], []
+        off = 0
+        for gi, d in enumerate(data_list):
+            n = int(d.x.shape[0])
+            xs.append(d.x)
+            eis.append(d.edge_index + off)
+            ets.append(d.edge_type)
+            ys.append(d.y.view(-1))
+            bs.append(torch.full((n,), gi, dtype=torch.int64, device=d.x.device))
+            off += n
+        return Batch.from_arrays(torch.cat(xs, 0), torch.cat(eis, 1), torch.cat(ets), torch.cat(bs),
+                                 torch.cat(ys), len(data_list), device)
+
+    # ---- message-passing adjacency ------------------------------------------------------------------
+    def adjacency(self):
+        """(lazily) build the (type, neighbour)-sorted in/out edge lists with igmc_batch_prepare."""
+        if self._adj is not None:
+            return self._adj
+        lib = _lib.load()
+        p = self._priv
+        dev = self.device
+        ecap, ncap = p["edge_cap"], p["node_cap"]
+        cache = getattr(self, "_adj_cache", None)
+        if self._lazy is not None:
+            ei, et = self._lazy["edge_index"], self._lazy["edge_type"]
+        else:
+            ei, et = self.edge_index, self.edge_type
+        sym = int(p["symmetric"])
+        if cache is not None and "t" in cache:
+            t = cache["t"]
+        else:
+            t = dict(in_ptr=torch.zeros(ncap + 1, dtype=torch.int32, device=dev),
+                     in_adj=torch.empty(ecap, dtype=torch.int32, device=dev),
+                     in_eid=torch.empty(ecap, dtype=torch.int32, device=dev),
+                     tmp=torch.empty(ecap, dtype=torch.int64, device=dev))
+            if cache is not None:
+                cache["t"] = t
+        if not sym and "out_ptr" not in t:
+            t.update(out_ptr=torch.zeros(ncap + 1, dtype=torch.int32, device=dev),
+                     out_adj=torch.empty(ecap, dtype=torch.int32, device=dev),
+                     out_eid=torch.empty(ecap, dtype=torch.int32, device=dev))
+        c = _lib.Adj(t["in_ptr"].data_ptr(), t["in_adj"].data_ptr(), t["in_eid"].data_ptr(),
+                     _lib.ptr(t.get("out_ptr")), _lib.ptr(t.get("out_adj")), _lib.ptr(t.get("out_eid")),
+                     t["tmp"].data_ptr(), sym)
+        _lib.check(lib.igmc_batch_prepare(ei.data_ptr(), p["edge_row_stride"], et.data_ptr(),
+                                          p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), self.num_graphs,
+                                          p["n_cap"], C.byref(c), self._err.data_ptr(), _stream_ptr()),
+                   "igmc_batch_prepare")
+        self._adj = (c, t)
+        return self._adj
+
+
+class SubgraphExtractor(object):
+    """Owns the workspace for batches of up to ``max_batch`` pairs and runs igmc_extract_batch.
+
+    One instance per dataset; ``extract(idx)`` is what the reference's DataLoader workers do with
+    ``MyDynamicDataset.get`` + collate (train_eval.py:40-45), as two kernel launches.
+    """
+
+    def __init__(self, graph, links_u, links_v, labels, class_values, h=1, sample_ratio=1.0,
+                 max_nodes_per_hop=None, max_batch=64, seed=0, emit_x=True):
+        if int(h) != 1:
+            raise NotImplementedError("igmc_b200 extraction implements hop=1 (the reference default, Main.py:88)")
+        self.lib = _lib.load()
+        self.graph = graph
+        self.device = graph.device if graph.device is not None else _require_cuda()
+        if graph.device is None:
+            graph.to(self.device)
+        dev = self.device
+        self.h = 1
+        self.sample_ratio = float(sample_ratio)
+        self.mnph = -1 if max_nodes_per_hop is None else int(max_nodes_per_hop)
+        self.seed = int(seed)
+        self.num_links = len(links_u)
+        self.links_u = torch.as_tensor(np.asarray(links_u), dtype=torch.int32).to(dev)
+        self.links_v = torch.as_tensor(np.asarray(links_v), dtype=torch.int32).to(dev)
+        self.links_label = torch.as_tensor(np.asarray(labels), dtype=torch.int32).to(dev)
+        self.class_values = torch.as_tensor(np.asarray(class_values, dtype=np.float32)).to(dev)
+        self.cap = graph.node_cap(max_nodes_per_hop)
+        self.feat_dim = 2 * self.h + 2
+        self.emit_x = emit_x
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)   # shared device error word
+        self._out_cache = {}
+        self.max_batch = 0
+        self._reserve(max_batch)
+
+    def _reserve(self, B):
+        if B <= self.max_batch:
+            return
+        dev, cap, g = self.device, self.cap, self.graph
+        self.max_batch = B
+        per_graph_edges = 2 * min(cap * min(cap, max(g.max_row_deg, 1)), max(g.nnz, 1))
+        self.node_cap = B * 2 * cap
+        self.edge_cap = max(B * per_graph_edges, 2)
+        i32 = dict(dtype=torch.int32, device=dev)
+        self.ws = dict(nodes_u=torch.empty(B * cap, **i32), nodes_v=torch.empty(B * cap, **i32),
+                       n_u=torch.zeros(B, **i32), n_v=torch.zeros(B, **i32),
+                       row_cnt=torch.empty(B * cap, **i32), m_cnt=torch.zeros(B, **i32))
+        self._ws_c = _lib.ExtractWS(*[self.ws[k].data_ptr() for k in ("nodes_u", "nodes_v", "n_u", "n_v",
+                                                                          "row_cnt", "m_cnt")])
+
+    def _alloc_out(self, B, reuse=False):
+        if reuse and B in self._out_cache:
+            return self._out_cache[B]
+        dev = self.device
+        ncap, ecap = B * 2 * self.cap, max(B * (self.edge_cap // self.max_batch), 2)
+        o = dict(x=torch.empty(ncap, self.feat_dim, dtype=torch.float32, device=dev) if self.emit_x else None,
+                 node_label=torch.empty(ncap, dtype=torch.uint8, device=dev),
+                 batch=torch.empty(ncap, dtype=torch.int64, device=dev),
+                 node_gid=torch.empty(ncap, dtype=torch.int32, device=dev),
+                 edge_index=torch.empty(2, ecap, dtype=torch.int64, device=dev),
+                 edge_type=torch.empty(ecap, dtype=torch.int64, device=dev),
+                 y=torch.empty(B, dtype=torch.float32, device=dev),
+                 node_ptr=torch.zeros(B + 1, dtype=torch.int32, device=dev),
+                 edge_ptr=torch.zeros(B + 1, dtype=torch.int32, device=dev),
+                 graph_nu=torch.zeros(B, dtype=torch.int32, device=dev),
+                 counts=torch.zeros(2, dtype=torch.int32, device=dev),
+                 err=self.err)
+        o["_caps"] = (ncap, ecap)
+        if reuse:
+            self._out_cache[B] = o
+        return o
+
+    def extract(self, idx=None, pairs=None, pair_ids=None, out=None, inject=None, seed=None, seed_dev=None,
+                reuse=False):
+        """Extract + collate.  ``idx``: int64 tensor/array of dataset indices (device tensor preferred),
+        or ``pairs=(u, v, label)`` explicit arrays.  ``inject=(nodes_u, nodes_v, n_u, n_v)`` supplies the
+        per-graph node lists ([B,cap] int32, target first) instead of sampling (parity tests).
+        ``reuse=True`` writes into one cached buffer set per batch size (training loop / CUDA graphs:
+        the previous batch of that size is overwritten).  ``seed_dev``: device uint64 overriding the seed.
+        Returns a ``Batch`` whose public tensors are materialised lazily."""
+        dev = self.device
+        keep = []
+        if pairs is not None:
+            pu = torch.as_tensor(np.asarray(pairs[0]), dtype=torch.int32).to(dev)
+            pv = torch.as_tensor(np.asarray(pairs[1]), dtype=torch.int32).to(dev)
+            pl = torch.as_tensor(np.asarray(pairs[2]), dtype=torch.int32).to(dev)
+            B = int(pu.numel())
+            pid = None
+            if pair_ids is not None:
+                pid = torch.as_tensor(np.asarray(pair_ids), dtype=torch.int64).to(dev)
+            P = _lib.Pairs(None, pu.data_ptr(), pv.data_ptr(), pl.data_ptr(), _lib.ptr(pid))
+            keep += [pu, pv, pl, pid]
+        else:
+            if not torch.is_tensor(idx):
+                idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+            idx = idx.to(device=dev, dtype=torch.int64)
+            B = int(idx.numel())
+            P = _lib.Pairs(idx.data_ptr(), self.links_u.data_ptr(), self.links_v.data_ptr(),
+                           self.links_label.data_ptr(), None)
+            keep += [idx]
+        self._reserve(B)
+        o = out if out is not None else self._alloc_out(B, reuse)
+        ncap, ecap = o["_caps"]
+        O = _lib.BatchOut(ncap, ecap, self.feat_dim, _lib.ptr(o["x"]), o["node_label"].data_ptr(),
+                          o["batch"].data_ptr(), o["node_gid"].data_ptr(), o["edge_index"].data_ptr(),
+                          o["edge_type"].data_ptr(), o["y"].data_ptr(), o["node_ptr"].data_ptr(),
+                          o["edge_ptr"].data_ptr(), o["graph_nu"].data_ptr(), o["counts"].data_ptr())
+        inj = [None] * 4
+        if inject is not None:
+            inj_t = [torch.as_tensor(np.asarray(a), dtype=torch.int32).to(dev).contiguous() for a in inject]
+            assert inj_t[0].shape == (B, self.cap) and inj_t[1].shape == (B, self.cap)
+            inj = [t.data_ptr() for t in inj_t]
+            keep += inj_t
+        _lib.check(self.lib.igmc_extract_batch(C.byref(self.graph._c), C.byref(P), B, self.mnph,
+                                               self.sample_ratio, self.seed if seed is None else int(seed),
+                                               _lib.ptr(seed_dev), self.cap, inj[0], inj[1], inj[2], inj[3],
+                                               C.byref(self._ws_c),
+                                               self.class_values.data_ptr(), C.byref(O), o["err"].data_ptr(),
+                                               _stream_ptr()), "igmc_extract_batch")
+        b = Batch(B, dev, y=o["y"])
+        b._lazy = o
+        b._err = o["err"]
+        b._keep = keep
+        b._priv = dict(node_label=o["node_label"], node_ptr=o["node_ptr"], edge_ptr=o["edge_ptr"],
+                       node_cap=ncap, edge_cap=ecap, n_cap=2 * self.cap, symmetric=1, edge_row_stride=ecap,
+                       graph_nu=o["graph_nu"], counts=o["counts"])
+        if reuse:
+            b._adj_cache = o.setdefault("_adj", {})
+        return b
+
+    def node_lists(self, B):
+        """(nodes_u [B,cap], nodes_v [B,cap], n_u [B], n_v [B]) of the last extract (host copies)."""
+        cap = self.cap
+        return (self.ws["nodes_u"][:B * cap].view(B, cap).cpu().numpy(),
+                self.ws["nodes_v"][:B * cap].view(B, cap).cpu().numpy(),
+                self.ws["n_u"][:B].cpu().numpy(), self.ws["n_v"][:B].cpu().numpy())
+
+
+class MyDynamicDataset(object):
+    """Reference signature (util_functions.py:114-115).  ``get(idx)`` extracts one enclosing subgraph on
+    the GPU; the train loop uses ``extract_batch(indices)`` to get a whole collated mini-batch."""
+
+    def __init__(self, root, A, links, labels, h, sample_ratio, max_nodes_per_hop, u_features, v_features,
+                 class_values, max_num=None, seed=0):
+        if u_features is not None or v_features is not None:
+            raise NotImplementedError("side features (--use-features) are outside the hot path (SURVEY.md §2)")
+        self.root = root
+        self.links = (np.asarray(links[0]), np.asarray(links[1]))
+        self.labels = np.asarray(labels)
+        self.h, self.sample_ratio, self.max_nodes_per_hop = int(h), sample_ratio, max_nodes_per_hop
+        self.class_values = np.asarray(class_values)
+        if max_num is not None:  # reference :127-133
+            np.random.seed(123)
+            perm = np.random.permutation(len(self.links[0]))[:max_num]
+            self.links = (self.links[0][perm], self.links[1][perm])
+            self.labels = self.labels[perm]
+        self.graph = A if isinstance(A, RatingGraph) else RatingGraph(A)
+        self.extractor = SubgraphExtractor(self.graph, self.links[0], self.links[1], self.labels,
+                                           self.class_values, self.h, sample_ratio, max_nodes_per_hop,
+                                           seed=seed)
+
+    def __len__(self):
+        return len(self.links[0])
+
+    @property
+    def num_features(self):
+        return 2 * self.h + 2
+
+    def extract_batch(self, indices):
+        return self.extractor.extract(idx=indices)
+
+    def get(self, idx):
+        b = self.extractor.extract(idx=np.asarray([idx], dtype=np.int64))
+        return Data(b.x, b.edge_index, edge_type=b.edge_type, y=b.y)
+
+    def __getitem__(self, idx):
+        return self.get(int(idx))
+
+
+class MyDataset(MyDynamicDataset):
+    """Static variant (reference util_functions.py:69-110): every subgraph is extracted ONCE (in large
+    GPU batches instead of an mp.Pool) and kept device-resident in the reference's ``(data, slices)``
+    form — per-graph LOCAL node ids, boundaries in ``slices``; mini-batches are
+    assembled from the slices."""
+
+    def __init__(self, root, A, links, labels, h, sample_ratio, max_nodes_per_hop, u_features, v_features,
+                 class_values, max_num=None, parallel=True, seed=0, chunk=512):
+        super().__init__(root, A, links, labels, h, sample_ratio, max_nodes_per_hop, u_features, v_features,
+                         class_values, max_num, seed)
+        self.parallel = parallel
+        self.process(chunk)
+
+    @property
+    def processed_file_names(self):
+        return ["data.pt"]
+
+    def process(self, chunk=512):
+        xs, eis, ets, ys = [], [], [], []
+        nptr, eptr = [torch.zeros(1, dtype=torch.int64)], [torch.zeros(1, dtype=torch.int64)]
+        n_tot = e_tot = 0
+        for s in range(0, len(self), chunk):
+            b = self.extractor.extract(idx=np.arange(s, min(s + chunk, len(self)), dtype=np.int64))
+            np_, ep_ = b._priv["node_ptr"].to(torch.int64), b._priv["edge_ptr"].to(torch.int64)
+            xs.append(b.x.clone())
+            # back to per-graph local ids (what InMemoryDataset.collate stores)
+            ei = b.edge_index.clone()
+            gid_of_edge = b.batch[ei[0]] if ei.shape[1] else torch.zeros(0, dtype=torch.int64, device=ei.device)
+            ei -= np_[gid_of_edge].unsqueeze(0)
+            eis.append(ei)
+            ets.append(b.edge_type.clone())
+            ys.append(b.y.clone())
+            nptr.append((np_[1:] + n_tot).cpu())
+            eptr.append((ep_[1:] + e_tot).cpu())
+            n_tot += int(np_[-1])
+            e_tot += int(ep_[-1])
+        dev = self.extractor.device
+        self.data = Data(torch.cat(xs, 0), torch.cat(eis, 1), edge_type=torch.cat(ets), y=torch.cat(ys))
+        self.slices = dict(x=torch.cat(nptr).to(dev), edge_index=torch.cat(eptr).to(dev))
+        self.slices["edge_type"] = self.slices["edge_index"]
+        self.slices["y"] = torch.arange(len(self) + 1, device=dev)
+
+    def get(self, idx):
+        n0, n1 = int(self.slices["x"][idx]), int(self.slices["x"][idx + 1])
+        e0, e1 = int(self.slices["edge_index"][idx]), int(self.slices["edge_index"][idx + 1])
+        return Data(self.data.x[n0:n1], self.data.edge_index[:, e0:e1], edge_type=self.data.edge_type[e0:e1],
+                    y=self.data.y[idx:idx + 1])
+
+    def extract_batch(self, indices):
+        """batch assembly from the stored slices (device-side gather + offset add)."""
+        dev = self.extractor.device
+        idx = torch.as_tensor(np.asarray(indices) if not torch.is_tensor(indices) else indices).to(dev).long()
+        sx, se = self.slices["x"], self.slices["edge_index"]
+        n0, n1, e0, e1 = sx[idx], sx[idx + 1], se[idx], se[idx + 1]
+        ncnt, ecnt = n1 - n0, e1 - e0
+        nptr = torch.zeros(len(idx) + 1, dtype=torch.int64, device=dev)
+        eptr = torch.zeros(len(idx) + 1, dtype=torch.int64, device=dev)
+        nptr[1:] = torch.cumsum(ncnt, 0)
+        eptr[1:] = torch.cumsum(ecnt, 0)
+        N, E = int(nptr[-1]), int(eptr[-1])
+        gb = torch.repeat_interleave(torch.arange(len(idx), device=dev), ncnt, output_size=N)
+        node_src = torch.arange(N, device=dev) - nptr[gb] + n0[gb]
+        ge = torch.repeat_interleave(torch.arange(len(idx), device=dev), ecnt, output_size=E)
+        edge_src = torch.arange(E, device=dev) - eptr[ge] + e0[ge]
+        ei = self.data.edge_index[:, edge_src] + nptr[ge].unsqueeze(0)
+        return Batch.from_arrays(self.data.x[node_src], ei, self.data.edge_type[edge_src], gb,
+                                 self.data.y[idx], len(idx), dev)

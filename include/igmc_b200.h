@@ -1,0 +1,195 @@
+/* igmc_b200 — C-ABI of the B200-native IGMC hot path (libigmc_b200.so).
+ *
+ * The reference (muhanzhang/IGMC) has no FFI: its boundary is the Python API that Main.py
+ * star-imports (Main.py:11-15).  The host side in igmc_b200/{util_functions,models,train_eval}.py
+ * mirrors that API and calls ONLY the entry points below (via ctypes; INTEGRATION.md shows the
+ * binding).  Every pointer is a DEVICE pointer owned by the caller (torch tensors), every call is
+ * asynchronous on `stream` (a cudaStream_t passed as void*), returns 0 on success, a negative
+ * value for argument errors, or 1000+cudaError for launch failures.  Data-dependent failures
+ * (capacity overflow, malformed batch) are reported through the device-side error word `err`
+ * (see IGMC_ERR_* in csrc/common.cuh) which the host checks at its next synchronisation point.
+ *
+ * Each entry point cites the reference code it replaces.
+ */
+#ifndef IGMC_B200_H
+#define IGMC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IGMC_MAX_LAYERS 8
+#define IGMC_HIDDEN 32      /* latent_dim entries are hard-coded to 32 in Main.py:391 */
+#define IGMC_MAX_BASES 4    /* num_bases=4 in Main.py:394 (IGMC's default is 2) */
+#define IGMC_LIN1_OUT 128   /* models.py:185 */
+
+/* Device-resident rating matrix.  Replaces SparseRowIndexer / SparseColIndexer
+ * (util_functions.py:20-66): flat CSR + CSC, int32 indices, uint8 rating label (= stored value-1). */
+typedef struct {
+  const int32_t* row_ptr;   /* [num_users+1] */
+  const int32_t* col_idx;   /* [nnz] ascending within a row */
+  const uint8_t* rating;    /* [nnz] rating label 0..R-1 */
+  const int32_t* col_ptr;   /* [num_items+1] */
+  const int32_t* row_idx;   /* [nnz] ascending within a column */
+  int32_t num_users, num_items;
+} igmc_csr_t;
+
+/* Where graph g of a batch takes its (user, item, label) from.  Replaces the `links`/`labels`
+ * members of MyDynamicDataset (util_functions.py:119-133) + DataLoader index sampling. */
+typedef struct {
+  const int64_t* idx;          /* [B] indices into links_*; NULL -> graph g uses entry g */
+  const int32_t* links_u;      /* dataset-resident pairs */
+  const int32_t* links_v;
+  const int32_t* links_label;  /* rating label of the pair (y = class_values[label]); may be NULL */
+  const int64_t* pair_id;      /* [B] sampling-stream id per graph; NULL -> idx[g] (or g) */
+} igmc_pairs_t;
+
+/* Scratch of igmc_extract_batch (per-graph node lists and counts). */
+typedef struct {
+  int32_t* nodes_u;  /* [B*cap] global user ids, target first then ascending */
+  int32_t* nodes_v;  /* [B*cap] global item ids */
+  int32_t* n_u;      /* [B] */
+  int32_t* n_v;      /* [B] */
+  int32_t* row_cnt;  /* [B*cap] */
+  int32_t* m_cnt;    /* [B] undirected edges per graph */
+} igmc_extract_ws_t;
+
+/* The collated batch in the reference's layout (what construct_pyg_graph + Batch.from_data_list
+ * produce, util_functions.py:280-297) plus graph offsets.  Buffers are capacity-sized; the true
+ * sizes are counts[0]=N, counts[1]=E (directed). */
+typedef struct {
+  int32_t node_cap, edge_cap, feat_dim;
+  float* x;             /* [node_cap*feat_dim] one-hot of node_label, may be NULL */
+  uint8_t* node_label;  /* [node_cap] 0 target user, 1 target item, 2 user, 3 item (h=1) */
+  int64_t* batch;       /* [node_cap] graph id per node */
+  int32_t* node_gid;    /* [node_cap] global user/item id per node */
+  int64_t* edge_index;  /* [2*edge_cap]: row 0 at 0, row 1 at edge_cap */
+  int64_t* edge_type;   /* [edge_cap] */
+  float* y;             /* [B] */
+  int32_t* node_ptr;    /* [B+1] */
+  int32_t* edge_ptr;    /* [B+1] directed-edge offsets */
+  int32_t* graph_nu;    /* [B] number of user nodes of each graph */
+  int32_t* counts;      /* [2] N, E */
+} igmc_batch_out_t;
+
+/* Enclosing-subgraph extraction + labelling + graph construction + collate for B pairs (h = 1).
+ * Replaces MyDynamicDataset.get -> subgraph_extraction_labeling -> construct_pyg_graph
+ * (util_functions.py:138-145, 208-297) and PyG's Batch.from_data_list.  `max_nodes_per_hop` < 0
+ * means None.  `inj_*` (all or none NULL) inject per-graph node lists [B*cap] (test hook: the
+ * reference's own random.sample draw).  `seed_dev` (optional, device) overrides `seed` so that a
+ * captured CUDA graph can be replayed with a fresh sampling stream every step. */
+int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int max_nodes_per_hop,
+                       double sample_ratio, uint64_t seed, const uint64_t* seed_dev, int cap,
+                       const int32_t* inj_nodes_u, const int32_t* inj_nodes_v,
+                       const int32_t* inj_n_u, const int32_t* inj_n_v,
+                       const igmc_extract_ws_t* W, const float* class_values,
+                       const igmc_batch_out_t* O, int* err, void* stream);
+
+/* Graph offsets of a foreign (PyG-collated) batch: node_ptr from `batch`, edge_ptr from the graph
+ * of each edge's source.  Replaces what Batch.from_data_list knows implicitly. */
+int igmc_batch_ptrs(const int64_t* batch, const int64_t* edge_src, int N, int E, int B,
+                    int32_t* node_ptr, int32_t* edge_ptr, int* err, void* stream);
+
+/* Message-passing adjacency of a batch: per node the incoming (and outgoing) edge lists sorted by
+ * (edge_type, neighbour), entries pack nbr_local | type<<16; *_eid holds the directed edge id used to
+ * index dropout draws.  `symmetric` != 0 (extractor output: [u|v ; v|u]) aliases out-lists to in-lists.
+ * This is the private structure the fused RGCN kernels consume instead of PyG's per-edge gather
+ * (RGCNConv.propagate, third party; call site models.py:201). */
+typedef struct {
+  int32_t* in_ptr;    /* [node_cap+1] */
+  uint32_t* in_adj;   /* [edge_cap] */
+  int32_t* in_eid;    /* [edge_cap] */
+  int32_t* out_ptr;   /* same three for outgoing edges; ignored when symmetric */
+  uint32_t* out_adj;
+  int32_t* out_eid;
+  uint64_t* tmp;      /* [edge_cap] scratch */
+  int32_t symmetric;
+} igmc_adj_t;
+
+int igmc_batch_prepare(const int64_t* edge_index, int64_t edge_row_stride, const int64_t* edge_type,
+                       const int32_t* node_ptr, const int32_t* edge_ptr, int B, int n_cap,
+                       const igmc_adj_t* A, int* err, void* stream);
+
+/* IGMC parameters: one flat fp32 buffer (also the NCCL gradient bucket layout).
+ * state_dict names of the reference (models.py:182-185, train_eval.py:168-172):
+ *   convs.{l}.att [R,NB] | convs.{l}.basis [NB,in,32] | convs.{l}.root [in,32] | convs.{l}.bias [32]
+ *   lin1.weight [128, 2*32*L] | lin1.bias [128] | lin2.weight [1,128] | lin2.bias [1] */
+typedef struct {
+  int32_t num_layers, num_relations, num_bases, in_dim0;
+  int32_t off_att[IGMC_MAX_LAYERS], off_basis[IGMC_MAX_LAYERS], off_root[IGMC_MAX_LAYERS],
+      off_bias[IGMC_MAX_LAYERS];
+  int32_t off_lin1_w, off_lin1_b, off_lin2_w, off_lin2_b;
+  int32_t conv_param_count;  /* params before off_lin1_w */
+  int32_t param_count;
+  float multiply_by;
+} igmc_model_t;
+
+/* Dropout draws of one step.  edge_keep/hidden_keep (uint8, 1 = keep) inject explicit draws
+ * (parity tests); otherwise counter-hash draws keyed by `seed` are used when p > 0. */
+typedef struct {
+  float adj_dropout;            /* models.py:193-198, 0 disables */
+  float hidden_dropout;         /* 0.5 in training (models.py:212), 0 in eval */
+  uint64_t seed;
+  const uint64_t* seed_dev;     /* optional device word overriding `seed` (CUDA-graph replay) */
+  const uint8_t* edge_keep;     /* [E] or NULL */
+  const uint8_t* hidden_keep;   /* [B*128] or NULL */
+} igmc_dropout_t;
+
+/* Activations kept between forward and backward. */
+typedef struct {
+  float* states;    /* [node_cap * 32*L]  concat_states (models.py:203) */
+  float* zsave;     /* [L * node_cap * NB*32] basis-space aggregates, training only (may be NULL in eval) */
+  float* inv_deg;   /* [node_cap] 1/max(kept in-degree,1) */
+  float* feat;      /* [B * 2*32*L] target-user | target-item rows */
+  float* hid;       /* [B * 128] relu(lin1) after dropout scaling */
+  float* hid_gscale;/* [B * 128] d hid / d pre-activation */
+  float* pred;      /* [B] */
+  int32_t* target;  /* [B*2] batch-global index of the target user / item node */
+  int32_t node_cap; /* row count of one zsave layer slab */
+} igmc_saved_t;
+
+/* IGMC.forward for a prepared batch (models.py:190-217): 4x (RGCNConv + tanh), concat, target-row
+ * readout, lin1/relu/dropout/lin2.  One CTA per subgraph, node features resident in shared memory.
+ * If `y` != NULL also writes dpred[g] = d(mean squared error)/d(lin2 output) for the fused train step
+ * (train_eval.py:162), with `loss_scale` = 1/(global number of graphs). */
+int igmc_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
+                 const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
+                 const igmc_dropout_t* D, int training, const igmc_saved_t* S, const float* y,
+                 float loss_scale, float* dpred, float* sqerr, int* err, void* stream);
+
+/* Backward of igmc_forward given dpred [B] (gradient wrt the lin2 output).  Writes per-graph partial
+ * gradients of the conv parameters gpart[B*conv_param_count] and the readout factors dhid [B*128];
+ * igmc_grad_reduce turns them into the flat gradient.  (autograd of models.py:190-217) */
+int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
+                  const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
+                  const igmc_dropout_t* D, const igmc_saved_t* S, const float* dpred,
+                  float* gpart, float* dhid, int* err, void* stream);
+
+/* grad[p] = sum_g gpart[g][p] (conv) ; lin1/lin2 gradients from (dhid, feat, hid, dpred) ;
+ * + ARR * d/dW sum_l sum_r ||W_{r+1}-W_r||^2 (train_eval.py:167-174).  Also writes
+ * loss_out[0] = sum_g sqerr[g]*loss_scale + ARR*reg  when loss_out != NULL. */
+int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, const float* gpart,
+                     const float* dhid, const float* feat, const float* hid, const float* dpred,
+                     const float* sqerr, float loss_scale, float arr, float grad_scale,
+                     float* grad, float* loss_out, void* stream);
+
+/* torch.optim.Adam step (train_eval.py:54,177; lr/weight_decay semantics of torch 1.4 Adam, eps outside
+ * the sqrt, no amsgrad) on the flat buffers.  `step_count` is a device int64 incremented by the kernel;
+ * grad is multiplied by grad_mul first (1/world after an NCCL sum); `lr_dev` (optional device float)
+ * overrides `lr` so LR decay does not invalidate a captured graph. */
+int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   int64_t* step_count, int n, float lr, const float* lr_dev, float beta1, float beta2,
+                   float eps, float weight_decay, float grad_mul, void* stream);
+
+/* Version / build info: returns the compiled SM arch (100) so the host can refuse stale builds. */
+int igmc_build_info(void);
+
+/* Dynamic shared memory the forward (backward != 0: backward) kernel needs for subgraphs of up to
+ * n_cap nodes; the host uses it to size n_cap and to refuse batches that cannot fit (227 KB). */
+int igmc_model_smem_bytes(int n_cap, int num_relations, int num_bases, int num_layers, int backward);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+"""Pure-torch CPU restatement of the model half of the IGMC hot path (TEST ORACLE).
+
+PARITY UNPINNED: the arithmetic lives in third-party PyTorch-Geometric 1.4.2
+(pinned only in prose, reference README.md:26), which is neither under
+/root/reference nor installable offline, and the reference ships no tests, golden
+outputs or checkpoints.  This file restates the published PyG 1.4.2 algorithms
+ and anchors on the reference's own call sites:
+
+* ``RGCNConv(in, out, num_relations, num_bases)``  built at models.py:182-184,
+  called at models.py:201; parameters ``att [R,B]``, ``basis [B,in,out]`` confirmed
+  by train_eval.py:168-172; ``root [in,out]``, ``bias [out]``; ``aggr='mean'`` over
+  ALL incoming edges; init ``U(-1/sqrt(B*in), 1/sqrt(B*in))`` for every parameter.
+* ``dropout_adj``  call site models.py:193-198 (Bernoulli(1-p) per directed edge).
+* ``IGMC.forward``  models.py:190-217 (concat of tanh layer outputs, target-row
+  readout, lin1 -> relu -> dropout(0.5) -> lin2).
+* train-step loss  train_eval.py:157-175 (MSE mean + ARR * sum_r ||W_{r+1}-W_r||^2).
+
+The message function deliberately uses the reference-era formulation
+(``index_select`` of a per-edge weight + ``bmm`` + scatter-mean): it is the CPU
+baseline that ``bench.py --impl reference`` times.
+"""
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def scatter_mean(src, index, dim_size):
+    out = torch.zeros(dim_size, src.shape[1], dtype=src.dtype).index_add_(0, index, src)
+    cnt = torch.zeros(dim_size, dtype=src.dtype).index_add_(0, index, torch.ones_like(index, dtype=src.dtype))
+    return out / cnt.clamp(min=1).unsqueeze(1)
+
+
+def dropout_adj(edge_index, edge_attr, p, training=True, keep_mask=None, generator=None):
+    """PyG 1.4.2 ``dropout_adj`` with force_undirected=False.  ``keep_mask`` injects the
+    Bernoulli draw (bool [E]) so that two implementations can share it."""
+    if not training or p == 0.0:
+        return edge_index, edge_attr
+    if keep_mask is None:
+        keep_mask = torch.bernoulli(torch.full((edge_index.shape[1],), 1 - p), generator=generator).bool()
+    return edge_index[:, keep_mask], edge_attr[keep_mask]
+
+
+class RGCNConvRef(nn.Module):
+    def __init__(self, in_channels, out_channels, num_relations, num_bases, aggr="mean_all"):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.num_relations, self.num_bases = num_relations, num_bases
+        self.aggr = aggr
+        self.basis = nn.Parameter(torch.empty(num_bases, in_channels, out_channels))
+        self.att = nn.Parameter(torch.empty(num_relations, num_bases))
+        self.root = nn.Parameter(torch.empty(in_channels, out_channels))
+        self.bias = nn.Parameter(torch.empty(out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        bound = 1.0 / math.sqrt(self.num_bases * self.in_channels)
+        for p in (self.basis, self.att, self.root, self.bias):
+            p.data.uniform_(-bound, bound)
+
+    def forward(self, x, edge_index, edge_type):
+        src, dst = edge_index[0], edge_index[1]
+        w = torch.matmul(self.att, self.basis.view(self.num_bases, -1))
+        w = w.view(self.num_relations, self.in_channels, self.out_channels)
+        w_e = torch.index_select(w, 0, edge_type)                     # [E, in, out]
+        msg = torch.bmm(x[src].unsqueeze(1), w_e).squeeze(1)          # [E, out]
+        n = x.shape[0]
+        if self.aggr == "mean_all":
+            agg = scatter_mean(msg, dst, n)
+        elif self.aggr == "add":
+            agg = torch.zeros(n, msg.shape[1], dtype=msg.dtype).index_add_(0, dst, msg)
+        else:
+            raise ValueError(self.aggr)
+        return agg + x @ self.root + self.bias
+
+
+class IGMCRef(nn.Module):
+    """Restated ``IGMC`` (models.py:170-217); state_dict keys equal the reference's."""
+
+    def __init__(self, num_features=4, latent_dim=(32, 32, 32, 32), num_relations=5, num_bases=4,
+                 adj_dropout=0.2, multiply_by=1, aggr="mean_all"):
+        super().__init__()
+        self.adj_dropout, self.multiply_by = adj_dropout, multiply_by
+        dims = [num_features] + list(latent_dim)
+        self.convs = nn.ModuleList(
+            [RGCNConvRef(dims[l], dims[l + 1], num_relations, num_bases, aggr) for l in range(len(latent_dim))])
+        self.lin1 = nn.Linear(2 * sum(latent_dim), 128)
+        self.lin2 = nn.Linear(128, 1)
+
+    def reset_parameters(self):
+        for c in self.convs:
+            c.reset_parameters()
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+
+    def forward(self, x, edge_index, edge_type, edge_keep=None, hidden_keep=None, return_states=False):
+        """``edge_keep`` bool [E] / ``hidden_keep`` bool [B,128]: injected dropout draws (training
+        semantics).  With ``self.training`` False no dropout is applied at all."""
+        x0 = x
+        if self.training and self.adj_dropout > 0:
+            edge_index, edge_type = dropout_adj(edge_index, edge_type, self.adj_dropout, True, edge_keep)
+        states = []
+        for conv in self.convs:
+            x = torch.tanh(conv(x, edge_index, edge_type))
+            states.append(x)
+        cs = torch.cat(states, 1)
+        users, items = x0[:, 0] == 1, x0[:, 1] == 1
+        z = torch.cat([cs[users], cs[items]], 1)
+        z = F.relu(self.lin1(z))
+        if self.training:
+            if hidden_keep is not None:
+                z = z * hidden_keep.to(z.dtype) * 2.0
+            else:
+                z = F.dropout(z, p=0.5, training=True)
+        out = self.lin2(z)[:, 0] * self.multiply_by
+        return (out, cs) if return_states else out
+
+
+def arr_regulariser(model):
+    """train_eval.py:167-174."""
+    reg = 0.0
+    for g in model.convs:
+        w = torch.matmul(g.att, g.basis.view(g.num_bases, -1)).view(g.num_relations, g.in_channels, g.out_channels)
+        reg = reg + torch.sum((w[1:] - w[:-1]) ** 2)
+    return reg
+
+
+def train_loss(model, batch, ARR=0.001, edge_keep=None, hidden_keep=None):
+    """MSE (mean over graphs) + ARR term (train_eval.py:162,167-174)."""
+    out = model(batch["x"], batch["edge_index"], batch["edge_type"], edge_keep, hidden_keep)
+    loss = F.mse_loss(out, batch["y"].view(-1))
+    if ARR != 0:
+        loss = loss + ARR * arr_regulariser(model)
+    return loss, out
+
+
+def to_torch_batch(np_batch, dtype=torch.float32):
+    return dict(x=torch.from_numpy(np_batch["x"]).to(dtype),
+                edge_index=torch.from_numpy(np_batch["edge_index"]),
+                edge_type=torch.from_numpy(np_batch["edge_type"]),
+                y=torch.from_numpy(np_batch["y"]).to(dtype),
+                batch=torch.from_numpy(np_batch["batch"]), num_graphs=np_batch["num_graphs"])

@@ -1,0 +1,114 @@
+"""GPU parity of the CUDA extractor against the numpy oracle / golden vectors (bit-exact)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import extract_np
+from tests.helpers import batch_equal, inject_arrays, load_random_cases, oracle_collated
+
+pytestmark = pytest.mark.gpu
+
+H1 = [g for g in load_random_cases() if g["h"] == 1]
+
+
+def _extractor(group, seed=0):
+    from igmc_b200.util_functions import RatingGraph, SubgraphExtractor
+    pu, pv, pl = group["pairs"]
+    G = RatingGraph(group["A"])
+    return SubgraphExtractor(G, pu, pv, pl, group["cv"], 1, group["ratio"], group["mnph"], seed=seed)
+
+
+@pytest.mark.parametrize("group", H1, ids=lambda g: g["tag"])
+def test_golden_injected(group):
+    """reference-produced vectors, the reference's own sample injected as node lists"""
+    ex = _extractor(group)
+    B = len(group["cases"])
+    b = ex.extract(idx=np.arange(B), inject=inject_arrays(group["cases"], ex.cap))
+    ob = oracle_collated(group)
+    res = batch_equal(b, ob)
+    assert all(res.values()), (group["tag"], res)
+    b.check()
+
+
+@pytest.mark.parametrize("group", H1, ids=lambda g: g["tag"])
+def test_hash_sampler_matches_oracle(group):
+    """no injection: the CUDA counter-hash radix-select == oracle hash_sample, hence identical batches"""
+    ex = _extractor(group, seed=1234)
+    B = len(group["cases"])
+    b = ex.extract(idx=np.arange(B))
+    ob = oracle_collated(group, sampler_from_cases=False, seed=1234)
+    res = batch_equal(b, ob)
+    assert all(res.values()), (group["tag"], res)
+    nu, nv, cu, cv = ex.node_lists(B)
+    for k, s in enumerate(ob["subs"]):
+        assert np.array_equal(nu[k, :cu[k]], s["u_nodes"]) and np.array_equal(nv[k, :cv[k]], s["v_nodes"])
+
+
+def test_explicit_pairs_and_single_get():
+    group = H1[0]
+    from igmc_b200.util_functions import MyDynamicDataset
+    pu, pv, pl = group["pairs"]
+    ds = MyDynamicDataset(None, group["A"], (pu, pv), pl, 1, group["ratio"], group["mnph"], None, None, group["cv"])
+    assert len(ds) == len(pu) and ds.num_features == 4
+    g = extract_np.RatingCSR(group["A"])
+    for k in (0, 5, len(pu) - 1):
+        d = ds[k]
+        sub = extract_np.extract_subgraph(g, pu[k], pv[k], 1, group["ratio"], group["mnph"], seed=0, pair_id=k)
+        od = extract_np.construct_graph(sub, group["cv"][pl[k]])
+        assert np.array_equal(d.edge_index.cpu().numpy(), od["edge_index"])
+        assert np.array_equal(d.edge_type.cpu().numpy(), od["edge_type"])
+        assert np.array_equal(d.x.cpu().numpy(), od["x"])
+        assert float(d.y) == float(np.float32(od["y"][0]))
+
+
+@pytest.mark.parametrize("name,mnph,B", [("ml_100k", 200, 50), ("ml_1m", 100, 50), ("ml_1m_r02", 100, 256)])
+def test_full_size_vs_oracle_and_properties(name, mnph, B):
+    """BASELINE configs at full size: first batches bit-exact vs the oracle (same hash sampler) and
+    size-independent properties on a larger sweep."""
+    from igmc_b200.data import make_synthetic_dataset
+    from igmc_b200.util_functions import MyDynamicDataset
+    ds = make_synthetic_dataset(name, seed=0)
+    tu, tv, tl = ds["train"]
+    d = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, mnph, None, None, ds["class_values"], seed=7)
+    g = extract_np.RatingCSR(ds["adj_train"])
+    idx = np.arange(12)
+    b = d.extract_batch(idx)
+    ob = extract_np.extract_batch(g, tu[idx], tv[idx], tl[idx], ds["class_values"], 1, 1.0, mnph, seed=7,
+                                  pair_ids=idx)
+    res = batch_equal(b, ob)
+    assert all(res.values()), res
+    # properties on bigger batches
+    rng = np.random.default_rng(0)
+    for _ in range(3):
+        idx = rng.choice(len(tu), B, replace=False)
+        b = d.extract_batch(idx)
+        b.check()
+        ei, et, bt, lab = b.edge_index.cpu().numpy(), b.edge_type.cpu().numpy(), b.batch.cpu().numpy(), \
+            b.node_label.cpu().numpy()
+        nptr, eptr = b._priv["node_ptr"].cpu().numpy(), b._priv["edge_ptr"].cpu().numpy()
+        gid = b.node_gid.cpu().numpy()
+        assert nptr[-1] == len(bt) and eptr[-1] == ei.shape[1]
+        A = ds["adj_train"]
+        for k in range(B):
+            n0, n1, e0, e1 = nptr[k], nptr[k + 1], eptr[k], eptr[k + 1]
+            m = (e1 - e0) // 2
+            l = lab[n0:n1]
+            nu = int((l % 2 == 0).sum())
+            assert l[0] == 0 and l[nu] == 1 and (l[1:nu] == 2).all() and (l[nu + 1:] == 3).all()
+            assert nu - 1 <= mnph and (n1 - n0 - nu - 1) <= mnph
+            assert gid[n0] == tu[idx[k]] and gid[n0 + nu] == tv[idx[k]]
+            assert (np.diff(gid[n0 + 1:n0 + nu]) > 0).all() and (np.diff(gid[n0 + nu + 1:n1]) > 0).all()
+            s, t = ei[0, e0:e0 + m], ei[1, e0:e0 + m]
+            assert np.array_equal(ei[0, e0 + m:e1], t) and np.array_equal(ei[1, e0 + m:e1], s)   # mirrored halves
+            assert np.array_equal(et[e0:e0 + m], et[e0 + m:e1])
+            assert (s >= n0).all() and (s < n0 + nu).all() and (t >= n0 + nu).all() and (t < n1).all()
+            key = (s - n0) * 100000 + (t - n0)
+            assert (np.diff(key) > 0).all()                       # sorted, duplicate-free
+            assert not ((s == n0) & (t == n0 + nu)).any()         # target edge removed
+            # every edge is a real rating with the right type
+            assert np.array_equal(np.asarray(A[gid[s], gid[t]]).ravel() - 1, et[e0:e0 + m])
+            # ... and every rating inside the node set is present (induced sub-matrix minus the target)
+            sub = A[gid[n0:n0 + nu]][:, gid[n0 + nu:n1]]
+            assert m == sub.nnz - (1 if A[tu[idx[k]], tv[idx[k]]] != 0 else 0)
+        if name != "ml_1m_r02":
+            assert (np.diff(nptr) > 2).all()
