@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py — enclosing-subgraphs/sec of the IGMC train step (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (1 process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+A *step* is one pass of the hot path over one batch of 50 (user,item) pairs per GPU of the synthetic
+ml_1m-shaped matrix (max-nodes-per-hop 100): H2D(indices) -> extract -> adjacency -> fused RGCN
+forward+loss -> backward -> gradient assembly(+ARR) -> [NCCL all-reduce] -> Adam.
+  value : device-timed throughput, step inputs already resident in HBM, L2 flushed between steps
+  e2e   : through the public TrainEngine.step() API with pinned-host indices in, loss read back, per step
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (preset, batch per GPU, description)
+    "ml_1m": ("ml_1m", 50, "ml_1m* synthetic 6040x3706 nnz 900188, mnph=100, batch=50/GPU, hop=1, R=5, 4xRGCN(32), "
+                           "adj_dropout=0, ARR=0.001, Adam lr 1e-3"),
+    "ml_100k": ("ml_100k", 50, "ml_100k* synthetic 943x1682 nnz 80000, mnph=200, batch=50/GPU, adj_dropout=0.2"),
+    "ml_1m_r02": ("ml_1m_r02", 256, "ml_1m* ratio 0.2 synthetic nnz 216045, mnph=100, batch=256/GPU"),
+}
+ARR = 0.001
+LR = 1e-3
+SAMPLE_SEED = 0x51ED270B7F4A7C15   # sampling stream of the timed `value` steps
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's extraction + restated PyG-1.4.2 model)
+# ------------------------------------------------------------------------------------------------
+_G = {}
+
+
+def _pool_init(adj_blob, cv, mnph):
+    import scipy.sparse as ssp
+    from oracle import extract_np
+    data, indices, indptr, shape = adj_blob
+    _G["g"] = extract_np.RatingCSR(ssp.csr_matrix((data, indices, indptr), shape=shape))
+    _G["cv"], _G["mnph"] = cv, mnph
+
+
+def _pool_extract(args):
+    from oracle import extract_np
+    u, v, lab, pid = args
+    sub = extract_np.extract_subgraph(_G["g"], u, v, 1, 1.0, _G["mnph"], seed=0, pair_id=pid)
+    return extract_np.construct_graph(sub, _G["cv"][lab], 1)
+
+
+class CpuReference(object):
+    """The reference's CPU train path: per-pair extraction in a process pool (DataLoader workers,
+    train_eval.py:40-45) + PyG-1.4.2-formulation model step on all host threads."""
+
+    def __init__(self, ds, batch, cores=None):
+        import multiprocessing as mp
+        import torch
+        from oracle import pyg_restated
+        self.ds, self.B = ds, batch
+        self.cores = cores or os.cpu_count()
+        A = ds["adj_train"]
+        self.pool = mp.get_context("fork").Pool(self.cores, _pool_init,
+                                                ((A.data, A.indices, A.indptr, A.shape), ds["class_values"],
+                                                 ds["max_nodes_per_hop"]))
+        torch.set_num_threads(self.cores)
+        torch.manual_seed(1)
+        self.model = pyg_restated.IGMCRef(4, (32, 32, 32, 32), ds["num_relations"], 4, ds["adj_dropout"]).train()
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=LR)
+        self.pyg = pyg_restated
+
+    def extract(self, idx):
+        from oracle import extract_np
+        tu, tv, tl = self.ds["train"]
+        graphs = self.pool.map(_pool_extract, [(int(tu[i]), int(tv[i]), int(tl[i]), int(i)) for i in idx],
+                               chunksize=max(1, len(idx) // (4 * self.cores)))
+        return extract_np.collate(graphs)
+
+    def model_step(self, nb):
+        tb = self.pyg.to_torch_batch(nb)
+        self.opt.zero_grad()
+        loss, _ = self.pyg.train_loss(self.model, tb, ARR)
+        loss.backward()
+        self.opt.step()
+        return float(loss)
+
+    def step(self, idx):
+        return self.model_step(self.extract(idx))
+
+    def close(self):
+        self.pool.terminate()
+
+
+def run_reference(args, ds, B, rank):
+    """--impl reference: whole steps on the host cores; throughput of the serial pipeline and the
+    overlapped estimate min(extraction, model) are both reported (value = overlapped, as the reference
+    overlaps the two with DataLoader workers)."""
+    ref = CpuReference(ds, B)
+    rng = np.random.default_rng(123)
+    n = len(ds["train"][0])
+    for _ in range(max(1, min(args.warmup, 2))):
+        ref.step(rng.choice(n, B, replace=False))
+    budget, t_ext, t_mod, steps = 120.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    while steps < args.steps and (time.perf_counter() - t0) < budget:
+        idx = rng.choice(n, B, replace=False)
+        a = time.perf_counter()
+        nb = ref.extract(idx)
+        b = time.perf_counter()
+        ref.model_step(nb)
+        c = time.perf_counter()
+        t_ext += b - a
+        t_mod += c - b
+        steps += 1
+    ref.close()
+    ext_rate, mod_rate = B * steps / t_ext, B * steps / t_mod
+    value = min(ext_rate, mod_rate)
+    return dict(value=value, steps=steps, ms_per_step=1000.0 * B / value, cores=ref.cores,
+                extraction_subgraphs_per_s=ext_rate, model_subgraphs_per_s=mod_rate,
+                serial_subgraphs_per_s=B * steps / (t_ext + t_mod),
+                sample="%d steps of %d subgraphs (extraction in a %d-process pool + PyG-1.4.2-formulation "
+                       "fwd/bwd/Adam on %d threads); value=min(extraction, model) as the reference overlaps them"
+                       % (steps, B, ref.cores, ref.cores))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def algorithmic_bytes(stats, in_dims=(4, 32, 32, 32)):
+    """SURVEY.md §8(d) compulsory HBM bytes for a batch with the measured totals in `stats`."""
+    n, E, d0, Du, B = stats["n"], stats["E"], stats["d0"], stats["Du"], stats["B"]
+    b_ext = 4 * d0 + 5 * Du + 24 * E + 16 * n + 8 * n + 4 * B
+    b_fwd = sum(9 * E + 4 * n * (i + 32) for i in in_dims) + (4 * 2 * 128 + 4) * B
+    return dict(extract=b_ext, forward=b_fwd, backward=2 * b_fwd, step=b_ext + 3 * b_fwd)
+
+
+def batch_stats(ds, engine, idx_list):
+    """measured sum n, sum E, sum d0, sum D_u over the timed batches (host side, outside timing)."""
+    A = ds["adj_train"]
+    rowdeg = np.diff(A.indptr)
+    coldeg = np.diff(A.tocsc().indptr)
+    tu, tv, _ = ds["train"]
+    tot = dict(n=0, E=0, d0=0, Du=0, B=0)
+    ex = engine.dataset.extractor
+    for idx in idx_list:
+        b = ex.extract(idx=idx, seed=SAMPLE_SEED)
+        cnt = b._priv["counts"].cpu().numpy()
+        nu, nv, cu, cv = ex.node_lists(len(idx))
+        tot["n"] += int(cnt[0]); tot["E"] += int(cnt[1]); tot["B"] += len(idx)
+        tot["d0"] += int(rowdeg[tu[idx]].sum() + coldeg[tv[idx]].sum())
+        for k in range(len(idx)):
+            tot["Du"] += int(rowdeg[nu[k, :cu[k]]].sum())
+    return tot
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from igmc_b200.data import make_synthetic_dataset
+    from igmc_b200.models import IGMC, FusedAdam
+    from igmc_b200.train_eval import TrainEngine
+    from igmc_b200.util_functions import MyDynamicDataset
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    preset, B, desc = WORKLOADS[args.workload]
+    ds = make_synthetic_dataset(preset, seed=0)
+    tu, tv, tl = ds["train"]
+    train = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, ds["max_nodes_per_hop"], None, None,
+                             ds["class_values"], seed=0)
+    torch.manual_seed(1)
+    model = IGMC(train, latent_dim=[32, 32, 32, 32], num_relations=ds["num_relations"], num_bases=4,
+                 regression=True, adj_dropout=ds["adj_dropout"]).cuda()
+    if world > 1:
+        dist.broadcast(model.flat_params, 0)
+    opt = FusedAdam(model, lr=LR)
+    eng = TrainEngine(train, model, opt, B, ARR=ARR, use_graph=not args.no_graph)
+    K, W = args.steps, max(args.warmup, 3)
+    G = B * world
+    rng = np.random.default_rng(1000)
+    perm = rng.permutation(len(tu))
+    steps_idx = [perm[(s * G + rank * B):(s * G + rank * B + B)] for s in range(W + 2 * K)]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (first step eager, second captures the graph) ----
+    for s in range(W):
+        eng.step(steps_idx[s], epoch=1, G=G)
+    eng.check()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    # ---- (1) value: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
+    staged = torch.zeros(K, B + 3, dtype=torch.int64)
+    from igmc_b200.train_eval import _u64_as_i64
+    from igmc_b200.models import splitmix64
+    for k in range(K):
+        staged[k, :B] = torch.as_tensor(steps_idx[W + k])
+        staged[k, B] = _u64_as_i64(SAMPLE_SEED)
+        staged[k, B + 1] = _u64_as_i64(splitmix64(model.drop_seed + 100000 + k))
+        staged[k, B + 2] = G
+    staged = staged.cuda()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    t_wall0 = time.perf_counter()
+    for k in range(K):
+        flush.fill_(k & 0xff)
+        ev0[k].record()
+        eng.stepbuf_dev.copy_(staged[k])
+        eng.step(steps_idx[W + k], epoch=1, G=G, staged=True)
+        ev1[k].record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    clk = clocks.stop()
+    dev_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms = float(t.item())
+    value = G * K / (dev_ms / 1000.0)
+
+    # ---- (1b) informative: back-to-back steps, warm L2 (what a real epoch looks like) ----
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(K):
+        eng.stepbuf_dev.copy_(staged[k])
+        eng.step(steps_idx[W + k], epoch=1, G=G, staged=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    warm_ms = float(t.item())
+
+    # ---- (2) e2e: public API, pinned host indices -> H2D every step, loss D2H every step ----
+    loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        eng.step(steps_idx[W + K + k], epoch=2, G=G)            # stages + copies (B+3) int64 from pinned memory
+        loss_host[k:k + 1].copy_(eng.last_loss, non_blocking=True)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    eng.check()
+    assert bool(torch.isfinite(loss_host).all()), "non-finite training loss"
+
+    out = None
+    if rank == 0:
+        # ---- per-kernel times (eager launches, CUDA events on the launching stream) + roofline ----
+        stats = batch_stats(ds, eng, [steps_idx[W + k] for k in range(min(K, 20))])
+        ab = algorithmic_bytes(stats)
+        nb_batches = min(K, 20)
+        names = ("extract", "adjacency", "forward", "backward", "grad_reduce", "adam")
+        acc = {n: 0.0 for n in names}
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        ex = train.extractor
+        reps = min(K, 50)
+        for k in range(reps):
+            idx = torch.as_tensor(steps_idx[W + k]).cuda()
+            flush.fill_(1)
+            evs[0].record()
+            b = ex.extract(idx=idx, reuse=True)
+            evs[1].record()
+            b._adj = None
+            b.adjacency()
+            evs[2].record()
+            model._step += 1
+            drop = model.make_dropout(True)
+            _, saved = model._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / G)
+            evs[3].record()
+            model._launch_backward(b, drop, saved, saved["ws"]["dpred"])
+            evs[4].record()
+            model._launch_grad_reduce(b, saved, 1.0 / G, ARR, True)
+            evs[5].record()
+            opt.step(lr_dev=eng.lr_dev)
+            evs[6].record()
+            torch.cuda.synchronize()
+            for i, n in enumerate(names):
+                acc[n] += evs[i].elapsed_time(evs[i + 1])
+        kern_ms = {n: acc[n] / reps for n in names}
+        dom = max(("extract", "forward", "backward"), key=lambda n: kern_ms[n])
+        peak, peak_src = peaks()
+        per_launch_bytes = ab[dom] / nb_batches
+        achieved = per_launch_bytes / (kern_ms[dom] * 1e-3) / 1e9
+        step_bytes = ab["step"] / nb_batches
+        cpu = None
+        if not args.skip_cpu_baseline:
+            ns = argparse.Namespace(steps=args.cpu_steps, warmup=1)
+            r = run_reference(ns, ds, B, 0)
+            cpu = {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
+                   "sample": r["sample"], "extraction_subgraphs_per_s": r["extraction_subgraphs_per_s"],
+                   "model_subgraphs_per_s": r["model_subgraphs_per_s"]}
+        out = {
+            "metric": "enclosing-subgraphs/sec (train step)", "value": value, "unit": "subgraphs/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "global_batch": G, "parallelism": "dp%d" % world,
+                       "l2": "flushed between timed steps (256 MiB fill), per-step CUDA events summed",
+                       "cuda_graph": not args.no_graph},
+            "clocks": clk,
+            "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 3) * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K},
+            "gpu_launches": 9 * K,
+            "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
+                        "note": "same steps back to back without the L2 flush (informative)"},
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": per_launch_bytes,
+                         "kernel_ms": kern_ms, "step_algorithmic_bytes": step_bytes,
+                         "step_frac": (step_bytes / (dev_ms / K * 1e-3) / 1e9) / peak},
+            "cpu_baseline": cpu,
+            "batch_stats": {k: v / stats["B"] for k, v in stats.items() if k != "B"},
+            "wall_s_timed_region": wall,
+        }
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml_1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps", type=int, default=12)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        from igmc_b200.data import make_synthetic_dataset
+        preset, B, desc = WORKLOADS[args.workload]
+        ds = make_synthetic_dataset(preset, seed=0)
+        r = run_reference(args, ds, B, rank)
+        line = {"impl": "reference", "metric": "enclosing-subgraphs/sec (train step)", "value": r["value"],
+                "unit": "subgraphs/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
+                "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc, "global_batch": B, "parallelism": "cpu"},
+                "cpu_baseline": {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"],
+                                 "extraction_subgraphs_per_s": r["extraction_subgraphs_per_s"],
+                                 "model_subgraphs_per_s": r["model_subgraphs_per_s"]},
+                "e2e": {"value": r["value"], "unit": "subgraphs/s", "h2d_bytes_per_step": 0,
+                        "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+    out = run_ours(args)
+    if out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

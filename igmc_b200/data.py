@@ -60,6 +60,7 @@ def make_synthetic_dataset(name="ml_1m", seed=0, num_test=2000):
     test pairs are additional pairs NOT in adj_train.
     """
     nu, nv, nnz, R, mnph, adj_dropout = PRESETS[name]
+    num_test = max(0, min(num_test, (nu * nv - nnz) // 2))   # unique pairs must exist (tiny presets)
     u, v, lab = synth_ratings(nu, nv, nnz + num_test, R, seed)
     tu, tv, tl = u[:nnz], v[:nnz], lab[:nnz]
     adj = build_adj(tu, tv, tl, nu, nv)
