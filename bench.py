@@ -123,7 +123,8 @@ class CpuReference(object):
         self.pool = mp.get_context("fork").Pool(self.cores, _pool_init,
                                                 ((A.data, A.indices, A.indptr, A.shape), ds["class_values"],
                                                  ds["max_nodes_per_hop"]))
-        torch.set_num_threads(self.cores)
+        self.threads = min(self.cores, 16)
+        torch.set_num_threads(self.threads)
         torch.manual_seed(1)
         self.model = pyg_restated.IGMCRef(4, (32, 32, 32, 32), ds["num_relations"], 4, ds["adj_dropout"]).train()
         self.opt = torch.optim.Adam(self.model.parameters(), lr=LR)
@@ -155,9 +156,21 @@ def run_reference(args, ds, B, rank):
     """--impl reference: whole steps on the host cores; throughput of the serial pipeline and the
     overlapped estimate min(extraction, model) are both reported (value = overlapped, as the reference
     overlaps the two with DataLoader workers)."""
+    import torch
     ref = CpuReference(ds, B)
     rng = np.random.default_rng(123)
     n = len(ds["train"][0])
+    # give the reference its best thread count for the small per-edge bmm ops (oversubscription hurts it)
+    nb0 = ref.extract(rng.choice(n, B, replace=False))
+    best = (1e30, ref.threads)
+    for th in sorted({8, 16, 32, 64, ref.cores} & set(range(1, ref.cores + 1))):
+        torch.set_num_threads(th)
+        ref.model_step(nb0)
+        t = time.perf_counter()
+        ref.model_step(nb0)
+        best = min(best, (time.perf_counter() - t, th))
+    ref.threads = best[1]
+    torch.set_num_threads(ref.threads)
     for _ in range(max(1, min(args.warmup, 2))):
         ref.step(rng.choice(n, B, replace=False))
     budget, t_ext, t_mod, steps = 120.0, 0.0, 0.0, 0
@@ -179,8 +192,8 @@ def run_reference(args, ds, B, rank):
                 extraction_subgraphs_per_s=ext_rate, model_subgraphs_per_s=mod_rate,
                 serial_subgraphs_per_s=B * steps / (t_ext + t_mod),
                 sample="%d steps of %d subgraphs (extraction in a %d-process pool + PyG-1.4.2-formulation "
-                       "fwd/bwd/Adam on %d threads); value=min(extraction, model) as the reference overlaps them"
-                       % (steps, B, ref.cores, ref.cores))
+                       "fwd/bwd/Adam on %d torch threads, best of {8,16,32,64,all}); value=min(extraction, model) "
+                       "as the reference overlaps them" % (steps, B, ref.cores, ref.threads))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -324,7 +337,7 @@ def run_ours(args):
         stats = batch_stats(ds, eng, [steps_idx[W + k] for k in range(min(K, 20))])
         ab = algorithmic_bytes(stats)
         nb_batches = min(K, 20)
-        names = ("extract", "adjacency", "forward", "backward", "grad_reduce", "adam")
+        names = ("extract", "forward", "backward", "grad_reduce", "adam")
         acc = {n: 0.0 for n in names}
         evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
         ex = train.extractor
@@ -335,19 +348,16 @@ def run_ours(args):
             evs[0].record()
             b = ex.extract(idx=idx, reuse=True)
             evs[1].record()
-            b._adj = None
-            b.adjacency()
-            evs[2].record()
             model._step += 1
             drop = model.make_dropout(True)
             _, saved = model._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / G)
-            evs[3].record()
+            evs[2].record()
             model._launch_backward(b, drop, saved, saved["ws"]["dpred"])
-            evs[4].record()
+            evs[3].record()
             model._launch_grad_reduce(b, saved, 1.0 / G, ARR, True)
-            evs[5].record()
+            evs[4].record()
             opt.step(lr_dev=eng.lr_dev)
-            evs[6].record()
+            evs[5].record()
             torch.cuda.synchronize()
             for i, n in enumerate(names):
                 acc[n] += evs[i].elapsed_time(evs[i + 1])
@@ -374,7 +384,7 @@ def run_ours(args):
             "clocks": clk,
             "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 3) * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K},
-            "gpu_launches": 9 * K,
+            "gpu_launches": 8 * K,
             "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
                         "note": "same steps back to back without the L2 flush (informative)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -37,14 +37,15 @@ class Pairs(C.Structure):
 
 
 class ExtractWS(C.Structure):
-    _fields_ = [("nodes_u", vp), ("nodes_v", vp), ("n_u", vp), ("n_v", vp), ("row_cnt", vp), ("m_cnt", vp)]
+    _fields_ = [("nodes_u", vp), ("nodes_v", vp), ("n_u", vp), ("n_v", vp), ("row_cnt", vp), ("m_cnt", vp),
+                ("col_cnt", vp)]
 
 
 class BatchOut(C.Structure):
     _fields_ = [("node_cap", C.c_int32), ("edge_cap", C.c_int32), ("feat_dim", C.c_int32),
                 ("x", vp), ("node_label", vp), ("batch", vp), ("node_gid", vp), ("edge_index", vp),
                 ("edge_type", vp), ("y", vp), ("node_ptr", vp), ("edge_ptr", vp), ("graph_nu", vp),
-                ("counts", vp)]
+                ("counts", vp), ("adj_in_ptr", vp), ("adj_in", vp), ("adj_eid", vp), ("adj_tmp", vp)]
 
 
 class Adj(C.Structure):
@@ -69,7 +70,7 @@ class Dropout(C.Structure):
 
 class Saved(C.Structure):
     _fields_ = [("states", vp), ("zsave", vp), ("inv_deg", vp), ("feat", vp), ("hid", vp),
-                ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32)]
+                ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp)]
 
 
 _SIGS = {
@@ -78,15 +79,15 @@ _SIGS = {
     "igmc_batch_ptrs": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
     "igmc_batch_prepare": [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Adj), vp, vp],
     "igmc_forward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),
-                     C.c_int, C.POINTER(Saved), vp, C.c_float, vp, vp, vp, vp],
+                     C.c_int, C.POINTER(Saved), vp, C.c_float, vp, vp, C.c_int, vp, vp],
     "igmc_backward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),
-                      C.POINTER(Saved), vp, vp, vp, vp, vp],
-    "igmc_grad_reduce": [C.POINTER(Model), vp, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float,
-                         vp, vp, vp],
+                      C.POINTER(Saved), vp, vp, vp, C.c_int, vp, vp],
+    "igmc_grad_reduce": [C.POINTER(Model), vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+                         C.c_float, vp, vp, vp, vp],
     "igmc_adam_step": [vp, vp, vp, vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                        C.c_float, vp],
     "igmc_build_info": [],
-    "igmc_model_smem_bytes": [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int],
+    "igmc_model_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int],
 }
 
 EXPORTS = tuple(_SIGS)

@@ -10,7 +10,7 @@
 
 namespace {
 
-constexpr int BP_THREADS = 256;
+constexpr int BP_THREADS = 1024;
 
 // node_ptr[b] = first node with batch >= b ; edge_ptr[b] = first edge whose source lies in graph >= b
 __global__ void k_batch_ptrs(const int64_t* __restrict__ batch, const int64_t* __restrict__ edge_src,

@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int EX_THREADS = 256;
+constexpr int EX_THREADS = 1024;
 constexpr uint16_t NONE16 = 0xFFFF;
 
 // Select the node list of one side: out[0] = target, out[1..] = (sampled) fringe ascending.
@@ -127,9 +127,11 @@ k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double rat
                        const int32_t* __restrict__ inj_n_u, const int32_t* __restrict__ inj_n_v,
                        int32_t* __restrict__ nodes_u, int32_t* __restrict__ nodes_v,
                        int32_t* __restrict__ n_u, int32_t* __restrict__ n_v,
-                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ m_cnt, int* err) {
+                       int32_t* __restrict__ row_cnt, int32_t* __restrict__ m_cnt, int32_t* __restrict__ col_cnt,
+                       int* err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint16_t* tab = reinterpret_cast<uint16_t*>(smem_raw);
+  int* colcnt = reinterpret_cast<int*>(smem_raw);                 // [cap]
+  uint16_t* tab = reinterpret_cast<uint16_t*>(colcnt + cap);      // [num_items]
   __shared__ int hist[256];
   __shared__ int ws[34];
   __shared__ int sh[4];
@@ -164,6 +166,7 @@ k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double rat
   const int nu = s_nu, nv = s_nv;
   // item-id -> local-id table
   for (int t = tid; t < G.num_items; t += nt) tab[t] = NONE16;
+  for (int b = tid; b < nv; b += nt) colcnt[b] = 0;
   __syncthreads();
   for (int b = tid; b < nv; b += nt) tab[gv[b]] = (uint16_t)b;
   __syncthreads();
@@ -175,8 +178,8 @@ k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double rat
     for (int p = s + lane; p < e; p += 32) {
       const uint16_t b = tab[G.col_idx[p]];
       if (b != NONE16) {
-        if (b == 0) { hasj = 1; if (a != 0) ++cnt; }   // (0,0) is the target edge: dropped (ref :238)
-        else ++cnt;
+        if (b == 0) { hasj = 1; if (a != 0) { ++cnt; atomicAdd(&colcnt[0], 1); } }   // (0,0) = target edge: dropped (ref :238)
+        else { ++cnt; atomicAdd(&colcnt[b], 1); }
       }
     }
     cnt = warp_sum_i(cnt);
@@ -187,6 +190,7 @@ k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double rat
     }
   }
   __syncthreads();
+  for (int b = tid; b < nv; b += nt) col_cnt[(size_t)g * cap + b] = colcnt[b];
   if (tid == 0) { n_u[g] = nu; n_v[g] = nv; m_cnt[g] = s_m; }
 }
 
@@ -195,10 +199,12 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
                const int32_t* __restrict__ nodes_u, const int32_t* __restrict__ nodes_v,
                const int32_t* __restrict__ n_u, const int32_t* __restrict__ n_v,
                const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ m_cnt,
+               const int32_t* __restrict__ col_cnt,
                const float* __restrict__ class_values, igmc_batch_out_t O, int* err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* rowoff = reinterpret_cast<int*>(smem_raw);                 // [cap]
-  uint16_t* tab = reinterpret_cast<uint16_t*>(rowoff + cap);      // [num_items]
+  int* colfill = rowoff + cap;                                    // [cap] running fill pointer of the item lists
+  uint16_t* tab = reinterpret_cast<uint16_t*>(colfill + cap);     // [num_items]
   __shared__ int ws[34];
   const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
@@ -210,11 +216,13 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
   const int32_t* gu = nodes_u + (size_t)g * cap;
   const int32_t* gv = nodes_v + (size_t)g * cap;
   const bool overflow = (Nbase + n > O.node_cap) || (2 * (Mbase + m) > O.edge_cap);
+  const bool want_adj = O.adj_in_ptr != nullptr;
   if (g == B - 1 && tid == 0) {
     O.counts[0] = Nbase + n;
     O.counts[1] = 2 * (Mbase + m);
     O.node_ptr[B] = Nbase + n;
     O.edge_ptr[B] = 2 * (Mbase + m);
+    if (want_adj && Nbase + n <= O.node_cap) O.adj_in_ptr[Nbase + n] = 2 * (Mbase + m);
   }
   if (tid == 0) { O.node_ptr[g] = Nbase; O.edge_ptr[g] = 2 * Mbase; }
   if (overflow) {
@@ -246,8 +254,25 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
     const int c = a < nu ? (row_cnt[(size_t)g * cap + a] & 0x7fffffff) : 0;
     int tot;
     const int ex = block_excl_scan_i(c, ws, &tot);
-    if (a < nu) rowoff[a] = running + ex;
+    if (a < nu) {
+      rowoff[a] = running + ex;
+      if (want_adj) O.adj_in_ptr[Nbase + a] = 2 * Mbase + running + ex;       // user a: in-edges from its items
+    }
     running += tot;
+  }
+  if (want_adj) {   // item b: in-edges from users, stored after the m user-side entries of this graph
+    running = 0;
+    for (int base = 0; base < nv; base += nt) {
+      const int b = base + tid;
+      const int c = b < nv ? col_cnt[(size_t)g * cap + b] : 0;
+      int tot;
+      const int ex = block_excl_scan_i(c, ws, &tot);
+      if (b < nv) {
+        colfill[b] = running + ex;
+        O.adj_in_ptr[Nbase + nu + b] = 2 * Mbase + m + running + ex;
+      }
+      running += tot;
+    }
   }
   for (int t = tid; t < G.num_items; t += nt) tab[t] = NONE16;
   __syncthreads();
@@ -276,8 +301,30 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
         const int64_t un = Nbase + a, vn = Nbase + nu + b;
         ei0[e1] = un; ei1[e1] = vn; O.edge_type[e1] = r;
         ei0[e2] = vn; ei1[e2] = un; O.edge_type[e2] = r;
+        if (want_adj) {
+          // user a's list: edge item->user is the mirrored copy e2; entry sits at the edge's first-half slot
+          O.adj_in[e1] = (uint32_t)(nu + b) | ((uint32_t)r << 16);
+          O.adj_eid[e1] = (int32_t)e2;
+          // item b's list: edge user->item is e1; unordered placement, sorted below
+          const int slot = atomicAdd(&colfill[b], 1);
+          O.adj_tmp[(size_t)2 * Mbase + m + slot] = ((uint64_t)a << 40) | ((uint64_t)r << 32) | (uint64_t)(uint32_t)e1;
+        }
       }
       seen += __popc(bal);
+    }
+  }
+  if (want_adj) {   // deterministic item lists: rank-sort by user index (lists are short)
+    __syncthreads();
+    for (int b = warp; b < nv; b += nwarps) {
+      const int k = col_cnt[(size_t)g * cap + b];
+      const size_t beg = (size_t)2 * Mbase + m + (colfill[b] - k);
+      for (int i = lane; i < k; i += 32) {
+        const uint64_t key = O.adj_tmp[beg + i];
+        int rank = 0;
+        for (int q = 0; q < k; ++q) rank += (O.adj_tmp[beg + q] < key) ? 1 : 0;
+        O.adj_in[beg + rank] = (uint32_t)(key >> 40) | ((uint32_t)((key >> 32) & 0xffu) << 16);
+        O.adj_eid[beg + rank] = (int32_t)(uint32_t)(key & 0xffffffffu);
+      }
     }
   }
 }
@@ -293,18 +340,18 @@ extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, in
   if (B <= 0) return 0;
   if (cap < 1 || cap > 65534) return -2;
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smemA = (size_t)G->num_items * sizeof(uint16_t);
-  const size_t smemB = (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
+  const size_t smemA = (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
+  const size_t smemB = 2 * (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
   if (smemB > 220 * 1024) return -3;  // item table does not fit in shared memory
   cudaFuncSetAttribute(k_extract_select_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
   cudaFuncSetAttribute(k_extract_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
   k_extract_select_count<<<B, EX_THREADS, smemA, st>>>(*G, *P, B, max_nodes_per_hop, sample_ratio, seed, seed_dev, cap,
                                                        inj_nodes_u, inj_nodes_v, inj_n_u, inj_n_v,
                                                        W->nodes_u, W->nodes_v, W->n_u, W->n_v, W->row_cnt, W->m_cnt,
-                                                       err);
+                                                       W->col_cnt, err);
   IGMC_CUDA_CHECK_LAUNCH();
   k_extract_fill<<<B, EX_THREADS, smemB, st>>>(*G, *P, B, cap, W->nodes_u, W->nodes_v, W->n_u, W->n_v,
-                                               W->row_cnt, W->m_cnt, class_values, *O, err);
+                                               W->row_cnt, W->m_cnt, W->col_cnt, class_values, *O, err);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -11,19 +11,52 @@ namespace {
 constexpr int HID = IGMC_HIDDEN;
 constexpr int L1O = IGMC_LIN1_OUT;
 
-// grad[p] for every parameter: conv params = fixed-order sum of per-graph partials; lin1/lin2 from
-// the saved readout factors.  One thread per parameter, loop over graphs (coalesced across threads).
-__global__ void k_grad_reduce(igmc_model_t M, int B, const float* __restrict__ gpart,
-                              const float* __restrict__ dhid, const float* __restrict__ feat,
-                              const float* __restrict__ hid, const float* __restrict__ dpred,
-                              const float* __restrict__ sqerr, float loss_scale, float grad_scale,
-                              float* __restrict__ grad, float* __restrict__ loss_out) {
+// dW_r[kj] of the adjacent-rating regulariser for one (layer, kj):  reg = sum_{r<R-1} ||W_{r+1}-W_r||^2,
+// W_r = sum_b att[r,b] basis[b];  d reg / d W_r = 2 (W_r - W_{r-1}) [r>0] - 2 (W_{r+1} - W_r) [r<R-1].
+__device__ __forceinline__ float arr_dw(const float* __restrict__ att, const float* __restrict__ bs, int NB, int KJ,
+                                        int R, int r, int kj, float* reg_pair) {
+  float wm = 0.f, w0 = 0.f, wp = 0.f;
+  for (int b = 0; b < NB; ++b) {
+    const float bv = bs[b * KJ + kj];
+    w0 = fmaf(att[r * NB + b], bv, w0);
+    if (r > 0) wm = fmaf(att[(r - 1) * NB + b], bv, wm);
+    if (r < R - 1) wp = fmaf(att[(r + 1) * NB + b], bv, wp);
+  }
+  float dw = 0.f;
+  if (r > 0) dw += 2.f * (w0 - wm);
+  if (r < R - 1) { dw -= 2.f * (wp - w0); if (reg_pair) *reg_pair = (wp - w0) * (wp - w0); }
+  else if (reg_pair) *reg_pair = 0.f;
+  return dw;
+}
+
+// grad[p] for every parameter: conv params = fixed-order sum of the per-CTA partial rows (+ the ARR term
+// for basis entries, thread-local); lin1/lin2 from the saved readout factors.  One thread per parameter.
+__global__ void k_grad_reduce(igmc_model_t M, const float* __restrict__ params, int B, int rows,
+                              const float* __restrict__ gpart, const float* __restrict__ dhid,
+                              const float* __restrict__ feat, const float* __restrict__ hid,
+                              const float* __restrict__ dpred, const float* __restrict__ sqerr, float loss_scale,
+                              float arr, float grad_scale, float* __restrict__ grad, float* __restrict__ loss_out) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   const int PC = M.conv_param_count, F = 2 * HID * M.num_layers;
   if (p < M.param_count) {
     float s = 0.f;
     if (p < PC) {
-      for (int g = 0; g < B; ++g) s += gpart[(size_t)g * PC + p];
+      for (int g = 0; g < rows; ++g) s += gpart[(size_t)g * PC + p];
+      if (arr != 0.f) {
+        for (int l = 0; l < M.num_layers; ++l) {
+          const int in = l == 0 ? M.in_dim0 : HID, KJ = in * HID;
+          const int q = p - M.off_basis[l];
+          if (q >= 0 && q < M.num_bases * KJ) {   // basis[b][kj]:  += arr * sum_r att[r,b] dW_r[kj]
+            const int b = q / KJ, kj = q - b * KJ;
+            const float* att = params + M.off_att[l];
+            float t = 0.f;
+            for (int r = 0; r < M.num_relations; ++r)
+              t = fmaf(att[r * M.num_bases + b],
+                       arr_dw(att, params + M.off_basis[l], M.num_bases, KJ, M.num_relations, r, kj, nullptr), t);
+            s = fmaf(arr, t, s);
+          }
+        }
+      }
     } else if (p >= M.off_lin1_w && p < M.off_lin1_w + L1O * F) {
       const int q = p - M.off_lin1_w, o = q / F, i = q - o * F;      // lin1.weight[o][i]
       for (int g = 0; g < B; ++g) s = fmaf(dhid[(size_t)g * L1O + o], feat[(size_t)g * F + i], s);
@@ -46,70 +79,52 @@ __global__ void k_grad_reduce(igmc_model_t M, int B, const float* __restrict__ g
   }
 }
 
-// ARR term (one CTA, loops layers): reg = sum_l sum_{r<R-1} ||W_l[r+1]-W_l[r]||^2, W = att @ basis.
-// Adds arr * d reg to grad (att, basis) and arr * reg to loss_out.
+// ARR, att part + regulariser value: one CTA per layer, one warp per (r,b) (looped).
+//   d att[r,b] += arr * < dW_r , basis[b] > ;   reg_l = sum_{r<R-1} ||W_{r+1}-W_r||^2
+// The last CTA to finish adds arr * sum_l reg_l to loss_out in layer order (deterministic).
 __global__ void __launch_bounds__(256)
-k_arr(igmc_model_t M, const float* __restrict__ params, float arr, float grad_scale, float* __restrict__ grad,
-      float* __restrict__ loss_out) {
-  extern __shared__ float sm[];
-  const int R = M.num_relations, NB = M.num_bases;
-  float* att_s = sm;               // [R*NB]
-  float* datt = att_s + R * NB;    // [R*NB]
-  __shared__ float red[8];
-  __shared__ float s_reg;
+k_arr_att(igmc_model_t M, const float* __restrict__ params, float arr, float grad_scale, float* __restrict__ grad,
+          float* __restrict__ loss_out, float* __restrict__ reg_ws) {
+  const int l = blockIdx.x, R = M.num_relations, NB = M.num_bases;
+  const int in = l == 0 ? M.in_dim0 : HID, KJ = in * HID;
+  const float* att = params + M.off_att[l];
+  const float* bs = params + M.off_basis[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_reg = 0.f;
-  for (int l = 0; l < M.num_layers; ++l) {
-    const int in = l == 0 ? M.in_dim0 : HID;
-    const int KJ = in * HID;
-    const float* bs = params + M.off_basis[l];
-    for (int i = tid; i < R * NB; i += 256) { att_s[i] = params[M.off_att[l] + i]; datt[i] = 0.f; }
-    __syncthreads();
-    float reg = 0.f;
-    for (int r = 0; r < R; ++r) {
-      // dW[r][kj] = 2 * ((W[r]-W[r-1]) [r>0] - (W[r+1]-W[r]) [r<R-1])
-      float part[IGMC_MAX_BASES] = {0.f, 0.f, 0.f, 0.f};
-      for (int kj = tid; kj < KJ; kj += 256) {
-        float wm = 0.f, w0 = 0.f, wp = 0.f;
-        for (int b = 0; b < NB; ++b) {
-          const float bv = bs[b * KJ + kj];
-          w0 = fmaf(att_s[r * NB + b], bv, w0);
-          if (r > 0) wm = fmaf(att_s[(r - 1) * NB + b], bv, wm);
-          if (r < R - 1) wp = fmaf(att_s[(r + 1) * NB + b], bv, wp);
-        }
-        float dw = 0.f;
-        if (r > 0) dw += 2.f * (w0 - wm);
-        if (r < R - 1) { dw -= 2.f * (wp - w0); reg += (wp - w0) * (wp - w0); }
-        for (int b = 0; b < NB; ++b) {
-          part[b] = fmaf(dw, bs[b * KJ + kj], part[b]);
-          // d basis[b][kj] += att[r][b] * dW[r][kj]; this thread owns kj -> plain accumulate
-          grad[M.off_basis[l] + b * KJ + kj] += arr * grad_scale * att_s[r * NB + b] * dw;
-        }
-      }
-      for (int b = 0; b < NB; ++b) {
-        float v = warp_sum_f(part[b]);
-        if (lane == 0) red[warp] = v;
-        __syncthreads();
-        if (tid == 0) {
-          float s = 0.f;
-          for (int w = 0; w < 8; ++w) s += red[w];
-          datt[r * NB + b] = s;
-        }
-        __syncthreads();
-      }
-    }
-    reg = warp_sum_f(reg);
-    if (lane == 0) red[warp] = reg;
-    __syncthreads();
-    if (tid == 0) {
-      float s = 0.f;
-      for (int w = 0; w < 8; ++w) s += red[w];
-      s_reg += s;
-    }
-    for (int i = tid; i < R * NB; i += 256) grad[M.off_att[l] + i] += arr * grad_scale * datt[i];
-    __syncthreads();
+  __shared__ float red[8];
+  __shared__ int s_last;
+  for (int rb = warp; rb < R * NB; rb += 8) {
+    const int r = rb / NB, b = rb - r * NB;
+    float s = 0.f;
+    for (int kj = lane; kj < KJ; kj += 32) s = fmaf(arr_dw(att, bs, NB, KJ, R, r, kj, nullptr), bs[b * KJ + kj], s);
+    s = warp_sum_f(s);
+    if (lane == 0) grad[M.off_att[l] + rb] += arr * grad_scale * s;
   }
-  if (tid == 0 && loss_out) loss_out[0] += arr * s_reg;
+  float reg = 0.f;
+  for (int idx = tid; idx < (R - 1) * KJ; idx += 256) {
+    const int r = idx / KJ, kj = idx - r * KJ;
+    float pr;
+    arr_dw(att, bs, NB, KJ, R, r, kj, &pr);
+    reg += pr;
+  }
+  reg = warp_sum_f(reg);
+  if (lane == 0) red[warp] = reg;
+  __syncthreads();
+  if (tid == 0) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    reg_ws[l] = s;
+    __threadfence();
+    int* ticket = reinterpret_cast<int*>(reg_ws + IGMC_MAX_LAYERS);
+    s_last = (atomicAdd(ticket, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && tid == 0) {
+    __threadfence();
+    float s = 0.f;
+    for (int q = 0; q < (int)gridDim.x; ++q) s += __ldcg(reg_ws + q);
+    if (loss_out) loss_out[0] += arr * s;
+    *reinterpret_cast<int*>(reg_ws + IGMC_MAX_LAYERS) = 0;   // re-arm for the next step
+  }
 }
 
 __global__ void k_adam(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
@@ -136,18 +151,18 @@ __global__ void k_inc_step(int64_t* step_count) { step_count[0] += 1; }
 
 }  // namespace
 
-extern "C" int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, const float* gpart,
+extern "C" int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, int gpart_rows, const float* gpart,
                                 const float* dhid, const float* feat, const float* hid, const float* dpred,
                                 const float* sqerr, float loss_scale, float arr, float grad_scale, float* grad,
-                                float* loss_out, void* stream) {
+                                float* loss_out, float* reg_ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = (M->param_count + 255) / 256;
-  k_grad_reduce<<<blocks, 256, 0, st>>>(*M, B, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, grad_scale, grad,
-                                        loss_out);
+  k_grad_reduce<<<blocks, 256, 0, st>>>(*M, params, B, gpart_rows, gpart, dhid, feat, hid, dpred, sqerr, loss_scale,
+                                        arr, grad_scale, grad, loss_out);
   IGMC_CUDA_CHECK_LAUNCH();
   if (arr != 0.f) {
-    const size_t smem = 2 * (size_t)M->num_relations * M->num_bases * sizeof(float);
-    k_arr<<<1, 256, smem, st>>>(*M, params, arr, grad_scale, grad, loss_out);
+    if (!reg_ws) return -18;
+    k_arr_att<<<M->num_layers, 256, 0, st>>>(*M, params, arr, grad_scale, grad, loss_out, reg_ws);
     IGMC_CUDA_CHECK_LAUNCH();
   }
   return 0;

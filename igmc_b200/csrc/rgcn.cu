@@ -578,16 +578,49 @@ int check_model(const igmc_model_t* M) {
 
 }  // namespace
 
+// relation-space / cluster kernels (csrc/rgcn_rs.cu)
+int rs_supported(const igmc_model_t* M);
+int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem);
+int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
+               const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
+               const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, int cluster,
+               int* err, cudaStream_t st);
+int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
+                const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
+                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, float* dstate, int cluster,
+                int* err, cudaStream_t st);
+
+extern "C" int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, int backward) {
+  int rc = check_model(M);
+  if (rc) return rc;
+  if (cluster == 0) {
+    const size_t b = backward ? bwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers)
+                              : fwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
+    return b > 227 * 1024 ? -3 : (int)b;
+  }
+  if (cluster != 1 && cluster != 2 && cluster != 4) return -15;
+  if (!rs_supported(M)) return -16;
+  int threads;
+  size_t smem;
+  rc = rs_plan(M, n_cap, cluster, backward, &threads, &smem);
+  return rc ? rc : (int)smem;
+}
+
 extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                             const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                             const igmc_dropout_t* D, int training, const igmc_saved_t* S, const float* y,
-                            float loss_scale, float* dpred, float* sqerr, int* err, void* stream) {
+                            float loss_scale, float* dpred, float* sqerr, int cluster, int* err, void* stream) {
   if (B <= 0) return 0;
   int rc = check_model(M);
   if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cluster > 0) {
+    if (!rs_supported(M)) return -16;
+    return rs_forward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, training, S, y, loss_scale, dpred,
+                      sqerr, cluster, err, st);
+  }
   const size_t smem = fwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
   if (smem > 227 * 1024) return -3;
-  cudaStream_t st = (cudaStream_t)stream;
   if (M->num_bases == 4) {
     cudaFuncSetAttribute(k_forward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_forward<4><<<B, MP_THREADS, smem, st>>>(*M, params, node_label, node_ptr, edge_ptr, *A, n_cap, *D, training, *S,
@@ -604,14 +637,20 @@ extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const ui
 extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                              const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                              const igmc_dropout_t* D, const igmc_saved_t* S, const float* dpred, float* gpart,
-                             float* dhid, int* err, void* stream) {
+                             float* dhid, int cluster, int* err, void* stream) {
   if (B <= 0) return 0;
   int rc = check_model(M);
   if (rc) return rc;
   if (!S->zsave) return -14;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cluster > 0) {
+    if (!rs_supported(M)) return -16;
+    if (!S->dstate) return -17;
+    return rs_backward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, dpred, gpart, dhid, S->dstate,
+                       cluster, err, st);
+  }
   const size_t smem = bwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
   if (smem > 227 * 1024) return -3;
-  cudaStream_t st = (cudaStream_t)stream;
   if (M->num_bases == 4) {
     cudaFuncSetAttribute(k_backward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     k_backward<4><<<B, MP_THREADS, smem, st>>>(*M, params, node_label, node_ptr, edge_ptr, *A, n_cap, *D, *S, dpred,
@@ -623,10 +662,4 @@ extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const u
   }
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
-}
-
-// smem requirement query so the host can size n_cap / report limits
-extern "C" int igmc_model_smem_bytes(int n_cap, int num_relations, int num_bases, int num_layers, int backward) {
-  return (int)(backward ? bwd_smem_bytes(n_cap, num_relations, num_bases, num_layers)
-                        : fwd_smem_bytes(n_cap, num_relations, num_bases, num_layers));
 }

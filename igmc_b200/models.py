@@ -168,6 +168,7 @@ class IGMC(nn.Module):
         self.flat_params, self.flat_grad = flat, grad
         self._layout, self._cmodel = layout, m
         self._ws = {}
+        self._plans = {}
 
     def alias_grads(self):
         """point every ``p.grad`` at its slice of ``flat_grad`` (for stock torch optimizers)."""
@@ -186,16 +187,34 @@ class IGMC(nn.Module):
         self.lin2.reset_parameters()
 
     # ---- kernel launches ---------------------------------------------------------------------------------
-    def _check_fit(self, n_cap, backward):
+    kernel_plan = "auto"   # "auto" | 0 (generic kernels) | 1 | 2 | 4 (relation-space kernels, CTAs per subgraph)
+    NUM_SMS = 148
+
+    def _plan(self, batch):
+        """cluster size for this batch: use the relation-space kernels when the relation count allows and
+        spread each subgraph over as many CTAs (1/2/4) as keeps the grid within one wave of the SMs."""
+        p = batch._priv
+        key = (p["n_cap"], batch.num_graphs)
+        c = self._plans.get(key)
+        if c is not None:
+            return c
         lib = _lib.load()
-        need = lib.igmc_model_smem_bytes(n_cap, self.num_relations, self.num_bases, len(self.convs), int(backward))
-        if need > SMEM_LIMIT:
-            raise RuntimeError("igmc_b200: subgraphs of up to %d nodes need %d B of shared memory per CTA "
-                               "(limit %d); lower --max-nodes-per-hop" % (n_cap, need, SMEM_LIMIT))
+        n_cap, B = p["n_cap"], batch.num_graphs
+        want = self.kernel_plan
+        cands = [want] if want != "auto" else [cl for cl in (4, 2, 1) if B * cl <= self.NUM_SMS or cl == 1] + [0]
+        for cl in cands:
+            f = lib.igmc_model_plan(C.byref(self._cmodel), n_cap, int(cl), 0)
+            b = lib.igmc_model_plan(C.byref(self._cmodel), n_cap, int(cl), 1)
+            if f > 0 and b > 0:
+                self._plans[key] = int(cl)
+                return int(cl)
+        raise RuntimeError("igmc_b200: no kernel plan fits subgraphs of up to %d nodes with %d relations in %d B of "
+                           "shared memory per CTA; lower --max-nodes-per-hop" % (n_cap, self.num_relations, SMEM_LIMIT))
 
     def _workspace(self, batch, train):
         p = batch._priv
-        key = (p["node_cap"], batch.num_graphs, bool(train))
+        cl = self._plan(batch)
+        key = (p["node_cap"], batch.num_graphs, bool(train), cl)
         ws = self._ws.get(key)
         if ws is None:
             dev, L, NB, B, ncap = self.flat_params.device, len(self.convs), self.num_bases, batch.num_graphs, \
@@ -205,10 +224,13 @@ class IGMC(nn.Module):
                       feat=torch.empty(B, 2 * HID * L, **f32), hid=torch.empty(B, 128, **f32),
                       hid_gscale=torch.empty(B, 128, **f32), pred=torch.empty(B, **f32),
                       target=torch.empty(B, 2, dtype=torch.int32, device=dev),
-                      dpred=torch.zeros(B, **f32), sqerr=torch.zeros(B, **f32), loss=torch.zeros(1, **f32))
+                      dpred=torch.zeros(B, **f32), sqerr=torch.zeros(B, **f32), loss=torch.zeros(1, **f32),
+                      reg_ws=torch.zeros(_lib.MAX_LAYERS + 1, **f32), cluster=cl)
             if train:
-                ws.update(zsave=torch.empty(L, ncap, NB * HID, **f32),
-                          gpart=torch.zeros(B, self._cmodel.conv_param_count, **f32),
+                zdim = max(NB, self.num_relations if cl > 0 else 0) * HID
+                ws.update(zsave=torch.empty(L, ncap, zdim, **f32),
+                          dstate=torch.empty(L, ncap, HID, **f32),
+                          gpart=torch.zeros(B * max(cl, 1), self._cmodel.conv_param_count, **f32),
                           dhid=torch.empty(B, 128, **f32))
             if len(self._ws) > 8:
                 self._ws.clear()
@@ -218,7 +240,7 @@ class IGMC(nn.Module):
     def _saved_struct(self, ws, ncap):
         return _lib.Saved(ws["states"].data_ptr(), _lib.ptr(ws.get("zsave")), ws["inv_deg"].data_ptr(),
                           ws["feat"].data_ptr(), ws["hid"].data_ptr(), ws["hid_gscale"].data_ptr(),
-                          ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap)
+                          ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap, _lib.ptr(ws.get("dstate")))
 
     def make_dropout(self, training, edge_keep=None, hidden_keep=None, seed=None, seed_dev=None):
         """dropout descriptor of one step (+ the tensors it references, to keep them alive)."""
@@ -245,7 +267,6 @@ class IGMC(nn.Module):
     def _launch_forward(self, batch, training, drop, y=None, loss_scale=0.0):
         lib = _lib.load()
         p = batch._priv
-        self._check_fit(p["n_cap"], False)
         adj_c, _ = batch.adjacency()
         ws = self._workspace(batch, training)
         S = self._saved_struct(ws, p["node_cap"])
@@ -254,14 +275,13 @@ class IGMC(nn.Module):
                                     p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
                                     batch.num_graphs, p["n_cap"], C.byref(d), int(training), C.byref(S),
                                     _lib.ptr(y), float(loss_scale), ws["dpred"].data_ptr() if y is not None else None,
-                                    ws["sqerr"].data_ptr() if y is not None else None, batch._err.data_ptr(),
-                                    _stream_ptr()), "igmc_forward")
+                                    ws["sqerr"].data_ptr() if y is not None else None, ws["cluster"],
+                                    batch._err.data_ptr(), _stream_ptr()), "igmc_forward")
         return ws["pred"], dict(ws=ws, S=S, train=bool(training))
 
     def _launch_backward(self, batch, drop, saved, dpred):
         lib = _lib.load()
         p = batch._priv
-        self._check_fit(p["n_cap"], True)
         adj_c, _ = batch.adjacency()
         ws = saved["ws"]
         d, keep = drop
@@ -269,19 +289,20 @@ class IGMC(nn.Module):
         _lib.check(lib.igmc_backward(C.byref(self._cmodel), self.flat_params.data_ptr(), p["node_label"].data_ptr(),
                                      p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
                                      batch.num_graphs, p["n_cap"], C.byref(d), C.byref(saved["S"]),
-                                     dpred.data_ptr(), ws["gpart"].data_ptr(), ws["dhid"].data_ptr(),
+                                     dpred.data_ptr(), ws["gpart"].data_ptr(), ws["dhid"].data_ptr(), ws["cluster"],
                                      batch._err.data_ptr(), _stream_ptr()), "igmc_backward")
 
     def _launch_grad_reduce(self, batch, saved, loss_scale, arr, with_loss=True):
         lib = _lib.load()
         ws = saved["ws"]
         _lib.check(lib.igmc_grad_reduce(C.byref(self._cmodel), self.flat_params.data_ptr(), batch.num_graphs,
+                                        batch.num_graphs * max(ws["cluster"], 1),
                                         ws["gpart"].data_ptr(), ws["dhid"].data_ptr(), ws["feat"].data_ptr(),
                                         ws["hid"].data_ptr(), saved["dpred_used"].data_ptr(),
                                         ws["sqerr"].data_ptr() if with_loss else None, float(loss_scale),
                                         float(arr), 1.0, self.flat_grad.data_ptr(),
-                                        ws["loss"].data_ptr() if with_loss else None, _stream_ptr()),
-                   "igmc_grad_reduce")
+                                        ws["loss"].data_ptr() if with_loss else None, ws["reg_ws"].data_ptr(),
+                                        _stream_ptr()), "igmc_grad_reduce")
 
     # ---- public API ------------------------------------------------------------------------------------------
     def _as_batch(self, data):

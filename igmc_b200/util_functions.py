@@ -286,9 +286,10 @@ class SubgraphExtractor(object):
         i32 = dict(dtype=torch.int32, device=dev)
         self.ws = dict(nodes_u=torch.empty(B * cap, **i32), nodes_v=torch.empty(B * cap, **i32),
                        n_u=torch.zeros(B, **i32), n_v=torch.zeros(B, **i32),
-                       row_cnt=torch.empty(B * cap, **i32), m_cnt=torch.zeros(B, **i32))
+                       row_cnt=torch.empty(B * cap, **i32), m_cnt=torch.zeros(B, **i32),
+                       col_cnt=torch.empty(B * cap, **i32))
         self._ws_c = _lib.ExtractWS(*[self.ws[k].data_ptr() for k in ("nodes_u", "nodes_v", "n_u", "n_v",
-                                                                          "row_cnt", "m_cnt")])
+                                                                          "row_cnt", "m_cnt", "col_cnt")])
 
     def _alloc_out(self, B, reuse=False):
         if reuse and B in self._out_cache:
@@ -306,6 +307,10 @@ class SubgraphExtractor(object):
                  edge_ptr=torch.zeros(B + 1, dtype=torch.int32, device=dev),
                  graph_nu=torch.zeros(B, dtype=torch.int32, device=dev),
                  counts=torch.zeros(2, dtype=torch.int32, device=dev),
+                 adj_in_ptr=torch.zeros(ncap + 1, dtype=torch.int32, device=dev),
+                 adj_in=torch.empty(ecap, dtype=torch.int32, device=dev),
+                 adj_eid=torch.empty(ecap, dtype=torch.int32, device=dev),
+                 adj_tmp=torch.empty(ecap, dtype=torch.int64, device=dev),
                  err=self.err)
         o["_caps"] = (ncap, ecap)
         if reuse:
@@ -346,7 +351,9 @@ class SubgraphExtractor(object):
         O = _lib.BatchOut(ncap, ecap, self.feat_dim, _lib.ptr(o["x"]), o["node_label"].data_ptr(),
                           o["batch"].data_ptr(), o["node_gid"].data_ptr(), o["edge_index"].data_ptr(),
                           o["edge_type"].data_ptr(), o["y"].data_ptr(), o["node_ptr"].data_ptr(),
-                          o["edge_ptr"].data_ptr(), o["graph_nu"].data_ptr(), o["counts"].data_ptr())
+                          o["edge_ptr"].data_ptr(), o["graph_nu"].data_ptr(), o["counts"].data_ptr(),
+                          o["adj_in_ptr"].data_ptr(), o["adj_in"].data_ptr(), o["adj_eid"].data_ptr(),
+                          o["adj_tmp"].data_ptr())
         inj = [None] * 4
         if inject is not None:
             inj_t = [torch.as_tensor(np.asarray(a), dtype=torch.int32).to(dev).contiguous() for a in inject]
@@ -366,8 +373,9 @@ class SubgraphExtractor(object):
         b._priv = dict(node_label=o["node_label"], node_ptr=o["node_ptr"], edge_ptr=o["edge_ptr"],
                        node_cap=ncap, edge_cap=ecap, n_cap=2 * self.cap, symmetric=1, edge_row_stride=ecap,
                        graph_nu=o["graph_nu"], counts=o["counts"])
-        if reuse:
-            b._adj_cache = o.setdefault("_adj", {})
+        # the extractor already built the (symmetric) message-passing adjacency in the same pass
+        b._adj = (_lib.Adj(o["adj_in_ptr"].data_ptr(), o["adj_in"].data_ptr(), o["adj_eid"].data_ptr(), None, None,
+                           None, o["adj_tmp"].data_ptr(), 1), o)
         return b
 
     def node_lists(self, B):

@@ -53,6 +53,7 @@ typedef struct {
   int32_t* n_v;      /* [B] */
   int32_t* row_cnt;  /* [B*cap] */
   int32_t* m_cnt;    /* [B] undirected edges per graph */
+  int32_t* col_cnt;  /* [B*cap] matches per item column */
 } igmc_extract_ws_t;
 
 /* The collated batch in the reference's layout (what construct_pyg_graph + Batch.from_data_list
@@ -71,6 +72,12 @@ typedef struct {
   int32_t* edge_ptr;    /* [B+1] directed-edge offsets */
   int32_t* graph_nu;    /* [B] number of user nodes of each graph */
   int32_t* counts;      /* [2] N, E */
+  /* optional (all or none): the message-passing adjacency of igmc_adj_t (symmetric form), built in the
+   * same pass so that igmc_batch_prepare is not needed for extracted batches; lists ordered by neighbour */
+  int32_t* adj_in_ptr;  /* [node_cap+1] */
+  uint32_t* adj_in;     /* [edge_cap] */
+  int32_t* adj_eid;     /* [edge_cap] */
+  uint64_t* adj_tmp;    /* [edge_cap] scratch */
 } igmc_batch_out_t;
 
 /* Enclosing-subgraph extraction + labelling + graph construction + collate for B pairs (h = 1).
@@ -139,40 +146,50 @@ typedef struct {
 /* Activations kept between forward and backward. */
 typedef struct {
   float* states;    /* [node_cap * 32*L]  concat_states (models.py:203) */
-  float* zsave;     /* [L * node_cap * NB*32] basis-space aggregates, training only (may be NULL in eval) */
+  float* zsave;     /* [L * node_cap * zdim] saved aggregates (zdim = max(NB,R)*32), training only, NULL in eval */
   float* inv_deg;   /* [node_cap] 1/max(kept in-degree,1) */
   float* feat;      /* [B * 2*32*L] target-user | target-item rows */
   float* hid;       /* [B * 128] relu(lin1) after dropout scaling */
   float* hid_gscale;/* [B * 128] d hid / d pre-activation */
   float* pred;      /* [B] */
   int32_t* target;  /* [B*2] batch-global index of the target user / item node */
-  int32_t node_cap; /* row count of one zsave layer slab */
+  int32_t node_cap; /* row count of one zsave / dstate layer slab */
+  float* dstate;    /* [L * node_cap * 32] d h_l rows exchanged between the CTAs of a cluster (backward) */
 } igmc_saved_t;
 
+/* Kernel plan.  `cluster` = 0 selects the generic kernels (csrc/rgcn.cu: one 256-thread CTA per
+ * subgraph, any num_relations <= 256); 1/2/4 select the relation-space kernels (csrc/rgcn_rs.cu,
+ * num_relations <= 12) with that many CTAs (a thread-block cluster) per subgraph.  Returns the dynamic
+ * shared memory in bytes the chosen kernel needs for subgraphs of up to n_cap nodes, or a negative value
+ * if the plan is not available (too many relations / does not fit in 227 KB). */
+int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, int backward);
+
 /* IGMC.forward for a prepared batch (models.py:190-217): 4x (RGCNConv + tanh), concat, target-row
- * readout, lin1/relu/dropout/lin2.  One CTA per subgraph, node features resident in shared memory.
+ * readout, lin1/relu/dropout/lin2.  Node features resident in shared memory for all layers.
  * If `y` != NULL also writes dpred[g] = d(mean squared error)/d(lin2 output) for the fused train step
  * (train_eval.py:162), with `loss_scale` = 1/(global number of graphs). */
 int igmc_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                  const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                  const igmc_dropout_t* D, int training, const igmc_saved_t* S, const float* y,
-                 float loss_scale, float* dpred, float* sqerr, int* err, void* stream);
+                 float loss_scale, float* dpred, float* sqerr, int cluster, int* err, void* stream);
 
-/* Backward of igmc_forward given dpred [B] (gradient wrt the lin2 output).  Writes per-graph partial
- * gradients of the conv parameters gpart[B*conv_param_count] and the readout factors dhid [B*128];
- * igmc_grad_reduce turns them into the flat gradient.  (autograd of models.py:190-217) */
+/* Backward of igmc_forward given dpred [B] (gradient wrt the lin2 output).  Writes partial gradients of
+ * the conv parameters, one row per CTA: gpart[B*max(cluster,1)][conv_param_count], and the readout
+ * factors dhid [B*128]; igmc_grad_reduce turns them into the flat gradient.  Must use the same `cluster`
+ * as the forward that produced S.  (autograd of models.py:190-217) */
 int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                   const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                   const igmc_dropout_t* D, const igmc_saved_t* S, const float* dpred,
-                  float* gpart, float* dhid, int* err, void* stream);
+                  float* gpart, float* dhid, int cluster, int* err, void* stream);
 
-/* grad[p] = sum_g gpart[g][p] (conv) ; lin1/lin2 gradients from (dhid, feat, hid, dpred) ;
+/* grad[p] = sum over gpart rows (conv) ; lin1/lin2 gradients from (dhid, feat, hid, dpred) ;
  * + ARR * d/dW sum_l sum_r ||W_{r+1}-W_r||^2 (train_eval.py:167-174).  Also writes
- * loss_out[0] = sum_g sqerr[g]*loss_scale + ARR*reg  when loss_out != NULL. */
-int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, const float* gpart,
+ * loss_out[0] = sum_g sqerr[g]*loss_scale + ARR*reg  when loss_out != NULL.  `reg_ws` is a scratch of
+ * IGMC_MAX_LAYERS+1 floats (+1 int ticket) used to add the per-layer regulariser values in a fixed order. */
+int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, int gpart_rows, const float* gpart,
                      const float* dhid, const float* feat, const float* hid, const float* dpred,
                      const float* sqerr, float loss_scale, float arr, float grad_scale,
-                     float* grad, float* loss_out, void* stream);
+                     float* grad, float* loss_out, float* reg_ws, void* stream);
 
 /* torch.optim.Adam step (train_eval.py:54,177; lr/weight_decay semantics of torch 1.4 Adam, eps outside
  * the sqrt, no amsgrad) on the flat buffers.  `step_count` is a device int64 incremented by the kernel;
@@ -184,10 +201,6 @@ int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_
 
 /* Version / build info: returns the compiled SM arch (100) so the host can refuse stale builds. */
 int igmc_build_info(void);
-
-/* Dynamic shared memory the forward (backward != 0: backward) kernel needs for subgraphs of up to
- * n_cap nodes; the host uses it to size n_cap and to refuse batches that cannot fit (227 KB). */
-int igmc_model_smem_bytes(int n_cap, int num_relations, int num_bases, int num_layers, int backward);
 
 #ifdef __cplusplus
 }

@@ -21,13 +21,14 @@ def _oracle_batch(nu=120, nv=90, nnz=2500, R=5, B=16, mnph=30, seed=3):
     return A, (u, v, lab), cv, ob
 
 
-def _models(R=5, NB=4, adj_dropout=0.2, seed=0, multiply_by=1):
+def _models(R=5, NB=4, adj_dropout=0.2, seed=0, multiply_by=1, plan="auto"):
     from igmc_b200.models import IGMC
     torch.manual_seed(seed)
     ref = pyg_restated.IGMCRef(4, (32, 32, 32, 32), R, NB, adj_dropout, multiply_by).double()
     m = IGMC(4, latent_dim=[32, 32, 32, 32], num_relations=R, num_bases=NB, regression=True,
              adj_dropout=adj_dropout, multiply_by=multiply_by).cuda()
     m.load_state_dict({k: v.float() for k, v in ref.state_dict().items()})
+    m.kernel_plan = plan   # 0: generic basis-space kernels; 1/2/4: relation-space kernels, CTAs per subgraph
     return ref, m
 
 
@@ -40,10 +41,11 @@ def _rmse(a, b):
     return float(torch.sqrt(torch.mean((a.double().cpu() - b.double().cpu()) ** 2)))
 
 
-@pytest.mark.parametrize("R,NB,mult", [(5, 4, 1), (10, 2, 1), (5, 4, 2)])
-def test_forward_eval_parity(R, NB, mult):
+@pytest.mark.parametrize("R,NB,mult,plan", [(5, 4, 1, 0), (5, 4, 1, 1), (5, 4, 1, 2), (5, 4, 1, 4), (10, 2, 1, 0),
+                                            (10, 2, 1, 2), (5, 4, 2, "auto"), (30, 4, 1, "auto")])
+def test_forward_eval_parity(R, NB, mult, plan):
     A, links, cv, ob = _oracle_batch(R=R)
-    ref, m = _models(R, NB, multiply_by=mult)
+    ref, m = _models(R, NB, multiply_by=mult, plan=plan)
     ref.eval(); m.eval()
     tb = pyg_restated.to_torch_batch(ob, torch.float64)
     with torch.no_grad():
@@ -68,8 +70,10 @@ def test_forward_on_extracted_batch_matches_foreign_batch():
     assert torch.equal(p1, p2)
 
 
-@pytest.mark.parametrize("R,NB,symmetric", [(5, 4, True), (10, 2, True), (5, 4, False)])
-def test_train_forward_backward_parity(R, NB, symmetric):
+@pytest.mark.parametrize("R,NB,symmetric,plan", [(5, 4, True, 0), (5, 4, True, 1), (5, 4, True, 2), (5, 4, True, 4),
+                                                 (10, 2, True, 0), (10, 2, True, 2), (5, 4, False, 0),
+                                                 (5, 4, False, 2), (30, 4, True, "auto")])
+def test_train_forward_backward_parity(R, NB, symmetric, plan):
     """injected edge/hidden dropout draws; loss, predictions and every parameter gradient vs autograd"""
     A, links, cv, ob = _oracle_batch(R=R)
     if not symmetric:   # make the message graph structurally asymmetric (foreign batch path)
@@ -77,7 +81,7 @@ def test_train_forward_backward_parity(R, NB, symmetric):
         keep = rng.random(ob["edge_index"].shape[1]) > 0.3
         # keep edges grouped by graph: boolean mask preserves order
         ob = dict(ob, edge_index=ob["edge_index"][:, keep], edge_type=ob["edge_type"][keep])
-    ref, m = _models(R, NB, adj_dropout=0.2)
+    ref, m = _models(R, NB, adj_dropout=0.2, plan=plan)
     ref.train(); m.train()
     E, B = ob["edge_index"].shape[1], ob["num_graphs"]
     gen = torch.Generator().manual_seed(11)
@@ -95,7 +99,9 @@ def test_train_forward_backward_parity(R, NB, symmetric):
     assert abs(float(loss) - float(loss_ref)) <= 1e-4 * max(1.0, abs(float(loss_ref)))
     sd_ref = dict(ref.named_parameters())
     worst = 0.0
-    for (o, n, s), (name, p) in zip(m._layout, m.named_parameters()):
+    names = {id(p): name for name, p in m.named_parameters()}
+    for (o, n, s), (_, _, p) in zip(m._layout, m._named_order()):
+        name = names[id(p)]
         gref = sd_ref[name].grad.reshape(-1)
         ggpu = m.flat_grad[o:o + n].double().cpu()
         denom = float(gref.abs().max()) + 1e-12
