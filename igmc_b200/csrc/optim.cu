@@ -87,11 +87,15 @@ k_arr_att(igmc_model_t M, const float* __restrict__ params, float arr, float gra
           float* __restrict__ loss_out, float* __restrict__ reg_ws) {
   const int l = blockIdx.x, R = M.num_relations, NB = M.num_bases;
   const int in = l == 0 ? M.in_dim0 : HID, KJ = in * HID;
-  const float* att = params + M.off_att[l];
-  const float* bs = params + M.off_basis[l];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ float sm_arr[];                 // att [R*NB] | basis [NB*KJ]  (latency-bound otherwise)
+  float* att = sm_arr;
+  float* bs = sm_arr + ((R * NB + 3) & ~3);
+  for (int i = tid; i < R * NB; i += 256) att[i] = params[M.off_att[l] + i];
+  for (int i = tid; i < NB * KJ; i += 256) bs[i] = params[M.off_basis[l] + i];
   __shared__ float red[8];
   __shared__ int s_last;
+  __syncthreads();
   for (int rb = warp; rb < R * NB; rb += 8) {
     const int r = rb / NB, b = rb - r * NB;
     float s = 0.f;
@@ -162,7 +166,8 @@ extern "C" int igmc_grad_reduce(const igmc_model_t* M, const float* params, int 
   IGMC_CUDA_CHECK_LAUNCH();
   if (arr != 0.f) {
     if (!reg_ws) return -18;
-    k_arr_att<<<M->num_layers, 256, 0, st>>>(*M, params, arr, grad_scale, grad, loss_out, reg_ws);
+    const size_t smem = (size_t)(((M->num_relations * M->num_bases + 3) & ~3) + M->num_bases * HID * HID) * sizeof(float);
+    k_arr_att<<<M->num_layers, 256, smem, st>>>(*M, params, arr, grad_scale, grad, loss_out, reg_ws);
     IGMC_CUDA_CHECK_LAUNCH();
   }
   return 0;

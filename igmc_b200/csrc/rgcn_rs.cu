@@ -1,11 +1,12 @@
 // v2 fused relational message passing: relation-space aggregate + dense transform, one thread-block
-// CLUSTER per enclosing subgraph (1/2/4 CTAs split the destination nodes), 16 warps per CTA.
+// CLUSTER per enclosing subgraph (1/2/4 CTAs split the destination nodes), up to 32 warps per CTA.
 //
 // Same math and C-ABI as csrc/rgcn.cu (which stays as the generic path for many relations); this is the
 // fast path for num_relations <= RS_MAX_R.  Per layer (reference: tanh(RGCNConv) models.py:200-202,
 // PyG 1.4.2 semantics SURVEY.md A.1), with W_r = sum_b att[r,b] basis[b] formed once per CTA in shared memory:
-//   AGG[v,r,:] = sum_{(u->v) of type r, kept} h[u,:]            warp owns 8 destination nodes; 8-lane groups x float4
-//   h'[v]      = tanh( 1/deg(v) * sum_r AGG[v,r,:] W_r + h[v] root + bias )    lane = (node, 8 output channels)
+//   AGG[v,r,:] = sum_{(u->v) of type r, kept} h[u,:]      warp owns 4 destination nodes; 8-lane groups x float4,
+//                                                          edge lists staged in shared memory, software-pipelined
+//   h'[v]      = tanh( 1/deg(v) * sum_r AGG[v,r,:] W_r + h[v] root + bias )    lane = (node, 4 output channels)
 // Node features of the WHOLE subgraph stay in shared memory; CTAs of a cluster exchange their rows through
 // L2 (ld/st.cg) + barrier.cluster once per layer.  Backward = same two passes on the out-lists with W_r^T,
 // a K=n weight-gradient tile GEMM, and the (att,basis) chain rule applied to the per-CTA dW_r.
@@ -22,14 +23,14 @@ namespace rs {
 constexpr int HID = IGMC_HIDDEN;
 constexpr int L1O = IGMC_LIN1_OUT;
 constexpr int RS_MAX_R = 12;
-constexpr int GN = 8;          // destination nodes per warp group
+constexpr int GN = 4;          // destination nodes per warp group (one 8-lane group each)
 constexpr int TW = 32;         // node tile of the weight-gradient GEMM
+constexpr int WP = 33;         // padded row stride of the transposition scratch
 constexpr uint32_t DROPPED = 0xFFFFFFFFu;
 
+// activation tiles [n][32]: column XOR-swizzled by the row in 4-float groups (a row stays one 128 B line,
+// a fixed column group over 8 consecutive rows hits 8 different bank groups)
 __device__ __forceinline__ int hix(int v, int c) { return (v << 5) + (c ^ ((v & 7) << 2)); }
-// weights [row][32] with the 4-float column groups XOR-swizzled by the row (conflict-free float4 row reads
-// AND cheap transposed writes)
-__device__ __forceinline__ int wix(int row, int c) { return (row << 5) + ((((c >> 2) ^ (row & 7)) << 2) | (c & 3)); }
 __host__ __device__ __forceinline__ int a4(int x) { return (x + 3) & ~3; }
 
 struct Keep {
@@ -51,7 +52,7 @@ __device__ __forceinline__ Keep make_keep(const igmc_dropout_t& D, int training)
   return K;
 }
 
-// entry of node list position p, DROPPED if the (possibly mirrored) edge is dropped this step
+// entry of list position p, DROPPED if the (possibly mirrored) edge is dropped this step
 __device__ __forceinline__ uint32_t load_entry(const uint32_t* __restrict__ adj, const int32_t* __restrict__ eid,
                                                int p, const Keep& K, bool mirror, int eb, int m_half) {
   uint32_t ent = __ldg(adj + p);
@@ -63,65 +64,105 @@ __device__ __forceinline__ uint32_t load_entry(const uint32_t* __restrict__ adj,
   return ent;
 }
 
-// Relation-space aggregate of up to GN nodes [base, base+cnt) into the warp's staging rows
-// stg[s][r*inp + k] (row stride SS).  8-lane groups walk 4 node lists concurrently, float4 per lane.
-// SRC_SCALED: feature rows already carry their 1/deg factor (backward).  Returns nothing; lists are
-// (type, neighbour)-sorted but no order is assumed.
-__device__ __forceinline__ void gather_group(const uint32_t* __restrict__ adj, const int32_t* __restrict__ eid,
-                                             const int32_t* __restrict__ ptr, int nb, int base, int cnt,
-                                             const Keep& K, bool mirror, int eb, int m_half, int lane,
-                                             const float* __restrict__ feat, float* __restrict__ stg, int SS,
-                                             int inp, int R) {
-  const int q = lane & 7, gq = lane >> 3;
-  // zero the staging rows
+// The lists of the own nodes [lo,hi) are one contiguous range [e_lo, e_hi) of the adjacency array: stage it
+// in shared memory (dropout draws applied once) when it fits.
+struct Lists {
+  const uint32_t* adj;
+  const int32_t* eid;
+  const int32_t* ptr;   // global node offsets
+  const uint32_t* lst;  // staged entries or nullptr
+  int e_lo;
+  bool mirror;
+  int eb, m_half;
+};
+__device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t* eid, const int32_t* ptr, int nb, int lo,
+                                             int hi, const Keep& K, bool mirror, int eb, int m_half, uint32_t* lbuf,
+                                             int lcap) {
+  Lists Ls;
+  Ls.adj = adj; Ls.eid = eid; Ls.ptr = ptr; Ls.mirror = mirror; Ls.eb = eb; Ls.m_half = m_half;
+  Ls.e_lo = ptr[nb + lo];
+  const int cnt = ptr[nb + hi] - Ls.e_lo;
+  Ls.lst = nullptr;
+  if (cnt <= lcap) {
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) lbuf[i] = load_entry(adj, eid, Ls.e_lo + i, K, mirror, eb, m_half);
+    Ls.lst = lbuf;
+  }
+  return Ls;
+}
+
+// Relation-space aggregate of the warp's nodes [base, base+cnt) (cnt <= GN) into its staging rows
+// stg[s][r*inp + k] (row stride SS): 8-lane group s walks node base+s, float4 per lane, next entry and
+// source row prefetched while the current one is accumulated.
+template <bool STAGED>
+__device__ __forceinline__ void gather_group(const Lists& Ls, const Keep& K, int nb, int base, int cnt, int lane,
+                                             const float* __restrict__ feat, float* __restrict__ stg, int SS, int inp) {
+  const int q = lane & 7, s = lane >> 3;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = lane * 4; i < GN * SS; i += 128) *reinterpret_cast<float4*>(stg + i) = z4;
   __syncwarp();
-  const bool lane_on = (4 * q) < inp;
-#pragma unroll
-  for (int round = 0; round < GN / 4; ++round) {
-    const int s = round * 4 + gq;
-    int p = 0, p1 = 0;
-    if (s < cnt) { p = ptr[nb + base + s]; p1 = ptr[nb + base + s + 1]; }
-    float* row = stg + s * SS + 4 * q;
-    for (; p < p1; ++p) {
-      const uint32_t ent = load_entry(adj, eid, p, K, mirror, eb, m_half);
-      if (ent == DROPPED || !lane_on) continue;
-      const int src = (int)(ent & 0xffffu), ty = (int)((ent >> 16) & 0xffu);
-      const float4 a = *reinterpret_cast<const float4*>(feat + hix(src, 4 * q));
-      float4* d = reinterpret_cast<float4*>(row + ty * inp);
+  int p = 0, p1 = 0;
+  if (s < cnt) { p = Ls.ptr[nb + base + s]; p1 = Ls.ptr[nb + base + s + 1]; }
+  if ((4 * q) >= inp) p1 = p;                       // lanes beyond the feature width idle (layer 0)
+  float* row = stg + s * SS + 4 * q;
+  const int fo = 4 * q;
+  auto entry = [&](int pp) -> uint32_t {
+    return STAGED ? Ls.lst[pp - Ls.e_lo] : load_entry(Ls.adj, Ls.eid, pp, K, Ls.mirror, Ls.eb, Ls.m_half);
+  };
+  uint32_t ent = p < p1 ? entry(p) : DROPPED;
+  float4 a = z4;
+  if (ent != DROPPED) a = *reinterpret_cast<const float4*>(feat + hix((int)(ent & 0xffffu), fo));
+  while (p < p1) {
+    const uint32_t nent = (p + 1 < p1) ? entry(p + 1) : DROPPED;
+    float4 na = z4;
+    if (nent != DROPPED) na = *reinterpret_cast<const float4*>(feat + hix((int)(nent & 0xffffu), fo));
+    if (ent != DROPPED) {
+      float4* d = reinterpret_cast<float4*>(row + (int)((ent >> 16) & 0xffu) * inp);
       float4 t = *d;
       t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
       *d = t;
     }
+    ent = nent;
+    a = na;
+    ++p;
   }
   __syncwarp();
 }
 
-// acc[j] (8 output channels c8..c8+7 of node slot s) += sum_kk stg[s][kk] * W[kk][c8+j]
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ a_row, int K, const float* __restrict__ W,
-                                          int row0, int c8, float (&acc)[8]) {
-#pragma unroll 4
-  for (int kk = 0; kk < K; ++kk) {
-    const float a = a_row[kk];
-    const float4 w0 = *reinterpret_cast<const float4*>(W + wix(row0 + kk, c8));
-    const float4 w1 = *reinterpret_cast<const float4*>(W + wix(row0 + kk, c8 + 4));
-    acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]);
-    acc[3] = fmaf(a, w0.w, acc[3]); acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
-    acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+// acc[j] (4 output channels c4..c4+3 of one node) += sum_kk a_row[kk] * W[kk][c4+j]; K multiple of 4,
+// W row-major [K][32]
+__device__ __forceinline__ void gemm_rows(const float* __restrict__ a_row, int K, const float* __restrict__ W, int c4,
+                                          float (&acc)[4]) {
+  const float* w = W + c4;
+#pragma unroll 2
+  for (int kk = 0; kk < K; kk += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(a_row + kk);
+    const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * HID);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * HID);
+    const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * HID);
+    const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * HID);
+    acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.x, w0.y, acc[1]); acc[2] = fmaf(a.x, w0.z, acc[2]); acc[3] = fmaf(a.x, w0.w, acc[3]);
+    acc[0] = fmaf(a.y, w1.x, acc[0]); acc[1] = fmaf(a.y, w1.y, acc[1]); acc[2] = fmaf(a.y, w1.z, acc[2]); acc[3] = fmaf(a.y, w1.w, acc[3]);
+    acc[0] = fmaf(a.z, w2.x, acc[0]); acc[1] = fmaf(a.z, w2.y, acc[1]); acc[2] = fmaf(a.z, w2.z, acc[2]); acc[3] = fmaf(a.z, w2.w, acc[3]);
+    acc[0] = fmaf(a.w, w3.x, acc[0]); acc[1] = fmaf(a.w, w3.y, acc[1]); acc[2] = fmaf(a.w, w3.z, acc[2]); acc[3] = fmaf(a.w, w3.w, acc[3]);
   }
 }
-// same with the A operand read from a swizzled activation row
+// same with the A operand taken from row v of a swizzled activation tile
 __device__ __forceinline__ void gemm_hrow(const float* __restrict__ Hbuf, int v, int K, const float* __restrict__ W,
-                                          int row0, int c8, float (&acc)[8]) {
-#pragma unroll 4
-  for (int kk = 0; kk < K; ++kk) {
-    const float a = Hbuf[hix(v, kk)];
-    const float4 w0 = *reinterpret_cast<const float4*>(W + wix(row0 + kk, c8));
-    const float4 w1 = *reinterpret_cast<const float4*>(W + wix(row0 + kk, c8 + 4));
-    acc[0] = fmaf(a, w0.x, acc[0]); acc[1] = fmaf(a, w0.y, acc[1]); acc[2] = fmaf(a, w0.z, acc[2]);
-    acc[3] = fmaf(a, w0.w, acc[3]); acc[4] = fmaf(a, w1.x, acc[4]); acc[5] = fmaf(a, w1.y, acc[5]);
-    acc[6] = fmaf(a, w1.z, acc[6]); acc[7] = fmaf(a, w1.w, acc[7]);
+                                          int c4, float (&acc)[4]) {
+  const float* w = W + c4;
+  const float* hrow = Hbuf + (v << 5);
+  const int sw = (v & 7) << 2;
+#pragma unroll 2
+  for (int kk = 0; kk < K; kk += 4) {
+    const float4 a = *reinterpret_cast<const float4*>(hrow + (kk ^ sw));
+    const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * HID);
+    const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * HID);
+    const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * HID);
+    const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * HID);
+    acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.x, w0.y, acc[1]); acc[2] = fmaf(a.x, w0.z, acc[2]); acc[3] = fmaf(a.x, w0.w, acc[3]);
+    acc[0] = fmaf(a.y, w1.x, acc[0]); acc[1] = fmaf(a.y, w1.y, acc[1]); acc[2] = fmaf(a.y, w1.z, acc[2]); acc[3] = fmaf(a.y, w1.w, acc[3]);
+    acc[0] = fmaf(a.z, w2.x, acc[0]); acc[1] = fmaf(a.z, w2.y, acc[1]); acc[2] = fmaf(a.z, w2.z, acc[2]); acc[3] = fmaf(a.z, w2.w, acc[3]);
+    acc[0] = fmaf(a.w, w3.x, acc[0]); acc[1] = fmaf(a.w, w3.y, acc[1]); acc[2] = fmaf(a.w, w3.z, acc[2]); acc[3] = fmaf(a.w, w3.w, acc[3]);
   }
 }
 
@@ -137,10 +178,10 @@ __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(1024, 1)
 k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
-             igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y, float loss_scale,
+             int lcap, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y, float loss_scale,
              float* __restrict__ dpred, float* __restrict__ sqerr, int* err) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -152,13 +193,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const int SSmax = R * HID + 4;
   float* H = smem;                                   // [n_cap][32]
   float* Hn = H + (size_t)n_cap * HID;               // [n_cap][32]
-  float* W = Hn + (size_t)n_cap * HID;               // [(R+1)*32][32]
+  float* W = Hn + (size_t)n_cap * HID;               // [(R+1)*32][32] row-major
   float* stg_all = W + (size_t)(R + 1) * HID * HID;  // [nwarps][GN][SSmax]
-  float* att_s = stg_all + (size_t)nwarps * GN * SSmax;
-  float* bias_s = att_s + a4(R * NB);
+  float* bias_s = stg_all + (size_t)nwarps * GN * SSmax;
   float* invdeg = bias_s + HID;                      // [n_cap]
   float* feat_s = invdeg + a4(n_cap);
   float* hid_s = feat_s + a4(F);
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(hid_s + L1O);   // [lcap]
   __shared__ int s_t[2];
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
@@ -179,16 +220,17 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     if (c == 0 && lab == 0) atomicMin(&s_t[0], v);
     if (c == 0 && lab == 1) atomicMin(&s_t[1], v);
   }
+  const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap);
+  __syncthreads();
   // kept in-degree of the own nodes (dropout_adj is applied once, models.py:193)
   for (int v = own.lo + warp; v < own.hi; v += nwarps) {
     const int p0 = A.in_ptr[nb + v], p1 = A.in_ptr[nb + v + 1];
-    int kept = 0;
+    int kept = p1 - p0;
     if (K.active) {
+      kept = 0;
       for (int p = p0 + lane; p < p1; p += 32)
-        kept += load_entry(A.in_adj, A.in_eid, p, K, false, eb, m_half) != DROPPED;
+        kept += (Ls.lst ? Ls.lst[p - Ls.e_lo] : load_entry(A.in_adj, A.in_eid, p, K, false, eb, m_half)) != DROPPED;
       kept = warp_sum_i(kept);
-    } else {
-      kept = p1 - p0;
     }
     if (lane == 0) {
       const float id = 1.f / (float)max(kept, 1);
@@ -207,7 +249,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   for (int l = 0; l < L; ++l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, SS = K1 + 4;
-    // W_r = sum_b att[r,b] basis[b]  (rows r*inp+k), then root rows; zero rows for the k padding
+    // W rows r*inp+k = sum_b att[r,b] basis[b][k][:], then the root rows; zero rows for the k padding
     {
       const float* bs = params + M.off_basis[l];
       const float* at = params + M.off_att[l];
@@ -217,36 +259,28 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
         float w = 0.f;
         if (k < in)
           for (int b = 0; b < NB; ++b) w = fmaf(at[r * NB + b], bs[(b * in + k) * HID + j], w);
-        W[wix(row, j)] = w;
+        W[idx] = w;
       }
-      for (int idx = tid; idx < inp * HID; idx += NT) {
-        const int j = idx & 31, k = idx >> 5;
-        W[wix(K1 + k, j)] = k < in ? rt[k * HID + j] : 0.f;
-      }
+      for (int idx = tid; idx < inp * HID; idx += NT) W[K1 * HID + idx] = (idx >> 5) < in ? rt[idx] : 0.f;
       if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
     }
     __syncthreads();
     for (int base = own.lo + warp * GN; base < own.hi; base += nwarps * GN) {
       const int cnt = min(GN, own.hi - base);
-      gather_group(A.in_adj, A.in_eid, A.in_ptr, nb, base, cnt, K, false, eb, m_half, lane, H, stg, SS, inp, R);
-      const int s = lane >> 2, c8 = (lane & 3) * 8;
+      if (Ls.lst) gather_group<true>(Ls, K, nb, base, cnt, lane, H, stg, SS, inp);
+      else gather_group<false>(Ls, K, nb, base, cnt, lane, H, stg, SS, inp);
+      const int s = lane >> 3, c4 = (lane & 7) * 4;
       const int v = base + min(s, cnt - 1);
-      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      gemm_rows(stg + s * SS, K1, W, 0, c8, acc);
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      gemm_rows(stg + s * SS, K1, W, c4, acc);
       const float id = invdeg[v];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] *= id;
-      gemm_hrow(H, v, inp, W, K1, c8, acc);
+      acc[0] *= id; acc[1] *= id; acc[2] *= id; acc[3] *= id;
+      gemm_hrow(H, v, inp, W + K1 * HID, c4, acc);
       if (s < cnt) {
-        float4 o0 = make_float4(tanhf(acc[0] + bias_s[c8]), tanhf(acc[1] + bias_s[c8 + 1]),
-                                tanhf(acc[2] + bias_s[c8 + 2]), tanhf(acc[3] + bias_s[c8 + 3]));
-        float4 o1 = make_float4(tanhf(acc[4] + bias_s[c8 + 4]), tanhf(acc[5] + bias_s[c8 + 5]),
-                                tanhf(acc[6] + bias_s[c8 + 6]), tanhf(acc[7] + bias_s[c8 + 7]));
-        *reinterpret_cast<float4*>(Hn + hix(v, c8)) = o0;
-        *reinterpret_cast<float4*>(Hn + hix(v, c8 + 4)) = o1;
-        float* gs = S.states + (size_t)(nb + v) * CW + l * HID + c8;
-        __stcg(reinterpret_cast<float4*>(gs), o0);
-        __stcg(reinterpret_cast<float4*>(gs + 4), o1);
+        const float4 o = make_float4(tanhf(acc[0] + bias_s[c4]), tanhf(acc[1] + bias_s[c4 + 1]),
+                                     tanhf(acc[2] + bias_s[c4 + 2]), tanhf(acc[3] + bias_s[c4 + 3]));
+        *reinterpret_cast<float4*>(Hn + hix(v, c4)) = o;
+        __stcg(reinterpret_cast<float4*>(S.states + (size_t)(nb + v) * CW + l * HID + c4), o);
       }
       if (S.zsave) {   // 1/deg-scaled aggregate, reused by the weight-gradient GEMM
         for (int s2 = 0; s2 < cnt; ++s2) {
@@ -274,7 +308,6 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
 
   if (rank != 0) return;
   // ---- readout (models.py:205-215), one CTA of the cluster ----
-  if (CL == 1) __threadfence_block();
   for (int c = tid; c < F; c += NT) {
     const int node = c < CW ? tu : ti;
     const float v = __ldcg(S.states + (size_t)(nb + node) * CW + (c < CW ? c : c - CW));
@@ -380,10 +413,10 @@ __device__ __forceinline__ void wgrad(const igmc_saved_t& S, const uint8_t* __re
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(1024, 1)
 k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
               const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
-              igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred, float* __restrict__ gpart,
+              int lcap, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred, float* __restrict__ gpart,
               float* __restrict__ dhid_out, float* __restrict__ dstate, int* err) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
@@ -396,17 +429,20 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int own_cap = ((n_cap + CL - 1) / CL + GN - 1) / GN * GN;
   float* DPS = smem;                                    // [n_cap][32]   dpre / deg   (all nodes)
   float* DP = DPS + (size_t)n_cap * HID;                // [own_cap][32] dpre         (own nodes)
-  float* Wt = DP + (size_t)own_cap * HID;               // [(R+1)*32][32] transposed weights
-  float* stg_all = Wt + (size_t)(R + 1) * HID * HID;    // [nwarps][GN][SSmax]  | weight-grad tile | dW
+  float* Wt = DP + (size_t)own_cap * HID;               // [(R+1)*32][32] transposed weights, row-major
+  float* stg_all = Wt + (size_t)(R + 1) * HID * HID;    // [nwarps][GN][SSmax] | transposition scratch | tile + dW
   size_t stage_fl = (size_t)nwarps * GN * SSmax;        // must mirror bwd_smem()
   {
     const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;
     if (need > stage_fl) stage_fl = need;
+    const size_t need2 = (size_t)(R + 1) * HID * WP;
+    if (need2 > stage_fl) stage_fl = need2;
   }
   float* att_s = stg_all + stage_fl;
   float* invdeg = att_s + a4(R * NB);
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(dhid_s + L1O);   // [lcap]
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
   const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
@@ -416,13 +452,13 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   }
   const Keep K = make_keep(D, 1);
   const bool sym = A.symmetric != 0;
-  const int32_t* optr = sym ? A.in_ptr : A.out_ptr;
-  const uint32_t* oadj = sym ? A.in_adj : A.out_adj;
-  const int32_t* oeid = sym ? A.in_eid : A.out_eid;
   const Split own = own_range(n, rank, CL);
   const int n_own = own.hi - own.lo;
   const int tu = S.target[2 * g] - nb, ti = S.target[2 * g + 1] - nb;
   float* gp = gpart + ((size_t)g * CL + rank) * M.conv_param_count;
+  // out-lists of the own nodes (symmetric batches: the in-lists with mirrored edge ids)
+  const Lists Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb,
+                               own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap);
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
   const float dp = dpred[g];
@@ -472,37 +508,40 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     if (l > 0) {
       const float* bs = params + M.off_basis[l];
       const float* rt = params + M.off_root[l];
-      for (int idx = tid; idx < R * HID * HID; idx += NT) {   // Wt[(r*32+j)][k] = W_r[k][j]
+      float* Wp = stg_all;                                     // [(R+1)*32][WP]: W_r[k][j] rows (r*32+k), then root
+      for (int idx = tid; idx < R * HID * HID; idx += NT) {
         const int j = idx & 31, k = (idx >> 5) & 31, r = idx >> 10;
         float w = 0.f;
         for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bs[(b * HID + k) * HID + j], w);
-        Wt[wix(r * HID + j, k)] = w;
+        Wp[(r * HID + k) * WP + j] = w;
       }
-      for (int idx = tid; idx < HID * HID; idx += NT) {
-        const int j = idx & 31, k = idx >> 5;
-        Wt[wix(R * HID + j, k)] = rt[idx];
+      for (int idx = tid; idx < HID * HID; idx += NT) Wp[(R * HID + (idx >> 5)) * WP + (idx & 31)] = rt[idx];
+      __syncthreads();
+      for (int idx = tid; idx < (R + 1) * HID * HID; idx += NT) {   // Wt[(r*32+j)][k] = W_r[k][j]
+        const int k = idx & 31, j = (idx >> 5) & 31, r = idx >> 10;
+        Wt[idx] = Wp[(r * HID + k) * WP + j];
       }
       __syncthreads();
       for (int base = own.lo + warp * GN; base < own.hi; base += nwarps * GN) {
         const int cnt = min(GN, own.hi - base);
-        gather_group(oadj, oeid, optr, nb, base, cnt, K, sym, eb, m_half, lane, DPS, stg, SS, HID, R);
-        const int s = lane >> 2, c8 = (lane & 3) * 8;
+        if (Ls.lst) gather_group<true>(Ls, K, nb, base, cnt, lane, DPS, stg, SS, HID);
+        else gather_group<false>(Ls, K, nb, base, cnt, lane, DPS, stg, SS, HID);
+        const int s = lane >> 3, c4 = (lane & 7) * 4;
         const int u = base + min(s, cnt - 1);
-        float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        gemm_rows(stg + s * SS, K1, Wt, 0, c8, acc);
-        gemm_hrow(DP, u - own.lo, HID, Wt, K1, c8, acc);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        gemm_rows(stg + s * SS, K1, Wt, c4, acc);
+        gemm_hrow(DP, u - own.lo, HID, Wt + K1 * HID, c4, acc);
         if (s < cnt) {
           if (u == tu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += dfeat[(l - 1) * HID + c8 + j];
+            for (int j = 0; j < 4; ++j) acc[j] += dfeat[(l - 1) * HID + c4 + j];
           }
           if (u == ti) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] += dfeat[CW + (l - 1) * HID + c8 + j];
+            for (int j = 0; j < 4; ++j) acc[j] += dfeat[CW + (l - 1) * HID + c4 + j];
           }
-          float* gd = dstate + ((size_t)(l - 1) * S.node_cap + nb + u) * HID + c8;
-          __stcg(reinterpret_cast<float4*>(gd), make_float4(acc[0], acc[1], acc[2], acc[3]));
-          __stcg(reinterpret_cast<float4*>(gd + 4), make_float4(acc[4], acc[5], acc[6], acc[7]));
+          __stcg(reinterpret_cast<float4*>(dstate + ((size_t)(l - 1) * S.node_cap + nb + u) * HID + c4),
+                 make_float4(acc[0], acc[1], acc[2], acc[3]));
         }
         __syncwarp();
       }
@@ -514,23 +553,26 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     {
       const int KR = K1 + inp, TS = KR + 4;
       float* tile = stg_all;                       // [TW][TS]
-      float* dW = stg_all + TW * (SSmax + HID);    // [KR][32] (+ bias row), written after the loop
+      float* dW = stg_all + TW * (SSmax + HID);    // [KR][32], written after the loop
       const int c0 = (tid & 7) * 4, kg = tid >> 3, KG = NT >> 3;
-      const int nr = (KR + KG - 1) / KG;           // rows per thread (uniform): 3 for R=5 at 512 threads
+      const int nr = (KR + KG - 1) / KG;           // rows per thread (uniform): 2 for R=5 at 1024 threads
+#define IGMC_WGRAD(N_) wgrad<N_>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, \
+                                 gp + M.off_bias[l], c0, kg, KG, tid, NT)
       switch (nr) {
-        case 1: wgrad<1>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 2: wgrad<2>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 3: wgrad<3>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 4: wgrad<4>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 5: wgrad<5>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 6: wgrad<6>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 7: wgrad<7>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 8: wgrad<8>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 9: wgrad<9>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 10: wgrad<10>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        case 11: wgrad<11>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
-        default: wgrad<12>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, gp + M.off_bias[l], c0, kg, KG, tid, NT); break;
+        case 1: IGMC_WGRAD(1); break;
+        case 2: IGMC_WGRAD(2); break;
+        case 3: IGMC_WGRAD(3); break;
+        case 4: IGMC_WGRAD(4); break;
+        case 5: IGMC_WGRAD(5); break;
+        case 6: IGMC_WGRAD(6); break;
+        case 7: IGMC_WGRAD(7); break;
+        case 8: IGMC_WGRAD(8); break;
+        case 9: IGMC_WGRAD(9); break;
+        case 10: IGMC_WGRAD(10); break;
+        case 11: IGMC_WGRAD(11); break;
+        default: IGMC_WGRAD(12); break;
       }
+#undef IGMC_WGRAD
       __syncthreads();
       const float* bs = params + M.off_basis[l];
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
@@ -557,27 +599,26 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       __threadfence();
       cluster.sync();
     } else {
-      __threadfence_block();
       __syncthreads();
     }
   }
 }
 
-size_t fwd_smem(int n_cap, int R, int NB, int L, int nwarps) {
+size_t fwd_base_fl(int n_cap, int R, int L, int nwarps) {
   const size_t SSmax = (size_t)R * HID + 4, F = 2 * HID * L;
-  size_t fl = 2 * (size_t)n_cap * HID + (size_t)(R + 1) * HID * HID + (size_t)nwarps * GN * SSmax + a4(R * NB) + HID +
-              a4(n_cap) + a4((int)F) + L1O;
-  return fl * sizeof(float);
+  return 2 * (size_t)n_cap * HID + (size_t)(R + 1) * HID * HID + (size_t)nwarps * GN * SSmax + HID + a4(n_cap) +
+         a4((int)F) + L1O;
 }
-size_t bwd_smem(int n_cap, int R, int NB, int L, int nwarps, int CL) {
+size_t bwd_base_fl(int n_cap, int R, int NB, int L, int nwarps, int CL) {
   const size_t SSmax = (size_t)R * HID + 4, F = 2 * HID * L;
   const size_t own_cap = (size_t)(((n_cap + CL - 1) / CL + GN - 1) / GN * GN);
   size_t stage = (size_t)nwarps * GN * SSmax;
   const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;   // tile + dW
   if (need > stage) stage = need;
-  size_t fl = (size_t)n_cap * HID + own_cap * HID + (size_t)(R + 1) * HID * HID + stage + a4(R * NB) + a4(n_cap) +
-              a4((int)F) + L1O;
-  return fl * sizeof(float);
+  const size_t need2 = (size_t)(R + 1) * HID * WP;                                       // transposition scratch
+  if (need2 > stage) stage = need2;
+  return (size_t)n_cap * HID + own_cap * HID + (size_t)(R + 1) * HID * HID + stage + a4(R * NB) + a4(n_cap) +
+         a4((int)F) + L1O;
 }
 
 }  // namespace rs
@@ -585,15 +626,22 @@ size_t bwd_smem(int n_cap, int R, int NB, int L, int nwarps, int CL) {
 // ---- host-side dispatch helpers used by rgcn.cu's extern "C" entry points ----------------------------------
 int rs_supported(const igmc_model_t* M) { return M->num_relations <= rs::RS_MAX_R; }
 
-int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem) {
+// threads per CTA, dynamic shared memory and the edge-list staging capacity for a plan
+int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap) {
   const size_t limit = 227 * 1024;
-  for (int nt = 512; nt >= 128; nt >>= 1) {
-    const size_t b = backward ? rs::bwd_smem(n_cap, M->num_relations, M->num_bases, M->num_layers, nt >> 5, cluster)
-                              : rs::fwd_smem(n_cap, M->num_relations, M->num_bases, M->num_layers, nt >> 5);
+  const int KR = (M->num_relations + 1) * rs::HID;
+  for (int nt = 1024; nt >= 128; nt >>= 1) {
+    const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, M->num_relations, M->num_bases, M->num_layers, nt >> 5, cluster)
+                                      : rs::fwd_base_fl(n_cap, M->num_relations, M->num_layers, nt >> 5));
     // the weight-gradient mapping needs ceil(KR / (threads/8)) <= 12
-    const int KR = (M->num_relations + 1) * rs::HID;
     if (backward && (KR + (nt >> 3) - 1) / (nt >> 3) > 12) continue;
-    if (b <= limit) { *threads = nt; *smem = b; return 0; }
+    if (base + 4096 > limit) continue;
+    size_t lc = (limit - base) / 4;
+    if (lc > 16384) lc = 16384;
+    *threads = nt;
+    *lcap = (int)lc;
+    *smem = base + lc * 4;
+    return 0;
   }
   return -3;
 }
@@ -622,22 +670,22 @@ int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_l
                const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
                const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, int cluster,
                int* err, cudaStream_t st) {
-  int threads;
+  int threads, lcap;
   size_t smem;
-  int rc = rs_plan(M, n_cap, cluster, 0, &threads, &smem);
+  int rc = rs_plan(M, n_cap, cluster, 0, &threads, &smem, &lcap);
   if (rc) return rc;
   return launch_cluster(rs::k_forward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
-                        edge_ptr, *A, n_cap, *D, training, *S, y, loss_scale, dpred, sqerr, err);
+                        edge_ptr, *A, n_cap, lcap, *D, training, *S, y, loss_scale, dpred, sqerr, err);
 }
 
 int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                 const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
                 const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, float* dstate, int cluster,
                 int* err, cudaStream_t st) {
-  int threads;
+  int threads, lcap;
   size_t smem;
-  int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem);
+  int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem, &lcap);
   if (rc) return rc;
   return launch_cluster(rs::k_backward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
-                        edge_ptr, *A, n_cap, *D, *S, dpred, gpart, dhid, dstate, err);
+                        edge_ptr, *A, n_cap, lcap, *D, *S, dpred, gpart, dhid, dstate, err);
 }
