@@ -70,7 +70,7 @@ class Dropout(C.Structure):
 
 class Saved(C.Structure):
     _fields_ = [("states", vp), ("zsave", vp), ("inv_deg", vp), ("feat", vp), ("hid", vp),
-                ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp)]
+                ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp), ("wprep", vp)]
 
 
 _SIGS = {
@@ -86,6 +86,7 @@ _SIGS = {
                          C.c_float, vp, vp, vp, vp],
     "igmc_adam_step": [vp, vp, vp, vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                        C.c_float, vp],
+    "igmc_prep_weights": [C.POINTER(Model), vp, vp, vp],
     "igmc_build_info": [],
     "igmc_model_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int],
 }

@@ -590,6 +590,15 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
                 const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, float* dstate, int cluster,
                 int* err, cudaStream_t st);
 
+int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st);
+
+extern "C" int igmc_prep_weights(const igmc_model_t* M, const float* params, float* wprep, void* stream) {
+  int rc = check_model(M);
+  if (rc) return rc;
+  if (!rs_supported(M)) return -16;
+  return rs_prep_weights(M, params, wprep, (cudaStream_t)stream);
+}
+
 extern "C" int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, int backward) {
   int rc = check_model(M);
   if (rc) return rc;
@@ -616,6 +625,7 @@ extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const ui
   cudaStream_t st = (cudaStream_t)stream;
   if (cluster > 0) {
     if (!rs_supported(M)) return -16;
+    if (!S->wprep) return -17;
     return rs_forward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, training, S, y, loss_scale, dpred,
                       sqerr, cluster, err, st);
   }
@@ -645,7 +655,7 @@ extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const u
   cudaStream_t st = (cudaStream_t)stream;
   if (cluster > 0) {
     if (!rs_supported(M)) return -16;
-    if (!S->dstate) return -17;
+    if (!S->dstate || !S->wprep) return -17;
     return rs_backward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, dpred, gpart, dhid, S->dstate,
                        cluster, err, st);
   }

@@ -64,66 +64,127 @@ __device__ __forceinline__ uint32_t load_entry(const uint32_t* __restrict__ adj,
   return ent;
 }
 
-// The lists of the own nodes [lo,hi) are one contiguous range [e_lo, e_hi) of the adjacency array: stage it
-// in shared memory (dropout draws applied once) when it fits.
+// Edge lists of the own nodes [lo,hi): staged once per kernel in shared memory, dropped edges compacted out,
+// with block-local offsets lptr[0..n_own].  Falls back to the global arrays when they do not fit.
 struct Lists {
-  const uint32_t* adj;
+  const uint32_t* lst;   // staged entries (nullptr: not staged)
+  const int* lptr;       // [n_own+1] offsets into lst
+  const uint32_t* adj;   // global fallback
   const int32_t* eid;
-  const int32_t* ptr;   // global node offsets
-  const uint32_t* lst;  // staged entries or nullptr
-  int e_lo;
+  const int32_t* ptr;
   bool mirror;
   int eb, m_half;
 };
+
+// kept[] (optional, may be null) receives the kept entry count per own node.  Block-wide; ends with a barrier.
 __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t* eid, const int32_t* ptr, int nb, int lo,
                                              int hi, const Keep& K, bool mirror, int eb, int m_half, uint32_t* lbuf,
-                                             int lcap) {
+                                             int lcap, int* lptr, int* ws, float* invdeg_out, float* invdeg_glob) {
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+  const int n_own = hi - lo;
   Lists Ls;
   Ls.adj = adj; Ls.eid = eid; Ls.ptr = ptr; Ls.mirror = mirror; Ls.eb = eb; Ls.m_half = m_half;
-  Ls.e_lo = ptr[nb + lo];
-  const int cnt = ptr[nb + hi] - Ls.e_lo;
+  Ls.lptr = lptr;
+  // pass 1: kept count per node -> lptr[i+1] (count), degree
+  for (int i = warp; i < n_own; i += nwarps) {
+    const int p0 = ptr[nb + lo + i], p1 = ptr[nb + lo + i + 1];
+    int kept = p1 - p0;
+    if (K.active) {
+      kept = 0;
+      for (int p = p0 + lane; p < p1; p += 32) kept += load_entry(adj, eid, p, K, mirror, eb, m_half) != DROPPED;
+      kept = warp_sum_i(kept);
+    }
+    if (lane == 0) {
+      lptr[i + 1] = kept;
+      if (invdeg_out) {
+        const float id = 1.f / (float)max(kept, 1);
+        invdeg_out[lo + i] = id;
+        invdeg_glob[nb + lo + i] = id;
+      }
+    }
+  }
+  if (tid == 0) lptr[0] = 0;
+  __syncthreads();
+  // exclusive scan of the counts (in place: lptr[i+1] becomes the end offset of node i)
+  int running = 0;
+  for (int base = 0; base < n_own; base += NT) {
+    const int i = base + tid;
+    const int c = i < n_own ? lptr[i + 1] : 0;
+    int tot;
+    const int ex = block_excl_scan_i(c, ws, &tot);
+    if (i < n_own) lptr[i + 1] = running + ex + c;
+    running += tot;
+  }
+  __syncthreads();
+  const int total = n_own > 0 ? lptr[n_own] : 0;
   Ls.lst = nullptr;
-  if (cnt <= lcap) {
-    for (int i = threadIdx.x; i < cnt; i += blockDim.x) lbuf[i] = load_entry(adj, eid, Ls.e_lo + i, K, mirror, eb, m_half);
+  if (total <= lcap) {
+    // pass 2: compacted copy (warp per node, order preserved)
+    for (int i = warp; i < n_own; i += nwarps) {
+      const int p0 = ptr[nb + lo + i], p1 = ptr[nb + lo + i + 1];
+      int o = lptr[i];
+      for (int c = p0; c < p1; c += 32) {
+        const int p = c + lane;
+        uint32_t ent = DROPPED;
+        if (p < p1) ent = load_entry(adj, eid, p, K, mirror, eb, m_half);
+        const unsigned bal = __ballot_sync(IGMC_FULL, ent != DROPPED);
+        if (ent != DROPPED) lbuf[o + __popc(bal & ((1u << lane) - 1u))] = ent;
+        o += __popc(bal);
+      }
+    }
     Ls.lst = lbuf;
   }
+  __syncthreads();
   return Ls;
 }
 
-// Relation-space aggregate of the warp's nodes [base, base+cnt) (cnt <= GN) into its staging rows
-// stg[s][r*inp + k] (row stride SS): 8-lane group s walks node base+s, float4 per lane, next entry and
-// source row prefetched while the current one is accumulated.
-template <bool STAGED>
-__device__ __forceinline__ void gather_group(const Lists& Ls, const Keep& K, int nb, int base, int cnt, int lane,
-                                             const float* __restrict__ feat, float* __restrict__ stg, int SS, int inp) {
-  const int q = lane & 7, s = lane >> 3;
+// Relation-space aggregate of the warp's nodes [base, base+cnt) (cnt <= GN, base relative to the own range)
+// into its staging rows stg[s][r*inp + k] (row stride SS): 8-lane group s walks node base+s, float4 per lane.
+__device__ __forceinline__ void zero_stage(float* __restrict__ stg, int SS, int lane) {
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int i = lane * 4; i < GN * SS; i += 128) *reinterpret_cast<float4*>(stg + i) = z4;
   __syncwarp();
-  int p = 0, p1 = 0;
-  if (s < cnt) { p = Ls.ptr[nb + base + s]; p1 = Ls.ptr[nb + base + s + 1]; }
-  if ((4 * q) >= inp) p1 = p;                       // lanes beyond the feature width idle (layer 0)
-  float* row = stg + s * SS + 4 * q;
+}
+
+__device__ __forceinline__ void gather_staged(const uint32_t* __restrict__ lst, const int* __restrict__ lptr, int lbase,
+                                              int cnt, int lane, const float* __restrict__ feat,
+                                              float* __restrict__ stg, int SS, int inp) {
+  zero_stage(stg, SS, lane);
+  const int q = lane & 7, s = lane >> 3;
   const int fo = 4 * q;
-  auto entry = [&](int pp) -> uint32_t {
-    return STAGED ? Ls.lst[pp - Ls.e_lo] : load_entry(Ls.adj, Ls.eid, pp, K, Ls.mirror, Ls.eb, Ls.m_half);
-  };
-  uint32_t ent = p < p1 ? entry(p) : DROPPED;
-  float4 a = z4;
-  if (ent != DROPPED) a = *reinterpret_cast<const float4*>(feat + hix((int)(ent & 0xffffu), fo));
-  while (p < p1) {
-    const uint32_t nent = (p + 1 < p1) ? entry(p + 1) : DROPPED;
-    float4 na = z4;
-    if (nent != DROPPED) na = *reinterpret_cast<const float4*>(feat + hix((int)(nent & 0xffffu), fo));
-    if (ent != DROPPED) {
-      float4* d = reinterpret_cast<float4*>(row + (int)((ent >> 16) & 0xffu) * inp);
-      float4 t = *d;
-      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
-      *d = t;
-    }
-    ent = nent;
-    a = na;
-    ++p;
+  int p = 0, p1 = 0;
+  if (s < cnt && fo < inp) { p = lptr[lbase + s]; p1 = lptr[lbase + s + 1]; }
+  float* row = stg + s * SS + fo;
+  for (; p < p1; ++p) {
+    const uint32_t ent = lst[p];
+    const int src = (int)(ent & 0xffffu);
+    const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
+    float4* d = reinterpret_cast<float4*>(row + (int)(ent >> 16) * inp);
+    float4 t = *d;
+    t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    *d = t;
+  }
+  __syncwarp();
+}
+
+// fallback: lists read from global memory, dropout draws evaluated per edge
+__device__ __forceinline__ void gather_global(const Lists& Ls, const Keep& K, int nb, int gbase, int cnt, int lane,
+                                              const float* __restrict__ feat, float* __restrict__ stg, int SS, int inp) {
+  zero_stage(stg, SS, lane);
+  const int q = lane & 7, s = lane >> 3;
+  const int fo = 4 * q;
+  int p = 0, p1 = 0;
+  if (s < cnt && fo < inp) { p = Ls.ptr[nb + gbase + s]; p1 = Ls.ptr[nb + gbase + s + 1]; }
+  float* row = stg + s * SS + fo;
+  for (; p < p1; ++p) {
+    const uint32_t ent = load_entry(Ls.adj, Ls.eid, p, K, Ls.mirror, Ls.eb, Ls.m_half);
+    if (ent == DROPPED) continue;
+    const int src = (int)(ent & 0xffffu);
+    const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
+    float4* d = reinterpret_cast<float4*>(row + (int)((ent >> 16) & 0xffu) * inp);
+    float4 t = *d;
+    t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    *d = t;
   }
   __syncwarp();
 }
@@ -176,6 +237,60 @@ __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// per-step weight preparation:  wprep[l][0] = [W_r rows (r*inp+k) ; root rows] (forward, row-major [.][32]),
+//                               wprep[l][1] = [W_r^T rows (r*32+j) ; root^T rows] (backward, layers >= 1)
+// W_r = sum_b att[r,b] basis[b].  One small launch per step instead of R*NB global loads per element per CTA.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t wprep_slab(int R) { return (size_t)(R + 1) * HID * HID; }
+
+__global__ void __launch_bounds__(256)
+k_prep_weights(igmc_model_t M, const float* __restrict__ params, float* __restrict__ wprep) {
+  const int l = blockIdx.x >> 1, dir = blockIdx.x & 1;
+  const int R = M.num_relations, NB = M.num_bases;
+  const int in = l == 0 ? M.in_dim0 : HID, inp = a4(in);
+  const float* bs = params + M.off_basis[l];
+  const float* at = params + M.off_att[l];
+  const float* rt = params + M.off_root[l];
+  float* out = wprep + ((size_t)l * 2 + dir) * wprep_slab(R);
+  __shared__ float att_s[256];
+  for (int i = threadIdx.x; i < R * NB && i < 256; i += 256) att_s[i] = at[i];
+  __syncthreads();
+  if (dir == 0) {
+    const int K1 = R * inp;
+    for (int idx = threadIdx.x; idx < (K1 + inp) * HID; idx += 256) {
+      const int j = idx & 31, row = idx >> 5;
+      float w = 0.f;
+      if (row < K1) {
+        const int r = row / inp, k = row - r * inp;
+        if (k < in)
+          for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bs[(b * in + k) * HID + j], w);
+      } else {
+        const int k = row - K1;
+        if (k < in) w = rt[k * HID + j];
+      }
+      out[idx] = w;
+    }
+  } else if (l > 0) {
+    for (int idx = threadIdx.x; idx < (R + 1) * HID * HID; idx += 256) {   // out[(r*32+j)][k] = W_r[k][j]
+      const int k = idx & 31, j = (idx >> 5) & 31, r = idx >> 10;
+      float w = 0.f;
+      if (r < R) {
+        for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bs[(b * HID + k) * HID + j], w);
+      } else {
+        w = rt[k * HID + j];
+      }
+      out[idx] = w;
+    }
+  }
+}
+
+__device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __restrict__ src, int nfloats) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+  for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) d4[i] = __ldg(s4 + i);
+}
+
+// ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024, 1)
@@ -188,9 +303,10 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int g = blockIdx.x / CL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, NT = blockDim.x;
-  const int L = M.num_layers, R = M.num_relations, NB = M.num_bases, CW = HID * L, F = 2 * CW;
+  const int L = M.num_layers, R = M.num_relations, CW = HID * L, F = 2 * CW;
   const int in0 = M.in_dim0, in0p = a4(in0);
   const int SSmax = R * HID + 4;
+  const int own_cap = ((n_cap + CL - 1) / CL + GN - 1) / GN * GN;
   float* H = smem;                                   // [n_cap][32]
   float* Hn = H + (size_t)n_cap * HID;               // [n_cap][32]
   float* W = Hn + (size_t)n_cap * HID;               // [(R+1)*32][32] row-major
@@ -199,8 +315,10 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   float* invdeg = bias_s + HID;                      // [n_cap]
   float* feat_s = invdeg + a4(n_cap);
   float* hid_s = feat_s + a4(F);
-  uint32_t* lbuf = reinterpret_cast<uint32_t*>(hid_s + L1O);   // [lcap]
+  int* lptr = reinterpret_cast<int*>(hid_s + L1O);              // [own_cap+1]
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(lptr + a4(own_cap + 1));   // [lcap]
   __shared__ int s_t[2];
+  __shared__ int ws[34];
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
   const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
@@ -220,25 +338,9 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     if (c == 0 && lab == 0) atomicMin(&s_t[0], v);
     if (c == 0 && lab == 1) atomicMin(&s_t[1], v);
   }
-  const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap);
-  __syncthreads();
-  // kept in-degree of the own nodes (dropout_adj is applied once, models.py:193)
-  for (int v = own.lo + warp; v < own.hi; v += nwarps) {
-    const int p0 = A.in_ptr[nb + v], p1 = A.in_ptr[nb + v + 1];
-    int kept = p1 - p0;
-    if (K.active) {
-      kept = 0;
-      for (int p = p0 + lane; p < p1; p += 32)
-        kept += (Ls.lst ? Ls.lst[p - Ls.e_lo] : load_entry(A.in_adj, A.in_eid, p, K, false, eb, m_half)) != DROPPED;
-      kept = warp_sum_i(kept);
-    }
-    if (lane == 0) {
-      const float id = 1.f / (float)max(kept, 1);
-      invdeg[v] = id;
-      S.inv_deg[nb + v] = id;
-    }
-  }
-  __syncthreads();
+  // in-lists of the own nodes -> shared memory; kept in-degree (dropout_adj is applied once, models.py:193)
+  const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap,
+                               lptr, ws, invdeg, S.inv_deg);
   const int tu = s_t[0], ti = s_t[1];
   if (tu >= n || ti >= n) {
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
@@ -247,28 +349,16 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
 
   float* stg = stg_all + (size_t)warp * GN * SSmax;
   for (int l = 0; l < L; ++l) {
-    const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
+    const int inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, SS = K1 + 4;
-    // W rows r*inp+k = sum_b att[r,b] basis[b][k][:], then the root rows; zero rows for the k padding
-    {
-      const float* bs = params + M.off_basis[l];
-      const float* at = params + M.off_att[l];
-      const float* rt = params + M.off_root[l];
-      for (int idx = tid; idx < K1 * HID; idx += NT) {
-        const int j = idx & 31, row = idx >> 5, r = row / inp, k = row - r * inp;
-        float w = 0.f;
-        if (k < in)
-          for (int b = 0; b < NB; ++b) w = fmaf(at[r * NB + b], bs[(b * in + k) * HID + j], w);
-        W[idx] = w;
-      }
-      for (int idx = tid; idx < inp * HID; idx += NT) W[K1 * HID + idx] = (idx >> 5) < in ? rt[idx] : 0.f;
-      if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
-    }
+    copy_f4(W, S.wprep + (size_t)l * 2 * wprep_slab(R), (K1 + inp) * HID);
+    if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
     __syncthreads();
-    for (int base = own.lo + warp * GN; base < own.hi; base += nwarps * GN) {
+    for (int lb = warp * GN; lb < own.hi - own.lo; lb += nwarps * GN) {
+      const int base = own.lo + lb;
       const int cnt = min(GN, own.hi - base);
-      if (Ls.lst) gather_group<true>(Ls, K, nb, base, cnt, lane, H, stg, SS, inp);
-      else gather_group<false>(Ls, K, nb, base, cnt, lane, H, stg, SS, inp);
+      if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, lb, cnt, lane, H, stg, SS, inp);
+      else gather_global(Ls, K, nb, base, cnt, lane, H, stg, SS, inp);
       const int s = lane >> 3, c4 = (lane & 7) * 4;
       const int v = base + min(s, cnt - 1);
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -285,8 +375,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       if (S.zsave) {   // 1/deg-scaled aggregate, reused by the weight-gradient GEMM
         for (int s2 = 0; s2 < cnt; ++s2) {
           const float id2 = invdeg[base + s2];
-          float* zs = S.zsave + ((size_t)l * S.node_cap + nb + base + s2) * (size_t)(R * HID);
-          for (int kk = lane; kk < K1; kk += 32) zs[kk] = stg[s2 * SS + kk] * id2;
+          float4* zs = reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + base + s2) * (size_t)(R * HID));
+          const float4* src = reinterpret_cast<const float4*>(stg + s2 * SS);
+          for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) {
+            float4 t = src[k4];
+            t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
+            zs[k4] = t;
+          }
         }
       }
       __syncwarp();
@@ -357,42 +452,46 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
 }
 
-// K = n_own weight-gradient tile GEMM: thread owns rows {kg + i*KG, i < NR} x channels c0..c0+3 of
-// dW[kk][j] = sum_v A[v][kk] dpre[v][j];  A[v] = [saved 1/deg-scaled AGG | h_{l-1}[v]].  Result -> dW (shared),
-// d bias -> gbias (global).
-template <int NR>
+// K = n_own weight-gradient tile GEMM.  The block is cut into 256-thread slices that take every nsl-th node of
+// a tile; inside a slice a thread owns rows {kg + 32 i, i < NRW} x channels c0..c0+3 of
+//   dW[kk][j] = sum_v A[v][kk] dpre[v][j],   A[v] = [saved 1/deg-scaled AGG | h_{l-1}[v]].
+// Slices are summed into dW (shared) in slice order; d bias likewise into dB (shared).
+template <int NRW>
 __device__ __forceinline__ void wgrad(const igmc_saved_t& S, const uint8_t* __restrict__ node_label, int l, int nb,
                                       int lo, int n_own, int K1, int inp, int in0, int CW, int R, int TS, int KR,
-                                      float* __restrict__ tile, float* __restrict__ dW, const float* __restrict__ DP,
-                                      float* __restrict__ gbias, int c0, int kg, int KG, int tid, int NT) {
-  float acc[NR][4];
+                                      float* __restrict__ tile, float* __restrict__ dW, float* __restrict__ dB,
+                                      const float* __restrict__ DP) {
+  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+  const int nsl = NT >> 8, slice = tid >> 8, t = tid & 255;
+  const int c0 = (t & 7) * 4, kg = t >> 3;
+  float acc[NRW][4];
   float accb[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < NR; ++i)
+  for (int i = 0; i < NRW; ++i)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
   for (int t0 = 0; t0 < n_own; t0 += TW) {
     const int rows = min(TW, n_own - t0);
-    for (int idx = tid; idx < rows * K1; idx += NT) {
-      const int r_ = idx / K1, kk = idx - r_ * K1;
-      tile[r_ * TS + kk] = S.zsave[((size_t)l * S.node_cap + nb + lo + t0 + r_) * (size_t)(R * HID) + kk];
-    }
-    for (int idx = tid; idx < rows * inp; idx += NT) {
-      const int r_ = idx / inp, k = idx - r_ * inp;
+    for (int r_ = warp; r_ < rows; r_ += nwarps) {
       const int v = lo + t0 + r_;
-      float hv;
-      if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + k);
-      else hv = (k == (int)node_label[nb + v] && k < in0) ? 1.f : 0.f;
-      tile[r_ * TS + K1 + k] = hv;
+      const float4* src = reinterpret_cast<const float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID));
+      float4* dst = reinterpret_cast<float4*>(tile + r_ * TS);
+      for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) dst[k4] = src[k4];
+      if (lane < inp) {
+        float hv;
+        if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + lane);
+        else hv = (lane == (int)node_label[nb + v] && lane < in0) ? 1.f : 0.f;
+        tile[r_ * TS + K1 + lane] = hv;
+      }
     }
     __syncthreads();
-    for (int r_ = 0; r_ < rows; ++r_) {
+    for (int r_ = slice; r_ < rows; r_ += nsl) {
       const float4 d = *reinterpret_cast<const float4*>(DP + hix(t0 + r_, c0));
+      const float* arow = tile + r_ * TS + kg;
 #pragma unroll
-      for (int i = 0; i < NR; ++i) {
-        const int kk = kg + i * KG;
-        if (i < NR - 1 || kk < KR) {
-          const float a = tile[r_ * TS + kk];
+      for (int i = 0; i < NRW; ++i) {
+        if (i < NRW - 1 || kg + 32 * i < KR) {
+          const float a = arow[32 * i];
           acc[i][0] = fmaf(a, d.x, acc[i][0]); acc[i][1] = fmaf(a, d.y, acc[i][1]);
           acc[i][2] = fmaf(a, d.z, acc[i][2]); acc[i][3] = fmaf(a, d.w, acc[i][3]);
         }
@@ -401,13 +500,27 @@ __device__ __forceinline__ void wgrad(const igmc_saved_t& S, const uint8_t* __re
     }
     __syncthreads();
   }
+  for (int sl = 0; sl < nsl; ++sl) {
+    if (slice == sl) {
 #pragma unroll
-  for (int i = 0; i < NR; ++i) {
-    const int kk = kg + i * KG;
-    if (kk < KR)
-      *reinterpret_cast<float4*>(dW + kk * HID + c0) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+      for (int i = 0; i < NRW; ++i) {
+        const int kk = kg + 32 * i;
+        if (kk < KR) {
+          float4* o = reinterpret_cast<float4*>(dW + kk * HID + c0);
+          float4 v4 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+          if (sl > 0) { const float4 p4 = *o; v4.x += p4.x; v4.y += p4.y; v4.z += p4.z; v4.w += p4.w; }
+          *o = v4;
+        }
+      }
+      if (kg == 0) {
+        float4* o = reinterpret_cast<float4*>(dB + c0);
+        float4 v4 = make_float4(accb[0], accb[1], accb[2], accb[3]);
+        if (sl > 0) { const float4 p4 = *o; v4.x += p4.x; v4.y += p4.y; v4.z += p4.z; v4.w += p4.w; }
+        *o = v4;
+      }
+    }
+    __syncthreads();
   }
-  if (kg == 0) *reinterpret_cast<float4*>(gbias + c0) = make_float4(accb[0], accb[1], accb[2], accb[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -430,19 +543,19 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* DPS = smem;                                    // [n_cap][32]   dpre / deg   (all nodes)
   float* DP = DPS + (size_t)n_cap * HID;                // [own_cap][32] dpre         (own nodes)
   float* Wt = DP + (size_t)own_cap * HID;               // [(R+1)*32][32] transposed weights, row-major
-  float* stg_all = Wt + (size_t)(R + 1) * HID * HID;    // [nwarps][GN][SSmax] | transposition scratch | tile + dW
-  size_t stage_fl = (size_t)nwarps * GN * SSmax;        // must mirror bwd_smem()
+  float* stg_all = Wt + (size_t)(R + 1) * HID * HID;    // [nwarps][GN][SSmax] | tile + dW + dB
+  size_t stage_fl = (size_t)nwarps * GN * SSmax;        // must mirror bwd_base_fl()
   {
     const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;
     if (need > stage_fl) stage_fl = need;
-    const size_t need2 = (size_t)(R + 1) * HID * WP;
-    if (need2 > stage_fl) stage_fl = need2;
   }
   float* att_s = stg_all + stage_fl;
   float* invdeg = att_s + a4(R * NB);
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
-  uint32_t* lbuf = reinterpret_cast<uint32_t*>(dhid_s + L1O);   // [lcap]
+  int* lptr = reinterpret_cast<int*>(dhid_s + L1O);             // [own_cap+1]
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(lptr + a4(own_cap + 1));   // [lcap]
+  __shared__ int ws[34];
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
   const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
@@ -458,7 +571,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* gp = gpart + ((size_t)g * CL + rank) * M.conv_param_count;
   // out-lists of the own nodes (symmetric batches: the in-lists with mirrored edge ids)
   const Lists Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb,
-                               own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap);
+                               own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap, lptr, ws, nullptr, nullptr);
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
   const float dp = dpred[g];
@@ -473,6 +586,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     const float* W1 = params + M.off_lin1_w;
     for (int i = tid; i < F; i += NT) {
       float s = 0.f;
+#pragma unroll 8
       for (int o = 0; o < L1O; ++o) s = fmaf(W1[(size_t)o * F + i], dhid_s[o], s);
       dfeat[i] = s;
     }
@@ -482,50 +596,39 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* stg = stg_all + (size_t)warp * GN * SSmax;
   for (int l = L - 1; l >= 0; --l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
-    const int K1 = R * inp, SS = K1 + 4;
+    const int K1 = R * inp;
     // (0) d h_l of all nodes (top layer: readout rows only; below: exchanged through dstate),
     //     d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows
-    for (int idx = tid; idx < n * HID; idx += NT) {
-      const int v = idx >> 5, c = idx & 31;
-      float dh;
+    for (int idx = tid; idx < n * 8; idx += NT) {
+      const int v = idx >> 3, c4 = (idx & 7) * 4;
+      float4 dh;
       if (l == L - 1) {
-        dh = 0.f;
-        if (v == tu) dh += dfeat[l * HID + c];
-        if (v == ti) dh += dfeat[CW + l * HID + c];
+        dh = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (v == tu) { dh.x += dfeat[l * HID + c4]; dh.y += dfeat[l * HID + c4 + 1]; dh.z += dfeat[l * HID + c4 + 2]; dh.w += dfeat[l * HID + c4 + 3]; }
+        if (v == ti) { dh.x += dfeat[CW + l * HID + c4]; dh.y += dfeat[CW + l * HID + c4 + 1]; dh.z += dfeat[CW + l * HID + c4 + 2]; dh.w += dfeat[CW + l * HID + c4 + 3]; }
       } else {
-        dh = __ldcg(dstate + ((size_t)l * S.node_cap + nb + v) * HID + c);
+        dh = __ldcg(reinterpret_cast<const float4*>(dstate + ((size_t)l * S.node_cap + nb + v) * HID + c4));
       }
-      const float h = __ldcg(S.states + (size_t)(nb + v) * CW + l * HID + c);
-      const float dpre = dh * (1.f - h * h);
-      DPS[hix(v, c)] = dpre * invdeg[v];
-      if (v >= own.lo && v < own.hi) DP[hix(v - own.lo, c)] = dpre;
+      const float4 h = __ldcg(reinterpret_cast<const float4*>(S.states + (size_t)(nb + v) * CW + l * HID + c4));
+      const float4 dpre = make_float4(dh.x * (1.f - h.x * h.x), dh.y * (1.f - h.y * h.y), dh.z * (1.f - h.z * h.z),
+                                      dh.w * (1.f - h.w * h.w));
+      const float id = invdeg[v];
+      *reinterpret_cast<float4*>(DPS + hix(v, c4)) = make_float4(dpre.x * id, dpre.y * id, dpre.z * id, dpre.w * id);
+      if (v >= own.lo && v < own.hi) *reinterpret_cast<float4*>(DP + hix(v - own.lo, c4)) = dpre;
     }
     for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
+    if (l > 0) copy_f4(Wt, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), (R + 1) * HID * HID);
     __syncthreads();
 
     // (1) data gradient of the own nodes:  d h_{l-1}[u] = sum_r Q[u,r,:] W_r^T + dpre[u] root^T,
     //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)
     if (l > 0) {
-      const float* bs = params + M.off_basis[l];
-      const float* rt = params + M.off_root[l];
-      float* Wp = stg_all;                                     // [(R+1)*32][WP]: W_r[k][j] rows (r*32+k), then root
-      for (int idx = tid; idx < R * HID * HID; idx += NT) {
-        const int j = idx & 31, k = (idx >> 5) & 31, r = idx >> 10;
-        float w = 0.f;
-        for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bs[(b * HID + k) * HID + j], w);
-        Wp[(r * HID + k) * WP + j] = w;
-      }
-      for (int idx = tid; idx < HID * HID; idx += NT) Wp[(R * HID + (idx >> 5)) * WP + (idx & 31)] = rt[idx];
-      __syncthreads();
-      for (int idx = tid; idx < (R + 1) * HID * HID; idx += NT) {   // Wt[(r*32+j)][k] = W_r[k][j]
-        const int k = idx & 31, j = (idx >> 5) & 31, r = idx >> 10;
-        Wt[idx] = Wp[(r * HID + k) * WP + j];
-      }
-      __syncthreads();
-      for (int base = own.lo + warp * GN; base < own.hi; base += nwarps * GN) {
+      const int SS = K1 + 4;
+      for (int lb = warp * GN; lb < n_own; lb += nwarps * GN) {
+        const int base = own.lo + lb;
         const int cnt = min(GN, own.hi - base);
-        if (Ls.lst) gather_group<true>(Ls, K, nb, base, cnt, lane, DPS, stg, SS, HID);
-        else gather_group<false>(Ls, K, nb, base, cnt, lane, DPS, stg, SS, HID);
+        if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, lb, cnt, lane, DPS, stg, SS, HID);
+        else gather_global(Ls, K, nb, base, cnt, lane, DPS, stg, SS, HID);
         const int s = lane >> 3, c4 = (lane & 7) * 4;
         const int u = base + min(s, cnt - 1);
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -553,12 +656,11 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     {
       const int KR = K1 + inp, TS = KR + 4;
       float* tile = stg_all;                       // [TW][TS]
-      float* dW = stg_all + TW * (SSmax + HID);    // [KR][32], written after the loop
-      const int c0 = (tid & 7) * 4, kg = tid >> 3, KG = NT >> 3;
-      const int nr = (KR + KG - 1) / KG;           // rows per thread (uniform): 2 for R=5 at 1024 threads
-#define IGMC_WGRAD(N_) wgrad<N_>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, DP, \
-                                 gp + M.off_bias[l], c0, kg, KG, tid, NT)
-      switch (nr) {
+      float* dW = stg_all + TW * (SSmax + HID);    // [KR][32]
+      float* dB = dW + (size_t)(R + 1) * HID * HID;  // [32]
+      const int nrw = (KR + 31) >> 5;              // rows per thread (uniform): R+1 for the 32-wide layers
+#define IGMC_WGRAD(N_) wgrad<N_>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, dB, DP)
+      switch (nrw) {
         case 1: IGMC_WGRAD(1); break;
         case 2: IGMC_WGRAD(2); break;
         case 3: IGMC_WGRAD(3); break;
@@ -570,26 +672,26 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         case 9: IGMC_WGRAD(9); break;
         case 10: IGMC_WGRAD(10); break;
         case 11: IGMC_WGRAD(11); break;
-        default: IGMC_WGRAD(12); break;
+        case 12: IGMC_WGRAD(12); break;
+        default: IGMC_WGRAD(13); break;
       }
 #undef IGMC_WGRAD
-      __syncthreads();
       const float* bs = params + M.off_basis[l];
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
-      for (int idx = tid; idx < NB * in * HID; idx += NT) {
-        const int j = idx & 31, k = (idx >> 5) % in, b = (idx >> 5) / in;
+      for (int row = warp; row < NB * in; row += nwarps) {
+        const int b = row / in, k = row - b * in;
         float s = 0.f;
-        for (int r = 0; r < R; ++r) s = fmaf(att_s[r * NB + b], dW[(r * inp + k) * HID + j], s);
-        gp[M.off_basis[l] + idx] = s;
+        for (int r = 0; r < R; ++r) s = fmaf(att_s[r * NB + b], dW[(r * inp + k) * HID + lane], s);
+        gp[M.off_basis[l] + row * HID + lane] = s;
       }
-      // d root[k][j]
-      for (int idx = tid; idx < in * HID; idx += NT) gp[M.off_root[l] + idx] = dW[(K1 + (idx >> 5)) * HID + (idx & 31)];
+      // d root[k][j], d bias[j]
+      for (int idx = tid; idx < in * HID; idx += NT) gp[M.off_root[l] + idx] = dW[K1 * HID + idx];
+      if (tid < HID) gp[M.off_bias[l] + tid] = dB[tid];
       // d att[r,b] = < dW_r , basis[b] >   (warp per (r,b), fixed-order tree)
       for (int rb = warp; rb < R * NB; rb += nwarps) {
         const int r = rb / NB, b = rb - r * NB;
         float s = 0.f;
-        for (int idx = lane; idx < in * HID; idx += 32)
-          s = fmaf(dW[(r * inp + (idx >> 5)) * HID + (idx & 31)], bs[b * in * HID + idx], s);
+        for (int k = 0; k < in; ++k) s = fmaf(dW[(r * inp + k) * HID + lane], bs[(b * in + k) * HID + lane], s);
         s = warp_sum_f(s);
         if (lane == 0) gp[M.off_att[l] + rb] = s;
       }
@@ -604,21 +706,20 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   }
 }
 
-size_t fwd_base_fl(int n_cap, int R, int L, int nwarps) {
+size_t fwd_base_fl(int n_cap, int R, int L, int nwarps, int CL) {
   const size_t SSmax = (size_t)R * HID + 4, F = 2 * HID * L;
+  const size_t own_cap = (size_t)(((n_cap + CL - 1) / CL + GN - 1) / GN * GN);
   return 2 * (size_t)n_cap * HID + (size_t)(R + 1) * HID * HID + (size_t)nwarps * GN * SSmax + HID + a4(n_cap) +
-         a4((int)F) + L1O;
+         a4((int)F) + L1O + a4((int)own_cap + 1);
 }
 size_t bwd_base_fl(int n_cap, int R, int NB, int L, int nwarps, int CL) {
   const size_t SSmax = (size_t)R * HID + 4, F = 2 * HID * L;
   const size_t own_cap = (size_t)(((n_cap + CL - 1) / CL + GN - 1) / GN * GN);
   size_t stage = (size_t)nwarps * GN * SSmax;
-  const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;   // tile + dW
+  const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;   // tile + dW + dB
   if (need > stage) stage = need;
-  const size_t need2 = (size_t)(R + 1) * HID * WP;                                       // transposition scratch
-  if (need2 > stage) stage = need2;
   return (size_t)n_cap * HID + own_cap * HID + (size_t)(R + 1) * HID * HID + stage + a4(R * NB) + a4(n_cap) +
-         a4((int)F) + L1O;
+         a4((int)F) + L1O + a4((int)own_cap + 1);
 }
 
 }  // namespace rs
@@ -630,11 +731,13 @@ int rs_supported(const igmc_model_t* M) { return M->num_relations <= rs::RS_MAX_
 int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap) {
   const size_t limit = 227 * 1024;
   const int KR = (M->num_relations + 1) * rs::HID;
-  for (int nt = 1024; nt >= 128; nt >>= 1) {
+  for (int nt = 1024; nt >= 256; nt >>= 1) {
     const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, M->num_relations, M->num_bases, M->num_layers, nt >> 5, cluster)
-                                      : rs::fwd_base_fl(n_cap, M->num_relations, M->num_layers, nt >> 5));
-    // the weight-gradient mapping needs ceil(KR / (threads/8)) <= 12
-    if (backward && (KR + (nt >> 3) - 1) / (nt >> 3) > 12) continue;
+                                      : rs::fwd_base_fl(n_cap, M->num_relations, M->num_layers, nt >> 5, cluster));
+    // the weight-gradient slices are 256 threads wide and keep (R+1) x 4 accumulators per thread:
+    // 64 registers (1024 threads) are enough up to R = 7
+    if (nt < 256) continue;
+    if (backward && nt > 512 && KR > 8 * rs::HID) continue;
     if (base + 4096 > limit) continue;
     size_t lc = (limit - base) / 4;
     if (lc > 16384) lc = 16384;
@@ -688,4 +791,10 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
   if (rc) return rc;
   return launch_cluster(rs::k_backward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
                         edge_ptr, *A, n_cap, lcap, *D, *S, dpred, gpart, dhid, dstate, err);
+}
+
+int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st) {
+  rs::k_prep_weights<<<M->num_layers * 2, 256, 0, st>>>(*M, params, wprep);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e + 1000;
 }

@@ -169,6 +169,7 @@ class IGMC(nn.Module):
         self._layout, self._cmodel = layout, m
         self._ws = {}
         self._plans = {}
+        self._wprep = None
 
     def alias_grads(self):
         """point every ``p.grad`` at its slice of ``flat_grad`` (for stock torch optimizers)."""
@@ -240,7 +241,14 @@ class IGMC(nn.Module):
     def _saved_struct(self, ws, ncap):
         return _lib.Saved(ws["states"].data_ptr(), _lib.ptr(ws.get("zsave")), ws["inv_deg"].data_ptr(),
                           ws["feat"].data_ptr(), ws["hid"].data_ptr(), ws["hid_gscale"].data_ptr(),
-                          ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap, _lib.ptr(ws.get("dstate")))
+                          ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap, _lib.ptr(ws.get("dstate")),
+                          _lib.ptr(self._wprep_buf()) if ws["cluster"] > 0 else None)
+
+    def _wprep_buf(self):
+        if self._wprep is None or self._wprep.device != self.flat_params.device:
+            n = len(self.convs) * 2 * (self.num_relations + 1) * HID * HID
+            self._wprep = torch.zeros(n, dtype=torch.float32, device=self.flat_params.device)
+        return self._wprep
 
     def make_dropout(self, training, edge_keep=None, hidden_keep=None, seed=None, seed_dev=None):
         """dropout descriptor of one step (+ the tensors it references, to keep them alive)."""
@@ -271,6 +279,9 @@ class IGMC(nn.Module):
         ws = self._workspace(batch, training)
         S = self._saved_struct(ws, p["node_cap"])
         d, keep = drop
+        if ws["cluster"] > 0:   # W_r / W_r^T of the current parameters (one tiny launch per step)
+            _lib.check(lib.igmc_prep_weights(C.byref(self._cmodel), self.flat_params.data_ptr(),
+                                             self._wprep_buf().data_ptr(), _stream_ptr()), "igmc_prep_weights")
         _lib.check(lib.igmc_forward(C.byref(self._cmodel), self.flat_params.data_ptr(), p["node_label"].data_ptr(),
                                     p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
                                     batch.num_graphs, p["n_cap"], C.byref(d), int(training), C.byref(S),

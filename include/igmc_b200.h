@@ -155,7 +155,14 @@ typedef struct {
   int32_t* target;  /* [B*2] batch-global index of the target user / item node */
   int32_t node_cap; /* row count of one zsave / dstate layer slab */
   float* dstate;    /* [L * node_cap * 32] d h_l rows exchanged between the CTAs of a cluster (backward) */
+  const float* wprep; /* [L * 2 * (R+1)*32*32] per-step prepared weights (igmc_prep_weights), cluster plans only */
 } igmc_saved_t;
+
+/* W_r = sum_b att[r,b] basis[b] (and its transpose) for every layer, once per step, so that the
+ * per-subgraph CTAs only copy them into shared memory.  Required before igmc_forward / igmc_backward with
+ * cluster > 0 whenever the parameters changed (reference: the same product inside RGCNConv.message and the
+ * ARR term, train_eval.py:169-172). */
+int igmc_prep_weights(const igmc_model_t* M, const float* params, float* wprep, void* stream);
 
 /* Kernel plan.  `cluster` = 0 selects the generic kernels (csrc/rgcn.cu: one 256-thread CTA per
  * subgraph, any num_relations <= 256); 1/2/4 select the relation-space kernels (csrc/rgcn_rs.cu,
