@@ -227,6 +227,8 @@ __device__ __forceinline__ void gemm_hrow(const float* __restrict__ Hbuf, int v,
   }
 }
 
+#define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 32 + (i_)] = clock64(); } while (0)
+
 struct Split { int lo, hi; };
 __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
   const int per = ((n + CL - 1) / CL + GN - 1) / GN * GN;   // multiple of the warp group
@@ -328,6 +330,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   const Keep K = make_keep(D, training);
   const Split own = own_range(n, rank, CL);
+  IGMC_STAMP(0);
 
   if (tid == 0) { s_t[0] = 0x7fffffff; s_t[1] = 0x7fffffff; }
   __syncthreads();
@@ -348,12 +351,14 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
 
   float* stg = stg_all + (size_t)warp * GN * SSmax;
+  IGMC_STAMP(1);
   for (int l = 0; l < L; ++l) {
     const int inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, SS = K1 + 4;
     copy_f4(W, S.wprep + (size_t)l * 2 * wprep_slab(R), (K1 + inp) * HID);
     if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
     __syncthreads();
+    IGMC_STAMP(2 + 4 * l);
     for (int lb = warp * GN; lb < own.hi - own.lo; lb += nwarps * GN) {
       const int base = own.lo + lb;
       const int cnt = min(GN, own.hi - base);
@@ -386,6 +391,9 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       }
       __syncwarp();
     }
+    IGMC_STAMP(3 + 4 * l);
+    __syncthreads();
+    IGMC_STAMP(4 + 4 * l);
     // make the own rows visible to the other CTAs of the cluster, then fetch theirs
     if (CL > 1) {
       __threadfence();
@@ -398,6 +406,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       }
     }
     __syncthreads();
+    IGMC_STAMP(5 + 4 * l);
     float* t = H; H = Hn; Hn = t;
   }
 
@@ -450,6 +459,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       }
     }
   }
+  IGMC_STAMP(2 + 4 * L);
 }
 
 // K = n_own weight-gradient tile GEMM.  The block is cut into 256-thread slices that take every nsl-th node of
@@ -569,6 +579,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int n_own = own.hi - own.lo;
   const int tu = S.target[2 * g] - nb, ti = S.target[2 * g + 1] - nb;
   float* gp = gpart + ((size_t)g * CL + rank) * M.conv_param_count;
+  IGMC_STAMP(0);
   // out-lists of the own nodes (symmetric batches: the in-lists with mirrored edge ids)
   const Lists Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb,
                                own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap, lptr, ws, nullptr, nullptr);
@@ -594,9 +605,11 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   __syncthreads();
 
   float* stg = stg_all + (size_t)warp * GN * SSmax;
+  IGMC_STAMP(1);
   for (int l = L - 1; l >= 0; --l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
     const int K1 = R * inp;
+    const int sb = 2 + 5 * (L - 1 - l);
     // (0) d h_l of all nodes (top layer: readout rows only; below: exchanged through dstate),
     //     d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows
     for (int idx = tid; idx < n * 8; idx += NT) {
@@ -619,6 +632,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
     if (l > 0) copy_f4(Wt, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), (R + 1) * HID * HID);
     __syncthreads();
+    IGMC_STAMP(sb);
 
     // (1) data gradient of the own nodes:  d h_{l-1}[u] = sum_r Q[u,r,:] W_r^T + dpre[u] root^T,
     //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)
@@ -650,6 +664,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       }
       __syncthreads();
     }
+    IGMC_STAMP(sb + 1);
 
     // (2) weight gradients over the own nodes:  dW[kk][j] = sum_v A[v][kk] dpre[v][j]
     //     A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | h_{l-1}[v,k] ],   rows kk < KR = (R+1)*inp
@@ -676,6 +691,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         default: IGMC_WGRAD(13); break;
       }
 #undef IGMC_WGRAD
+      IGMC_STAMP(sb + 2);
       const float* bs = params + M.off_basis[l];
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
       for (int row = warp; row < NB * in; row += nwarps) {
@@ -696,6 +712,8 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         if (lane == 0) gp[M.off_att[l] + rb] = s;
       }
     }
+    __syncthreads();
+    IGMC_STAMP(sb + 3);
     // (3) d h_{l-1} rows are in dstate: publish to the cluster before the next layer reads them
     if (CL > 1) {
       __threadfence();
@@ -703,6 +721,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     } else {
       __syncthreads();
     }
+    IGMC_STAMP(sb + 4);
   }
 }
 

@@ -242,7 +242,8 @@ class IGMC(nn.Module):
         return _lib.Saved(ws["states"].data_ptr(), _lib.ptr(ws.get("zsave")), ws["inv_deg"].data_ptr(),
                           ws["feat"].data_ptr(), ws["hid"].data_ptr(), ws["hid_gscale"].data_ptr(),
                           ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap, _lib.ptr(ws.get("dstate")),
-                          _lib.ptr(self._wprep_buf()) if ws["cluster"] > 0 else None)
+                          _lib.ptr(self._wprep_buf()) if ws["cluster"] > 0 else None,
+                          _lib.ptr(getattr(self, "_prof_buf", None)))
 
     def _wprep_buf(self):
         if self._wprep is None or self._wprep.device != self.flat_params.device:

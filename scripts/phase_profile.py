@@ -1,0 +1,56 @@
+"""In-kernel phase timeline (clock64 stamps) of the cluster-plan forward / backward kernels."""
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from igmc_b200.data import make_synthetic_dataset
+from igmc_b200.models import IGMC
+from igmc_b200.util_functions import MyDynamicDataset
+
+ds = make_synthetic_dataset("ml_1m", seed=0)
+tu, tv, tl = ds["train"]
+d = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, 100, None, None, ds["class_values"])
+torch.manual_seed(1)
+m = IGMC(d, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=0.0).cuda()
+m.train()
+B = 50
+rng = np.random.default_rng(0)
+for plan in (2, 1):
+    m.kernel_plan = plan
+    m._plans.clear(); m._ws.clear()
+    grid = B * plan
+    m._prof_buf = torch.zeros(grid * 32, dtype=torch.int64, device="cuda")
+    for it in range(3):
+        b = d.extract_batch(rng.choice(len(tu), B, replace=False))
+        m._step += 1
+        drop = m.make_dropout(True)
+        m._prof_buf.zero_()
+        _, saved = m._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / B)
+        torch.cuda.synchronize()
+        f = m._prof_buf.view(grid, 32).cpu().numpy().copy()
+        m._prof_buf.zero_()
+        m._launch_backward(b, drop, saved, saved["ws"]["dpred"])
+        torch.cuda.synchronize()
+        bw = m._prof_buf.view(grid, 32).cpu().numpy().copy()
+    def show(name, a, labels):
+        a = a.astype(np.float64)
+        t0 = a[:, 0:1]
+        rel = (a - t0)
+        print("== %s plan=%d (cycles since kernel start, mean over CTAs that stamped; us at 1.965 GHz)" % (name, plan))
+        prev = 0.0
+        for i, lab in enumerate(labels):
+            col = rel[:, i]
+            ok = a[:, i] > 0
+            if not ok.any():
+                continue
+            mean = col[ok].mean()
+            print("  %-28s t=%9.0f cyc (%6.1f us)  +%8.0f   max=%9.0f" % (lab, mean, mean / 1965.0, mean - prev, col[ok].max()))
+            prev = mean
+    fl = ["start", "init+stage lists"]
+    for l in range(4):
+        fl += ["L%d weights copied" % l, "L%d groups done (thread0)" % l, "L%d block synced" % l, "L%d cluster exchanged" % l]
+    fl += ["readout done"]
+    show("forward", f, fl)
+    bl = ["start", "stage+readout bwd"]
+    for l in (3, 2, 1, 0):
+        bl += ["L%d dpre+Wt ready" % l, "L%d data-grad done" % l, "L%d wgrad done" % l, "L%d chain rule done" % l, "L%d cluster synced" % l]
+    show("backward", bw, bl)
