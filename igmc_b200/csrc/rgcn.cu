@@ -580,7 +580,7 @@ int check_model(const igmc_model_t* M) {
 
 // relation-space / cluster kernels (csrc/rgcn_rs.cu)
 int rs_supported(const igmc_model_t* M);
-int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap);
+int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap, int* chunk);
 int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
                const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, int cluster,
@@ -609,9 +609,9 @@ extern "C" int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, in
   }
   if (cluster != 1 && cluster != 2 && cluster != 4) return -15;
   if (!rs_supported(M)) return -16;
-  int threads, lcap;
+  int threads, lcap, chunk;
   size_t smem;
-  rc = rs_plan(M, n_cap, cluster, backward, &threads, &smem, &lcap);
+  rc = rs_plan(M, n_cap, cluster, backward, &threads, &smem, &lcap, &chunk);
   return rc ? rc : (int)smem;
 }
 

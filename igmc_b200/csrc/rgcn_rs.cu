@@ -189,45 +189,33 @@ __device__ __forceinline__ void gather_global(const Lists& Ls, const Keep& K, in
   __syncwarp();
 }
 
-// acc[j] (4 output channels c4..c4+3 of one node) += sum_kk a_row[kk] * W[kk][c4+j]; K multiple of 4,
-// W row-major [K][32]
-__device__ __forceinline__ void gemm_rows(const float* __restrict__ a_row, int K, const float* __restrict__ W, int c4,
-                                          float (&acc)[4]) {
-  const float* w = W + c4;
-#pragma unroll 2
-  for (int kk = 0; kk < K; kk += 4) {
-    const float4 a = *reinterpret_cast<const float4*>(a_row + kk);
-    const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * HID);
-    const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * HID);
-    const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * HID);
-    const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * HID);
-    acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.x, w0.y, acc[1]); acc[2] = fmaf(a.x, w0.z, acc[2]); acc[3] = fmaf(a.x, w0.w, acc[3]);
-    acc[0] = fmaf(a.y, w1.x, acc[0]); acc[1] = fmaf(a.y, w1.y, acc[1]); acc[2] = fmaf(a.y, w1.z, acc[2]); acc[3] = fmaf(a.y, w1.w, acc[3]);
-    acc[0] = fmaf(a.z, w2.x, acc[0]); acc[1] = fmaf(a.z, w2.y, acc[1]); acc[2] = fmaf(a.z, w2.z, acc[2]); acc[3] = fmaf(a.z, w2.w, acc[3]);
-    acc[0] = fmaf(a.w, w3.x, acc[0]); acc[1] = fmaf(a.w, w3.y, acc[1]); acc[2] = fmaf(a.w, w3.z, acc[2]); acc[3] = fmaf(a.w, w3.w, acc[3]);
-  }
+// ---- tensor-core tiles: mma.sync m16n8k8 TF32 with 3xTF32 error compensation (fp32-level accuracy) ----------
+// D(16x8) += A(16x8, row) * B(8x8, col).  lane: g = lane>>2, t = lane&3
+//   A: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4)   B: b0=(k=t,n=g) b1=(k=t+4,n=g)   D: d0=(g,2t) d1=(g,2t+1) d2=(g+8,2t) d3=(g+8,2t+1)
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
 }
-// same with the A operand taken from row v of a swizzled activation tile
-__device__ __forceinline__ void gemm_hrow(const float* __restrict__ Hbuf, int v, int K, const float* __restrict__ W,
-                                          int c4, float (&acc)[4]) {
-  const float* w = W + c4;
-  const float* hrow = Hbuf + (v << 5);
-  const int sw = (v & 7) << 2;
-#pragma unroll 2
-  for (int kk = 0; kk < K; kk += 4) {
-    const float4 a = *reinterpret_cast<const float4*>(hrow + (kk ^ sw));
-    const float4 w0 = *reinterpret_cast<const float4*>(w + (kk + 0) * HID);
-    const float4 w1 = *reinterpret_cast<const float4*>(w + (kk + 1) * HID);
-    const float4 w2 = *reinterpret_cast<const float4*>(w + (kk + 2) * HID);
-    const float4 w3 = *reinterpret_cast<const float4*>(w + (kk + 3) * HID);
-    acc[0] = fmaf(a.x, w0.x, acc[0]); acc[1] = fmaf(a.x, w0.y, acc[1]); acc[2] = fmaf(a.x, w0.z, acc[2]); acc[3] = fmaf(a.x, w0.w, acc[3]);
-    acc[0] = fmaf(a.y, w1.x, acc[0]); acc[1] = fmaf(a.y, w1.y, acc[1]); acc[2] = fmaf(a.y, w1.z, acc[2]); acc[3] = fmaf(a.y, w1.w, acc[3]);
-    acc[0] = fmaf(a.z, w2.x, acc[0]); acc[1] = fmaf(a.z, w2.y, acc[1]); acc[2] = fmaf(a.z, w2.z, acc[2]); acc[3] = fmaf(a.z, w2.w, acc[3]);
-    acc[0] = fmaf(a.w, w3.x, acc[0]); acc[1] = fmaf(a.w, w3.y, acc[1]); acc[2] = fmaf(a.w, w3.z, acc[2]); acc[3] = fmaf(a.w, w3.w, acc[3]);
-  }
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// x = hi + lo with hi, lo representable in tf32;  a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (small terms first)
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const float (&af)[4], const float (&bf)[2]) {
+  uint32_t ah[4], al[4], bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { ah[i] = f2tf32(af[i]); al[i] = f2tf32(af[i] - __uint_as_float(ah[i])); }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) { bh[i] = f2tf32(bf[i]); bl[i] = f2tf32(bf[i] - __uint_as_float(bh[i])); }
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
 }
 
-#define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 32 + (i_)] = clock64(); } while (0)
+__host__ __device__ __forceinline__ int a8(int x) { return (x + 7) & ~7; }
+__host__ __device__ __forceinline__ int a16(int x) { return (x + 15) & ~15; }
 
 struct Split { int lo, hi; };
 __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
@@ -237,52 +225,49 @@ __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
   s.hi = min(n, s.lo + per);
   return s;
 }
+__host__ __device__ __forceinline__ int own_cap_of(int n_cap, int CL) { return ((n_cap + CL - 1) / CL + GN - 1) / GN * GN; }
+
+#define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 32 + (i_)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// per-step weight preparation:  wprep[l][0] = [W_r rows (r*inp+k) ; root rows] (forward, row-major [.][32]),
-//                               wprep[l][1] = [W_r^T rows (r*32+j) ; root^T rows] (backward, layers >= 1)
-// W_r = sum_b att[r,b] basis[b].  One small launch per step instead of R*NB global loads per element per CTA.
+// per-step weight preparation.  slab(l, dir) = Bn[n][KS]  (n = output channel, KS = Ktot + 4):
+//   dir 0 (forward, B of  [AGG | h] . [W_r ; root]):   Bn[n][r*inp+k] = W_r[k][n],  Bn[n][K1p+k] = root[k][n]
+//   dir 1 (backward, B of [Q | dpre] . [W_r^T ; root^T], layers >= 1):  Bn[k][r*32+j] = W_r[k][j],  Bn[k][R*32+j] = root[k][j]
+// W_r = sum_b att[r,b] basis[b];  rows are n-major / K-contiguous so the mma B fragments load conflict-free.
 // ------------------------------------------------------------------------------------------------
-__host__ __device__ __forceinline__ size_t wprep_slab(int R) { return (size_t)(R + 1) * HID * HID; }
+__host__ __device__ __forceinline__ size_t wprep_slab(int R) { return (size_t)HID * ((size_t)(R + 1) * HID + 4); }
 
 __global__ void __launch_bounds__(256)
 k_prep_weights(igmc_model_t M, const float* __restrict__ params, float* __restrict__ wprep) {
   const int l = blockIdx.x >> 1, dir = blockIdx.x & 1;
   const int R = M.num_relations, NB = M.num_bases;
   const int in = l == 0 ? M.in_dim0 : HID, inp = a4(in);
+  const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), KS = K1p + inpp + 4;
   const float* bs = params + M.off_basis[l];
   const float* at = params + M.off_att[l];
   const float* rt = params + M.off_root[l];
   float* out = wprep + ((size_t)l * 2 + dir) * wprep_slab(R);
   __shared__ float att_s[256];
+  __shared__ float bas_s[IGMC_MAX_BASES * HID * HID];
   for (int i = threadIdx.x; i < R * NB && i < 256; i += 256) att_s[i] = at[i];
+  for (int i = threadIdx.x; i < NB * in * HID; i += 256) bas_s[i] = bs[i];
   __syncthreads();
-  if (dir == 0) {
-    const int K1 = R * inp;
-    for (int idx = threadIdx.x; idx < (K1 + inp) * HID; idx += 256) {
-      const int j = idx & 31, row = idx >> 5;
-      float w = 0.f;
-      if (row < K1) {
-        const int r = row / inp, k = row - r * inp;
-        if (k < in)
-          for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bs[(b * in + k) * HID + j], w);
-      } else {
-        const int k = row - K1;
-        if (k < in) w = rt[k * HID + j];
+  if (dir == 1 && l == 0) return;
+  for (int idx = threadIdx.x; idx < HID * KS; idx += 256) {
+    const int n = idx / KS, kk = idx - n * KS;
+    float w = 0.f;
+    if (kk < K1) {
+      const int r = kk / inp, q = kk - r * inp;
+      if (q < in) {
+        // dir 0: W_r[k=q][n] ; dir 1: W_r[k=n][j=q]
+        const int k = dir == 0 ? q : n, j = dir == 0 ? n : q;
+        for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bas_s[(b * in + k) * HID + j], w);
       }
-      out[idx] = w;
+    } else if (kk >= K1p && kk < K1p + inp) {
+      const int q = kk - K1p;
+      if (q < in) w = dir == 0 ? rt[q * HID + n] : rt[n * HID + q];
     }
-  } else if (l > 0) {
-    for (int idx = threadIdx.x; idx < (R + 1) * HID * HID; idx += 256) {   // out[(r*32+j)][k] = W_r[k][j]
-      const int k = idx & 31, j = (idx >> 5) & 31, r = idx >> 10;
-      float w = 0.f;
-      if (r < R) {
-        for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bs[(b * HID + k) * HID + j], w);
-      } else {
-        w = rt[k * HID + j];
-      }
-      out[idx] = w;
-    }
+    out[idx] = w;
   }
 }
 
@@ -298,8 +283,8 @@ __device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __
 __global__ void __launch_bounds__(1024, 1)
 k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
-             int lcap, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y, float loss_scale,
-             float* __restrict__ dpred, float* __restrict__ sqerr, int* err) {
+             int lcap, int chunk, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y,
+             float loss_scale, float* __restrict__ dpred, float* __restrict__ sqerr, int* err) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -307,13 +292,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, NT = blockDim.x;
   const int L = M.num_layers, R = M.num_relations, CW = HID * L, F = 2 * CW;
   const int in0 = M.in_dim0, in0p = a4(in0);
-  const int SSmax = R * HID + 4;
-  const int own_cap = ((n_cap + CL - 1) / CL + GN - 1) / GN * GN;
-  float* H = smem;                                   // [n_cap][32]
-  float* Hn = H + (size_t)n_cap * HID;               // [n_cap][32]
-  float* W = Hn + (size_t)n_cap * HID;               // [(R+1)*32][32] row-major
-  float* stg_all = W + (size_t)(R + 1) * HID * HID;  // [nwarps][GN][SSmax]
-  float* bias_s = stg_all + (size_t)nwarps * GN * SSmax;
+  const int SSmax = R * HID + 4, KSmax = (R + 1) * HID + 4;
+  const int own_cap = own_cap_of(n_cap, CL);
+  float* Hbuf0 = smem;                               // [n_cap][32]
+  float* Hbuf1 = Hbuf0 + (size_t)n_cap * HID;        // [n_cap][32]
+  float* Wn = Hbuf1 + (size_t)n_cap * HID;           // [32][KS]
+  float* stage = Wn + (size_t)HID * KSmax;           // [chunk][SSmax]
+  float* bias_s = stage + (size_t)chunk * SSmax;
   float* invdeg = bias_s + HID;                      // [n_cap]
   float* feat_s = invdeg + a4(n_cap);
   float* hid_s = feat_s + a4(F);
@@ -330,10 +315,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   const Keep K = make_keep(D, training);
   const Split own = own_range(n, rank, CL);
+  const int n_own = own.hi - own.lo;
   IGMC_STAMP(0);
 
   if (tid == 0) { s_t[0] = 0x7fffffff; s_t[1] = 0x7fffffff; }
   __syncthreads();
+  float* H = Hbuf0;
+  float* Hn = Hbuf1;
   for (int idx = tid; idx < n * HID; idx += NT) {
     const int v = idx >> 5, c = idx & 31;
     const int lab = node_label[nb + v];
@@ -349,77 +337,97 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
     return;
   }
-
-  float* stg = stg_all + (size_t)warp * GN * SSmax;
+  const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
   for (int l = 0; l < L; ++l) {
     const int inp = l == 0 ? in0p : HID;
-    const int K1 = R * inp, SS = K1 + 4;
-    copy_f4(W, S.wprep + (size_t)l * 2 * wprep_slab(R), (K1 + inp) * HID);
+    const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), SS = K1p + 4, KS = K1p + inpp + 4;
+    copy_f4(Wn, S.wprep + (size_t)l * 2 * wprep_slab(R), HID * KS);
     if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
     __syncthreads();
     IGMC_STAMP(2 + 4 * l);
-    for (int lb = warp * GN; lb < own.hi - own.lo; lb += nwarps * GN) {
-      const int base = own.lo + lb;
-      const int cnt = min(GN, own.hi - base);
-      if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, lb, cnt, lane, H, stg, SS, inp);
-      else gather_global(Ls, K, nb, base, cnt, lane, H, stg, SS, inp);
-      const int s = lane >> 3, c4 = (lane & 7) * 4;
-      const int v = base + min(s, cnt - 1);
-      float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      gemm_rows(stg + s * SS, K1, W, c4, acc);
-      const float id = invdeg[v];
-      acc[0] *= id; acc[1] *= id; acc[2] *= id; acc[3] *= id;
-      gemm_hrow(H, v, inp, W + K1 * HID, c4, acc);
-      if (s < cnt) {
-        const float4 o = make_float4(tanhf(acc[0] + bias_s[c4]), tanhf(acc[1] + bias_s[c4 + 1]),
-                                     tanhf(acc[2] + bias_s[c4 + 2]), tanhf(acc[3] + bias_s[c4 + 3]));
-        *reinterpret_cast<float4*>(Hn + hix(v, c4)) = o;
-        __stcg(reinterpret_cast<float4*>(S.states + (size_t)(nb + v) * CW + l * HID + c4), o);
-      }
-      if (S.zsave) {   // 1/deg-scaled aggregate, reused by the weight-gradient GEMM
+    for (int c0 = 0; c0 < n_own; c0 += chunk) {
+      const int crow = min(chunk, n_own - c0);
+      // ---- aggregate the chunk's nodes (warp = 4 nodes), scale by 1/deg, keep a copy for backward ----
+      for (int lb = warp * GN; lb < crow; lb += nwarps * GN) {
+        const int cnt = min(GN, crow - lb);
+        float* stg = stage + (size_t)lb * SS;
+        if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, c0 + lb, cnt, lane, H, stg, SS, inp);
+        else gather_global(Ls, K, nb, own.lo + c0 + lb, cnt, lane, H, stg, SS, inp);
         for (int s2 = 0; s2 < cnt; ++s2) {
-          const float id2 = invdeg[base + s2];
-          float4* zs = reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + base + s2) * (size_t)(R * HID));
-          const float4* src = reinterpret_cast<const float4*>(stg + s2 * SS);
+          const int v = own.lo + c0 + lb + s2;
+          const float id2 = invdeg[v];
+          float4* row = reinterpret_cast<float4*>(stg + s2 * SS);
+          float4* zs = S.zsave ? reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID))
+                               : nullptr;
           for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) {
-            float4 t = src[k4];
+            float4 t = row[k4];
             t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
-            zs[k4] = t;
+            row[k4] = t;
+            if (zs) zs[k4] = t;
           }
         }
       }
-      __syncwarp();
+      __syncthreads();
+      // ---- dense transform on tensor cores: out[16x8 tiles] = [AGG' | h] . [W_r ; root] ----
+      const int mt = (crow + 15) >> 4;
+      for (int tile = warp; tile < mt * 4; tile += nwarps) {
+        const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* a0p = stage + (size_t)(m0 + gq) * SS + tq;
+        const float* a1p = a0p + 8 * SS;
+        const float* bp = Wn + (size_t)(n0 + gq) * KS + tq;
+        for (int k0 = 0; k0 < K1p; k0 += 8) {
+          const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
+          const float bf[2] = {bp[k0], bp[k0 + 4]};
+          mma_3xtf32(d, af, bf);
+        }
+        const int r0 = c0 + m0 + gq, r1 = r0 + 8;           // rows relative to the own range
+        const int v0 = own.lo + min(r0, n_own - 1), v1 = own.lo + min(r1, n_own - 1);
+        const float* h0 = H + (v0 << 5);
+        const float* h1 = H + (v1 << 5);
+        const int sw0 = (v0 & 7) << 2, sw1 = (v1 & 7) << 2;
+        for (int k0 = 0; k0 < inpp; k0 += 8) {
+          const float af[4] = {h0[(k0 + tq) ^ sw0], h1[(k0 + tq) ^ sw1], h0[(k0 + tq + 4) ^ sw0], h1[(k0 + tq + 4) ^ sw1]};
+          const float bf[2] = {bp[K1p + k0], bp[K1p + k0 + 4]};
+          mma_3xtf32(d, af, bf);
+        }
+        const int cc = n0 + 2 * tq;
+        const float b0 = bias_s[cc], b1 = bias_s[cc + 1];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int r = half ? r1 : r0;
+          if (r < n_own) {
+            const int v = own.lo + r;
+            const float2 o = make_float2(tanhf(d[2 * half] + b0), tanhf(d[2 * half + 1] + b1));
+            const int off = hix(v, cc);
+            *reinterpret_cast<float2*>(Hn + off) = o;
+            for (int pr = 1; pr < CL; ++pr) {   // push the row slice to the other CTAs of the cluster (DSMEM)
+              float* peer = cluster.map_shared_rank(Hn, (rank + pr) % CL);
+              *reinterpret_cast<float2*>(peer + off) = o;
+            }
+            __stcg(reinterpret_cast<float2*>(S.states + (size_t)(nb + v) * CW + l * HID + cc), o);
+          }
+        }
+      }
+      __syncthreads();
     }
     IGMC_STAMP(3 + 4 * l);
-    __syncthreads();
-    IGMC_STAMP(4 + 4 * l);
-    // make the own rows visible to the other CTAs of the cluster, then fetch theirs
-    if (CL > 1) {
-      __threadfence();
-      cluster.sync();
-      for (int idx = tid; idx < n * 8; idx += NT) {
-        const int v = idx >> 3, c4 = (idx & 7) * 4;
-        if (v >= own.lo && v < own.hi) continue;
-        const float4 t = __ldcg(reinterpret_cast<const float4*>(S.states + (size_t)(nb + v) * CW + l * HID + c4));
-        *reinterpret_cast<float4*>(Hn + hix(v, c4)) = t;
-      }
-    }
-    __syncthreads();
+    if (CL > 1) cluster.sync();
     IGMC_STAMP(5 + 4 * l);
     float* t = H; H = Hn; Hn = t;
+    // concat_states rows of the two target nodes (models.py:203-207), all rows are local now
+    if (rank == 0 && tid < 2 * HID) {
+      const int node = tid < HID ? tu : ti, c = tid & 31;
+      feat_s[(tid < HID ? 0 : CW) + l * HID + c] = H[hix(node, c)];
+    }
   }
 
   if (rank != 0) return;
   // ---- readout (models.py:205-215), one CTA of the cluster ----
-  for (int c = tid; c < F; c += NT) {
-    const int node = c < CW ? tu : ti;
-    const float v = __ldcg(S.states + (size_t)(nb + node) * CW + (c < CW ? c : c - CW));
-    feat_s[c] = v;
-    S.feat[(size_t)g * F + c] = v;
-  }
-  if (tid == 0) { S.target[2 * g] = nb + tu; S.target[2 * g + 1] = nb + ti; }
   __syncthreads();
+  for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
+  if (tid == 0) { S.target[2 * g] = nb + tu; S.target[2 * g + 1] = nb + ti; }
   const float* W1 = params + M.off_lin1_w;
   for (int o = warp; o < L1O; o += nwarps) {
     float s = 0.f;
@@ -462,85 +470,16 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   IGMC_STAMP(2 + 4 * L);
 }
 
-// K = n_own weight-gradient tile GEMM.  The block is cut into 256-thread slices that take every nsl-th node of
-// a tile; inside a slice a thread owns rows {kg + 32 i, i < NRW} x channels c0..c0+3 of
-//   dW[kk][j] = sum_v A[v][kk] dpre[v][j],   A[v] = [saved 1/deg-scaled AGG | h_{l-1}[v]].
-// Slices are summed into dW (shared) in slice order; d bias likewise into dB (shared).
-template <int NRW>
-__device__ __forceinline__ void wgrad(const igmc_saved_t& S, const uint8_t* __restrict__ node_label, int l, int nb,
-                                      int lo, int n_own, int K1, int inp, int in0, int CW, int R, int TS, int KR,
-                                      float* __restrict__ tile, float* __restrict__ dW, float* __restrict__ dB,
-                                      const float* __restrict__ DP) {
-  const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
-  const int nsl = NT >> 8, slice = tid >> 8, t = tid & 255;
-  const int c0 = (t & 7) * 4, kg = t >> 3;
-  float acc[NRW][4];
-  float accb[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int i = 0; i < NRW; ++i)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
-  for (int t0 = 0; t0 < n_own; t0 += TW) {
-    const int rows = min(TW, n_own - t0);
-    for (int r_ = warp; r_ < rows; r_ += nwarps) {
-      const int v = lo + t0 + r_;
-      const float4* src = reinterpret_cast<const float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID));
-      float4* dst = reinterpret_cast<float4*>(tile + r_ * TS);
-      for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) dst[k4] = src[k4];
-      if (lane < inp) {
-        float hv;
-        if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + lane);
-        else hv = (lane == (int)node_label[nb + v] && lane < in0) ? 1.f : 0.f;
-        tile[r_ * TS + K1 + lane] = hv;
-      }
-    }
-    __syncthreads();
-    for (int r_ = slice; r_ < rows; r_ += nsl) {
-      const float4 d = *reinterpret_cast<const float4*>(DP + hix(t0 + r_, c0));
-      const float* arow = tile + r_ * TS + kg;
-#pragma unroll
-      for (int i = 0; i < NRW; ++i) {
-        if (i < NRW - 1 || kg + 32 * i < KR) {
-          const float a = arow[32 * i];
-          acc[i][0] = fmaf(a, d.x, acc[i][0]); acc[i][1] = fmaf(a, d.y, acc[i][1]);
-          acc[i][2] = fmaf(a, d.z, acc[i][2]); acc[i][3] = fmaf(a, d.w, acc[i][3]);
-        }
-      }
-      if (kg == 0) { accb[0] += d.x; accb[1] += d.y; accb[2] += d.z; accb[3] += d.w; }
-    }
-    __syncthreads();
-  }
-  for (int sl = 0; sl < nsl; ++sl) {
-    if (slice == sl) {
-#pragma unroll
-      for (int i = 0; i < NRW; ++i) {
-        const int kk = kg + 32 * i;
-        if (kk < KR) {
-          float4* o = reinterpret_cast<float4*>(dW + kk * HID + c0);
-          float4 v4 = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-          if (sl > 0) { const float4 p4 = *o; v4.x += p4.x; v4.y += p4.y; v4.z += p4.z; v4.w += p4.w; }
-          *o = v4;
-        }
-      }
-      if (kg == 0) {
-        float4* o = reinterpret_cast<float4*>(dB + c0);
-        float4 v4 = make_float4(accb[0], accb[1], accb[2], accb[3]);
-        if (sl > 0) { const float4 p4 = *o; v4.x += p4.x; v4.y += p4.y; v4.z += p4.z; v4.w += p4.w; }
-        *o = v4;
-      }
-    }
-    __syncthreads();
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
+constexpr int DPS_ = 40;   // row stride of the own-rows dpre copy (B operand of the weight-gradient tiles)
+
 __global__ void __launch_bounds__(1024, 1)
 k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
               const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
-              int lcap, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred, float* __restrict__ gpart,
-              float* __restrict__ dhid_out, float* __restrict__ dstate, int* err) {
+              int lcap, int chunk, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred,
+              float* __restrict__ gpart, float* __restrict__ dhid_out, int* err) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -548,22 +487,21 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, NT = blockDim.x;
   const int L = M.num_layers, R = M.num_relations, NB = M.num_bases, CW = HID * L, F = 2 * CW;
   const int in0 = M.in_dim0, in0p = a4(in0);
-  const int SSmax = R * HID + 4;
-  const int own_cap = ((n_cap + CL - 1) / CL + GN - 1) / GN * GN;
-  float* DPS = smem;                                    // [n_cap][32]   dpre / deg   (all nodes)
-  float* DP = DPS + (size_t)n_cap * HID;                // [own_cap][32] dpre         (own nodes)
-  float* Wt = DP + (size_t)own_cap * HID;               // [(R+1)*32][32] transposed weights, row-major
-  float* stg_all = Wt + (size_t)(R + 1) * HID * HID;    // [nwarps][GN][SSmax] | tile + dW + dB
-  size_t stage_fl = (size_t)nwarps * GN * SSmax;        // must mirror bwd_base_fl()
-  {
-    const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;
-    if (need > stage_fl) stage_fl = need;
-  }
-  float* att_s = stg_all + stage_fl;
+  const int SSmax = R * HID + 4, KSmax = (R + 1) * HID + 4, KRmax = (R + 1) * HID;
+  const int own_cap = own_cap_of(n_cap, CL), own_cap16 = a16(own_cap);
+  float* DH0 = smem;                                    // [2][n_cap][32]  d h_l of all nodes, double-buffered by layer
+  float* DH1 = DH0 + (size_t)n_cap * HID;               //   parity: peers push d h_{l-1} into one while the other, turned
+                                                        //   in place into dpre/deg (the gather source), is being read
+  float* DP = DH1 + (size_t)n_cap * HID;                // [own_cap16][DPS_] dpre of the own rows (zero padded)
+  float* Wn = DP + (size_t)own_cap16 * DPS_;            // [32][KS]
+  float* dW = Wn + (size_t)HID * KSmax;                 // [KRp][32]
+  float* stage = dW + (size_t)KRmax * HID;              // [chunk][SSmax]  |  weight-gradient tile [rows][TS]
+  float* att_s = stage + (size_t)chunk * SSmax;
   float* invdeg = att_s + a4(R * NB);
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
-  int* lptr = reinterpret_cast<int*>(dhid_s + L1O);             // [own_cap+1]
+  float* dB = dhid_s + L1O;                              // [32]
+  int* lptr = reinterpret_cast<int*>(dB + HID);          // [own_cap+1]
   uint32_t* lbuf = reinterpret_cast<uint32_t*>(lptr + a4(own_cap + 1));   // [lcap]
   __shared__ int ws[34];
 
@@ -603,94 +541,175 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     }
   }
   __syncthreads();
+  // d h_L : only the two target rows receive gradient from the readout
+  {
+    float* DHtop = ((L - 1) & 1) ? DH1 : DH0;
+    for (int idx = tid; idx < n * HID; idx += NT) {
+      const int v = idx >> 5, c = idx & 31;
+      float dh = 0.f;
+      if (v == tu) dh += dfeat[(L - 1) * HID + c];
+      if (v == ti) dh += dfeat[CW + (L - 1) * HID + c];
+      DHtop[hix(v, c)] = dh;
+    }
+  }
+  __syncthreads();
 
-  float* stg = stg_all + (size_t)warp * GN * SSmax;
+  const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
   for (int l = L - 1; l >= 0; --l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
-    const int K1 = R * inp;
+    const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), KRp = K1p + inpp;
     const int sb = 2 + 5 * (L - 1 - l);
-    // (0) d h_l of all nodes (top layer: readout rows only; below: exchanged through dstate),
-    //     d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows
+    float* DPS = (l & 1) ? DH1 : DH0;                    // d h_l on entry, dpre/deg after step (0)
+    float* DHn = (l & 1) ? DH0 : DH1;                    // d h_{l-1} (written here and by the peers)
+    // (0) d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows (padded with zeros)
     for (int idx = tid; idx < n * 8; idx += NT) {
       const int v = idx >> 3, c4 = (idx & 7) * 4;
-      float4 dh;
-      if (l == L - 1) {
-        dh = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (v == tu) { dh.x += dfeat[l * HID + c4]; dh.y += dfeat[l * HID + c4 + 1]; dh.z += dfeat[l * HID + c4 + 2]; dh.w += dfeat[l * HID + c4 + 3]; }
-        if (v == ti) { dh.x += dfeat[CW + l * HID + c4]; dh.y += dfeat[CW + l * HID + c4 + 1]; dh.z += dfeat[CW + l * HID + c4 + 2]; dh.w += dfeat[CW + l * HID + c4 + 3]; }
-      } else {
-        dh = __ldcg(reinterpret_cast<const float4*>(dstate + ((size_t)l * S.node_cap + nb + v) * HID + c4));
-      }
+      const float4 dh = *reinterpret_cast<const float4*>(DPS + hix(v, c4));
       const float4 h = __ldcg(reinterpret_cast<const float4*>(S.states + (size_t)(nb + v) * CW + l * HID + c4));
       const float4 dpre = make_float4(dh.x * (1.f - h.x * h.x), dh.y * (1.f - h.y * h.y), dh.z * (1.f - h.z * h.z),
                                       dh.w * (1.f - h.w * h.w));
       const float id = invdeg[v];
       *reinterpret_cast<float4*>(DPS + hix(v, c4)) = make_float4(dpre.x * id, dpre.y * id, dpre.z * id, dpre.w * id);
-      if (v >= own.lo && v < own.hi) *reinterpret_cast<float4*>(DP + hix(v - own.lo, c4)) = dpre;
+      if (v >= own.lo && v < own.hi) *reinterpret_cast<float4*>(DP + (size_t)(v - own.lo) * DPS_ + c4) = dpre;
+    }
+    for (int idx = tid; idx < (a16(n_own) - n_own) * 8; idx += NT) {
+      const int r = n_own + (idx >> 3), c4 = (idx & 7) * 4;
+      *reinterpret_cast<float4*>(DP + (size_t)r * DPS_ + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
-    if (l > 0) copy_f4(Wt, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), (R + 1) * HID * HID);
+    if (l > 0) copy_f4(Wn, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), HID * (KRp + 4));
     __syncthreads();
     IGMC_STAMP(sb);
 
-    // (1) data gradient of the own nodes:  d h_{l-1}[u] = sum_r Q[u,r,:] W_r^T + dpre[u] root^T,
-    //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)
+    // (1) data gradient of the own nodes:  d h_{l-1}[u] = [Q[u] | dpre[u]] . [W_r^T ; root^T],
+    //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)         -> pushed to every CTA's DH
     if (l > 0) {
-      const int SS = K1 + 4;
-      for (int lb = warp * GN; lb < n_own; lb += nwarps * GN) {
-        const int base = own.lo + lb;
-        const int cnt = min(GN, own.hi - base);
-        if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, lb, cnt, lane, DPS, stg, SS, HID);
-        else gather_global(Ls, K, nb, base, cnt, lane, DPS, stg, SS, HID);
-        const int s = lane >> 3, c4 = (lane & 7) * 4;
-        const int u = base + min(s, cnt - 1);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        gemm_rows(stg + s * SS, K1, Wt, c4, acc);
-        gemm_hrow(DP, u - own.lo, HID, Wt + K1 * HID, c4, acc);
-        if (s < cnt) {
-          if (u == tu) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] += dfeat[(l - 1) * HID + c4 + j];
-          }
-          if (u == ti) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] += dfeat[CW + (l - 1) * HID + c4 + j];
-          }
-          __stcg(reinterpret_cast<float4*>(dstate + ((size_t)(l - 1) * S.node_cap + nb + u) * HID + c4),
-                 make_float4(acc[0], acc[1], acc[2], acc[3]));
+      const int SS = K1p + 4, KS = KRp + 4;
+      for (int c0 = 0; c0 < n_own; c0 += chunk) {
+        const int crow = min(chunk, n_own - c0);
+        for (int lb = warp * GN; lb < crow; lb += nwarps * GN) {
+          const int cnt = min(GN, crow - lb);
+          float* stg = stage + (size_t)lb * SS;
+          if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, c0 + lb, cnt, lane, DPS, stg, SS, HID);
+          else gather_global(Ls, K, nb, own.lo + c0 + lb, cnt, lane, DPS, stg, SS, HID);
         }
-        __syncwarp();
+        __syncthreads();
+        const int mt = (crow + 15) >> 4;
+        for (int tile = warp; tile < mt * 4; tile += nwarps) {
+          const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
+          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          const float* a0p = stage + (size_t)(m0 + gq) * SS + tq;
+          const float* a1p = a0p + 8 * SS;
+          const float* bp = Wn + (size_t)(n0 + gq) * KS + tq;
+          for (int k0 = 0; k0 < K1p; k0 += 8) {
+            const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
+            const float bf[2] = {bp[k0], bp[k0 + 4]};
+            mma_3xtf32(d, af, bf);
+          }
+          const int r0 = c0 + m0 + gq, r1 = r0 + 8;
+          const float* p0 = DP + (size_t)min(r0, own_cap16 - 1) * DPS_ + tq;
+          const float* p1 = DP + (size_t)min(r1, own_cap16 - 1) * DPS_ + tq;
+          for (int k0 = 0; k0 < HID; k0 += 8) {
+            const float af[4] = {p0[k0], p1[k0], p0[k0 + 4], p1[k0 + 4]};
+            const float bf[2] = {bp[K1p + k0], bp[K1p + k0 + 4]};
+            mma_3xtf32(d, af, bf);
+          }
+          const int cc = n0 + 2 * tq;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int r = half ? r1 : r0;
+            if (r < n_own) {
+              const int u = own.lo + r;
+              float2 o = make_float2(d[2 * half], d[2 * half + 1]);
+              if (u == tu) { o.x += dfeat[(l - 1) * HID + cc]; o.y += dfeat[(l - 1) * HID + cc + 1]; }
+              if (u == ti) { o.x += dfeat[CW + (l - 1) * HID + cc]; o.y += dfeat[CW + (l - 1) * HID + cc + 1]; }
+              const int off = hix(u, cc);
+              *reinterpret_cast<float2*>(DHn + off) = o;
+              for (int pr = 1; pr < CL; ++pr) {
+                float* peer = cluster.map_shared_rank(DHn, (rank + pr) % CL);
+                *reinterpret_cast<float2*>(peer + off) = o;
+              }
+            }
+          }
+        }
+        __syncthreads();
       }
-      __syncthreads();
     }
     IGMC_STAMP(sb + 1);
 
-    // (2) weight gradients over the own nodes:  dW[kk][j] = sum_v A[v][kk] dpre[v][j]
-    //     A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | h_{l-1}[v,k] ],   rows kk < KR = (R+1)*inp
+    // (2) weight gradients over the own nodes on tensor cores:  dW[kk][j] = sum_v A[v][kk] dpre[v][j]
+    //     A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | h_{l-1}[v,k] ]  ->  M = KRp rows, N = 32, K = own nodes
     {
-      const int KR = K1 + inp, TS = KR + 4;
-      float* tile = stg_all;                       // [TW][TS]
-      float* dW = stg_all + TW * (SSmax + HID);    // [KR][32]
-      float* dB = dW + (size_t)(R + 1) * HID * HID;  // [32]
-      const int nrw = (KR + 31) >> 5;              // rows per thread (uniform): R+1 for the 32-wide layers
-#define IGMC_WGRAD(N_) wgrad<N_>(S, node_label, l, nb, own.lo, n_own, K1, inp, in0, CW, R, TS, KR, tile, dW, dB, DP)
-      switch (nrw) {
-        case 1: IGMC_WGRAD(1); break;
-        case 2: IGMC_WGRAD(2); break;
-        case 3: IGMC_WGRAD(3); break;
-        case 4: IGMC_WGRAD(4); break;
-        case 5: IGMC_WGRAD(5); break;
-        case 6: IGMC_WGRAD(6); break;
-        case 7: IGMC_WGRAD(7); break;
-        case 8: IGMC_WGRAD(8); break;
-        case 9: IGMC_WGRAD(9); break;
-        case 10: IGMC_WGRAD(10); break;
-        case 11: IGMC_WGRAD(11); break;
-        case 12: IGMC_WGRAD(12); break;
-        default: IGMC_WGRAD(13); break;
+      const int TS = KRp + 8;                              // tile row stride (== 8 mod 32: conflict-free A^T frags)
+      int trows = (int)(((size_t)chunk * SSmax) / TS) & ~7;   // node rows of one tile pass
+      if (trows > a8(n_own)) trows = a8(n_own);
+      const int mtiles = KRp >> 4;                          // KRp is a multiple of 8; odd multiples handled below
+      const int mt = (KRp + 15) >> 4;
+      (void)mtiles;
+      // accumulators live across node passes: tile list per warp is fixed (<= 2 tiles per warp for R <= 7 at 32 warps)
+      constexpr int MAXT = 4;
+      float acc[MAXT][4];
+#pragma unroll
+      for (int i = 0; i < MAXT; ++i)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+      float accb = 0.f;
+      for (int t0 = 0; t0 < a8(n_own) && trows > 0; t0 += trows) {
+        const int rows = min(trows, a8(n_own) - t0);        // multiple of 8, rows beyond n_own are zero
+        for (int r_ = warp; r_ < rows; r_ += nwarps) {
+          const int v = own.lo + t0 + r_;
+          float* dst = stage + (size_t)r_ * TS;
+          if (t0 + r_ < n_own) {
+            const float4* src = reinterpret_cast<const float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID));
+            for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) reinterpret_cast<float4*>(dst)[k4] = src[k4];
+            for (int kk = K1 + lane; kk < K1p; kk += 32) dst[kk] = 0.f;
+            if (lane < inpp) {
+              float hv = 0.f;
+              if (lane < in) {
+                if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + lane);
+                else hv = (lane == (int)node_label[nb + v]) ? 1.f : 0.f;
+              }
+              dst[K1p + lane] = hv;
+            }
+          } else {
+            for (int kk = lane; kk < KRp; kk += 32) dst[kk] = 0.f;
+          }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < MAXT; ++i) {
+          const int tile = warp + i * nwarps;
+          if (tile < mt * 4) {
+            const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
+            // A^T fragment: row = kk (m0+g), col = node (k0+t);  B: k = node, n = channel
+            const bool hi_ok = (m0 + 8) < KRp;               // KRp may be an odd multiple of 8
+            const float* ap = stage + (size_t)tq * TS + m0 + gq;
+            const float* bp = DP + (size_t)(t0 + tq) * DPS_ + n0 + gq;
+            for (int k0 = 0; k0 < rows; k0 += 8) {
+              const float* a = ap + (size_t)k0 * TS;
+              const float af[4] = {a[0], hi_ok ? a[8] : 0.f, a[4 * TS], hi_ok ? a[4 * TS + 8] : 0.f};
+              const float bf[2] = {bp[(size_t)k0 * DPS_], bp[(size_t)(k0 + 4) * DPS_]};
+              mma_3xtf32(acc[i], af, bf);
+            }
+          }
+        }
+        if (warp == nwarps - 1) {   // d bias: column sums of dpre over the pass (lane = channel)
+          for (int r_ = 0; r_ < rows; ++r_) accb += DP[(size_t)(t0 + r_) * DPS_ + lane];
+        }
+        __syncthreads();
       }
-#undef IGMC_WGRAD
+#pragma unroll
+      for (int i = 0; i < MAXT; ++i) {
+        const int tile = warp + i * nwarps;
+        if (tile < mt * 4) {
+          const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3, cc = n0 + 2 * tq;
+          *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq) * HID + cc) = make_float2(acc[i][0], acc[i][1]);
+          if (m0 + 8 < KRp) *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq + 8) * HID + cc) = make_float2(acc[i][2], acc[i][3]);
+        }
+      }
+      if (warp == nwarps - 1) dB[lane] = accb;
+      __syncthreads();
       IGMC_STAMP(sb + 2);
       const float* bs = params + M.off_basis[l];
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
@@ -701,7 +720,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         gp[M.off_basis[l] + row * HID + lane] = s;
       }
       // d root[k][j], d bias[j]
-      for (int idx = tid; idx < in * HID; idx += NT) gp[M.off_root[l] + idx] = dW[K1 * HID + idx];
+      for (int idx = tid; idx < in * HID; idx += NT) gp[M.off_root[l] + idx] = dW[K1p * HID + idx];
       if (tid < HID) gp[M.off_bias[l] + tid] = dB[tid];
       // d att[r,b] = < dW_r , basis[b] >   (warp per (r,b), fixed-order tree)
       for (int rb = warp; rb < R * NB; rb += nwarps) {
@@ -714,31 +733,22 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     }
     __syncthreads();
     IGMC_STAMP(sb + 3);
-    // (3) d h_{l-1} rows are in dstate: publish to the cluster before the next layer reads them
-    if (CL > 1) {
-      __threadfence();
-      cluster.sync();
-    } else {
-      __syncthreads();
-    }
+    // (3) every CTA's DH now holds d h_{l-1} of all nodes once the pushes have landed
+    if (CL > 1) cluster.sync();
     IGMC_STAMP(sb + 4);
   }
 }
 
-size_t fwd_base_fl(int n_cap, int R, int L, int nwarps, int CL) {
-  const size_t SSmax = (size_t)R * HID + 4, F = 2 * HID * L;
-  const size_t own_cap = (size_t)(((n_cap + CL - 1) / CL + GN - 1) / GN * GN);
-  return 2 * (size_t)n_cap * HID + (size_t)(R + 1) * HID * HID + (size_t)nwarps * GN * SSmax + HID + a4(n_cap) +
-         a4((int)F) + L1O + a4((int)own_cap + 1);
+size_t fwd_base_fl(int n_cap, int R, int L, int CL) {   // everything except the stage rows and the list buffer
+  const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;
+  const size_t own_cap = (size_t)own_cap_of(n_cap, CL);
+  return 2 * (size_t)n_cap * HID + HID * KSmax + HID + a4(n_cap) + a4((int)F) + L1O + a4((int)own_cap + 1);
 }
-size_t bwd_base_fl(int n_cap, int R, int NB, int L, int nwarps, int CL) {
-  const size_t SSmax = (size_t)R * HID + 4, F = 2 * HID * L;
-  const size_t own_cap = (size_t)(((n_cap + CL - 1) / CL + GN - 1) / GN * GN);
-  size_t stage = (size_t)nwarps * GN * SSmax;
-  const size_t need = (size_t)TW * (SSmax + HID) + ((size_t)(R + 1) * HID + 1) * HID;   // tile + dW + dB
-  if (need > stage) stage = need;
-  return (size_t)n_cap * HID + own_cap * HID + (size_t)(R + 1) * HID * HID + stage + a4(R * NB) + a4(n_cap) +
-         a4((int)F) + L1O + a4((int)own_cap + 1);
+size_t bwd_base_fl(int n_cap, int R, int NB, int L, int CL) {
+  const size_t KSmax = (size_t)(R + 1) * HID + 4, KRmax = (size_t)(R + 1) * HID, F = 2 * HID * L;
+  const size_t own_cap = (size_t)own_cap_of(n_cap, CL), own_cap16 = (size_t)a16((int)own_cap);
+  return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + KRmax * HID + a4(R * NB) + a4(n_cap) +
+         a4((int)F) + L1O + HID + a4((int)own_cap + 1);
 }
 
 }  // namespace rs
@@ -746,26 +756,31 @@ size_t bwd_base_fl(int n_cap, int R, int NB, int L, int nwarps, int CL) {
 // ---- host-side dispatch helpers used by rgcn.cu's extern "C" entry points ----------------------------------
 int rs_supported(const igmc_model_t* M) { return M->num_relations <= rs::RS_MAX_R; }
 
-// threads per CTA, dynamic shared memory and the edge-list staging capacity for a plan
-int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap) {
+// threads per CTA, dynamic shared memory, stage chunk rows and edge-list staging capacity for a plan
+int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap, int* chunk) {
   const size_t limit = 227 * 1024;
-  const int KR = (M->num_relations + 1) * rs::HID;
-  for (int nt = 1024; nt >= 256; nt >>= 1) {
-    const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, M->num_relations, M->num_bases, M->num_layers, nt >> 5, cluster)
-                                      : rs::fwd_base_fl(n_cap, M->num_relations, M->num_layers, nt >> 5, cluster));
-    // the weight-gradient slices are 256 threads wide and keep (R+1) x 4 accumulators per thread:
-    // 64 registers (1024 threads) are enough up to R = 7
-    if (nt < 256) continue;
-    if (backward && nt > 512 && KR > 8 * rs::HID) continue;
-    if (base + 4096 > limit) continue;
-    size_t lc = (limit - base) / 4;
-    if (lc > 16384) lc = 16384;
-    *threads = nt;
-    *lcap = (int)lc;
-    *smem = base + lc * 4;
-    return 0;
-  }
-  return -3;
+  const int R = M->num_relations;
+  const size_t SSmax = (size_t)R * rs::HID + 4;
+  const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, R, M->num_bases, M->num_layers, cluster)
+                                    : rs::fwd_base_fl(n_cap, R, M->num_layers, cluster));
+  const int own16 = rs::a16(rs::own_cap_of(n_cap, cluster));
+  // weight-gradient accumulators: ceil(4 * KRp/16 / nwarps) tiles per warp must be <= 4
+  const int tiles = 4 * ((R + 1) * rs::HID / 16);
+  if (backward && (tiles + 31) / 32 > 4) return -3;
+  // stage rows: as many as fit (multiple of 16, at least 16), leaving >= 4 KB for the edge lists
+  if (base + 4096 + 16 * SSmax * 4 > limit) return -3;
+  size_t rows = (limit - base - 4096) / (SSmax * 4);
+  rows &= ~(size_t)15;
+  if (rows > (size_t)own16) rows = own16;
+  // prefer a larger list buffer over more stage rows once half of the own rows fit
+  size_t left = limit - base - rows * SSmax * 4;
+  size_t lc = left / 4;
+  if (lc > 16384) lc = 16384;
+  *threads = 1024;
+  *chunk = (int)rows;
+  *lcap = (int)lc;
+  *smem = base + rows * SSmax * 4 + lc * 4;
+  return 0;
 }
 
 template <class Kern, class... Args>
@@ -792,24 +807,25 @@ int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_l
                const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
                const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, int cluster,
                int* err, cudaStream_t st) {
-  int threads, lcap;
+  int threads, lcap, chunk;
   size_t smem;
-  int rc = rs_plan(M, n_cap, cluster, 0, &threads, &smem, &lcap);
+  int rc = rs_plan(M, n_cap, cluster, 0, &threads, &smem, &lcap, &chunk);
   if (rc) return rc;
   return launch_cluster(rs::k_forward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
-                        edge_ptr, *A, n_cap, lcap, *D, training, *S, y, loss_scale, dpred, sqerr, err);
+                        edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, err);
 }
 
 int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                 const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
                 const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, float* dstate, int cluster,
                 int* err, cudaStream_t st) {
-  int threads, lcap;
+  (void)dstate;
+  int threads, lcap, chunk;
   size_t smem;
-  int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem, &lcap);
+  int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem, &lcap, &chunk);
   if (rc) return rc;
   return launch_cluster(rs::k_backward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
-                        edge_ptr, *A, n_cap, lcap, *D, *S, dpred, gpart, dhid, dstate, err);
+                        edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, err);
 }
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st) {

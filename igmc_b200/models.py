@@ -247,7 +247,7 @@ class IGMC(nn.Module):
 
     def _wprep_buf(self):
         if self._wprep is None or self._wprep.device != self.flat_params.device:
-            n = len(self.convs) * 2 * (self.num_relations + 1) * HID * HID
+            n = len(self.convs) * 2 * HID * ((self.num_relations + 1) * HID + 4)
             self._wprep = torch.zeros(n, dtype=torch.float32, device=self.flat_params.device)
         return self._wprep
 

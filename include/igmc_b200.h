@@ -155,7 +155,7 @@ typedef struct {
   int32_t* target;  /* [B*2] batch-global index of the target user / item node */
   int32_t node_cap; /* row count of one zsave / dstate layer slab */
   float* dstate;    /* [L * node_cap * 32] d h_l rows exchanged between the CTAs of a cluster (backward) */
-  const float* wprep; /* [L * 2 * (R+1)*32*32] per-step prepared weights (igmc_prep_weights), cluster plans only */
+  const float* wprep; /* [L * 2 * 32*((R+1)*32+4)] per-step prepared weights (igmc_prep_weights), cluster plans only */
   long long* prof;    /* optional debug: [grid][32] clock64() stamps of the kernel phases (cluster plans), or NULL */
 } igmc_saved_t;
 
