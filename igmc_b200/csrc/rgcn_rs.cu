@@ -758,7 +758,7 @@ int rs_supported(const igmc_model_t* M) { return M->num_relations <= rs::RS_MAX_
 
 // threads per CTA, dynamic shared memory, stage chunk rows and edge-list staging capacity for a plan
 int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap, int* chunk) {
-  const size_t limit = 227 * 1024;
+  const size_t limit = 227 * 1024 - 1024;   // static shared memory of the kernels (scan scratch) counts too
   const int R = M->num_relations;
   const size_t SSmax = (size_t)R * rs::HID + 4;
   const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, R, M->num_bases, M->num_layers, cluster)
