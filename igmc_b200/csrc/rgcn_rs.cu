@@ -64,129 +64,193 @@ __device__ __forceinline__ uint32_t load_entry(const uint32_t* __restrict__ adj,
   return ent;
 }
 
-// Edge lists of the own nodes [lo,hi): staged once per kernel in shared memory, dropped edges compacted out,
-// with block-local offsets lptr[0..n_own].  Falls back to the global arrays when they do not fit.
+// Edge lists of the own nodes [lo,hi): staged once per kernel in shared memory (dropped edges compacted out)
+// and cut into SEGMENTS of at most SEG edges.  A segment is the unit of gather work of one 8-lane group and owns
+// one staging row: the first segment of a node writes the node's row, further segments of a long list (the two
+// target nodes are adjacent to every other node of their subgraph) write extra rows behind the chunk's node rows,
+// which are then summed into the node row in segment order.  This bounds the gather critical path by SEG edges.
+constexpr int SEG = 32;        // edges per segment
+constexpr int XR = 16;         // extra staging rows per chunk
+constexpr int XCH = 8;         // chunks that may use extra rows
+
 struct Lists {
-  const uint32_t* lst;   // staged entries (nullptr: not staged)
-  const int* lptr;       // [n_own+1] offsets into lst
+  const uint32_t* lst;   // staged entries (nullptr: not staged -> adj/eid are read per edge)
+  const int* lptr;       // [n_own+1] list offsets (into lst when staged, else absolute positions in adj)
+  const int* segbase;    // [n_own+1] first segment of every node
+  const int* seg_p0;     // per segment: list range and staging row (relative to its chunk)
+  const int* seg_p1;
+  const int* seg_row;
+  const int* ex;         // per node: first extra row (relative to crow) | number of extra segments << 16
   const uint32_t* adj;   // global fallback
   const int32_t* eid;
-  const int32_t* ptr;
   bool mirror;
   int eb, m_half;
 };
 
-// kept[] (optional, may be null) receives the kept entry count per own node.  Block-wide; ends with a barrier.
+__host__ __device__ __forceinline__ int list_ints(int own_cap) { return 3 * (own_cap + 4) + 3 * (own_cap + XR * XCH); }
+
+// Block-wide; ends with a barrier.  `ibuf` has list_ints(own_cap) ints.  invdeg_out/invdeg_glob (optional) get
+// 1/max(kept degree,1) of the own nodes.
 __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t* eid, const int32_t* ptr, int nb, int lo,
                                              int hi, const Keep& K, bool mirror, int eb, int m_half, uint32_t* lbuf,
-                                             int lcap, int* lptr, int* ws, float* invdeg_out, float* invdeg_glob) {
+                                             int lcap, int* ibuf, int own_cap, int chunk, int* ws, float* invdeg_out,
+                                             float* invdeg_glob) {
   const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
   const int n_own = hi - lo;
+  int* lptr = ibuf;
+  int* segbase = lptr + (own_cap + 4);
+  int* ex = segbase + (own_cap + 4);
+  int* seg_p0 = ex + (own_cap + 4);
+  int* seg_p1 = seg_p0 + (own_cap + XR * XCH);
+  int* seg_row = seg_p1 + (own_cap + XR * XCH);
   Lists Ls;
-  Ls.adj = adj; Ls.eid = eid; Ls.ptr = ptr; Ls.mirror = mirror; Ls.eb = eb; Ls.m_half = m_half;
-  Ls.lptr = lptr;
-  // pass 1: kept count per node -> lptr[i+1] (count), degree
-  for (int i = warp; i < n_own; i += nwarps) {
-    const int p0 = ptr[nb + lo + i], p1 = ptr[nb + lo + i + 1];
-    int kept = p1 - p0;
-    if (K.active) {
-      kept = 0;
+  Ls.adj = adj; Ls.eid = eid; Ls.mirror = mirror; Ls.eb = eb; Ls.m_half = m_half;
+  Ls.lptr = lptr; Ls.segbase = segbase; Ls.ex = ex; Ls.seg_p0 = seg_p0; Ls.seg_p1 = seg_p1; Ls.seg_row = seg_row;
+  // ---- pass 1: kept entries per node ----
+  if (K.active) {
+    for (int i = warp; i < n_own; i += nwarps) {
+      const int p0 = ptr[nb + lo + i], p1 = ptr[nb + lo + i + 1];
+      int kept = 0;
       for (int p = p0 + lane; p < p1; p += 32) kept += load_entry(adj, eid, p, K, mirror, eb, m_half) != DROPPED;
       kept = warp_sum_i(kept);
+      if (lane == 0) lptr[i + 1] = kept;
     }
-    if (lane == 0) {
-      lptr[i + 1] = kept;
-      if (invdeg_out) {
-        const float id = 1.f / (float)max(kept, 1);
-        invdeg_out[lo + i] = id;
-        invdeg_glob[nb + lo + i] = id;
-      }
-    }
+  } else {
+    for (int i = tid; i < n_own; i += NT) lptr[i + 1] = ptr[nb + lo + i + 1] - ptr[nb + lo + i];
   }
   if (tid == 0) lptr[0] = 0;
   __syncthreads();
-  // exclusive scan of the counts (in place: lptr[i+1] becomes the end offset of node i)
-  int running = 0;
+  if (invdeg_out)
+    for (int i = tid; i < n_own; i += NT) {
+      const float id = 1.f / (float)max(lptr[i + 1], 1);
+      invdeg_out[lo + i] = id;
+      invdeg_glob[nb + lo + i] = id;
+    }
+  // ---- segments per node (uncapped) and their prefix sums: offsets | extras << 16 ----
+  int run_off = 0, run_ex = 0;
   for (int base = 0; base < n_own; base += NT) {
     const int i = base + tid;
-    const int c = i < n_own ? lptr[i + 1] : 0;
-    int tot;
-    const int ex = block_excl_scan_i(c, ws, &tot);
-    if (i < n_own) lptr[i + 1] = running + ex + c;
-    running += tot;
+    const int d = i < n_own ? lptr[i + 1] : 0;
+    const int extras = i < n_own ? max(0, (d + SEG - 1) / SEG - 1) : 0;
+    int tot_d, tot_e;
+    const int ex_d = block_excl_scan_i(d, ws, &tot_d);
+    const int ex_e = block_excl_scan_i(extras, ws, &tot_e);
+    if (i < n_own) {
+      segbase[i] = extras;                 // temporarily: uncapped extras
+      ex[i] = run_ex + ex_e;               // temporarily: exclusive prefix of the uncapped extras
+      lptr[i + 1] = run_off + ex_d + d;    // end offset of node i
+    }
+    run_off += tot_d;
+    run_ex += tot_e;
   }
   __syncthreads();
   const int total = n_own > 0 ? lptr[n_own] : 0;
-  Ls.lst = nullptr;
-  if (total <= lcap) {
-    // pass 2: compacted copy (warp per node, order preserved)
-    for (int i = warp; i < n_own; i += nwarps) {
-      const int p0 = ptr[nb + lo + i], p1 = ptr[nb + lo + i + 1];
-      int o = lptr[i];
-      for (int c = p0; c < p1; c += 32) {
-        const int p = c + lane;
-        uint32_t ent = DROPPED;
-        if (p < p1) ent = load_entry(adj, eid, p, K, mirror, eb, m_half);
-        const unsigned bal = __ballot_sync(IGMC_FULL, ent != DROPPED);
-        if (ent != DROPPED) lbuf[o + __popc(bal & ((1u << lane) - 1u))] = ent;
-        o += __popc(bal);
-      }
+  const bool staged = total <= lcap;
+  Ls.lst = staged ? lbuf : nullptr;
+  // ---- cap the extra segments of every chunk at XR, second prefix sum for the segment ids ----
+  int run_seg = 0;
+  for (int base = 0; base < n_own; base += NT) {
+    const int i = base + tid;
+    int nseg = 0, x = 0;
+    if (i < n_own) {
+      const int ci = i / chunk, cfirst = ci * chunk;
+      x = ex[i] - ex[cfirst];
+      const int allowed = ci < XCH ? max(0, min(segbase[i], XR - x)) : 0;
+      nseg = 1 + allowed;
     }
-    Ls.lst = lbuf;
+    int tot;
+    const int exs = block_excl_scan_i(nseg, ws, &tot);
+    __syncthreads();                       // every thread has read ex[] / segbase[] of this round
+    if (i < n_own) {
+      const int ci = i / chunk, c0 = ci * chunk, crow = min(chunk, n_own - c0);
+      const int sb = run_seg + exs;
+      // list offsets: staged lists are compacted (offset 0 = first own entry); unstaged use absolute positions
+      const int l0 = staged ? lptr[i] : ptr[nb + lo + i];
+      const int l1 = staged ? lptr[i + 1] : ptr[nb + lo + i + 1];
+      for (int j = 0; j < nseg; ++j) {
+        seg_p0[sb + j] = l0 + j * SEG;
+        seg_p1[sb + j] = (j == nseg - 1) ? l1 : l0 + (j + 1) * SEG;
+        seg_row[sb + j] = j == 0 ? (i - c0) : (crow + x + j - 1);
+      }
+      ex[i] = x | ((nseg - 1) << 16);
+      segbase[i] = sb;
+    }
+    run_seg += tot;
+    __syncthreads();
+  }
+  if (tid == 0) segbase[n_own] = run_seg;
+  // ---- pass 2: compacted copy of the entries ----
+  if (staged) {
+    if (K.active) {
+      for (int i = warp; i < n_own; i += nwarps) {
+        const int p0 = ptr[nb + lo + i], p1 = ptr[nb + lo + i + 1];
+        int o = lptr[i];
+        for (int c = p0; c < p1; c += 32) {
+          const int p = c + lane;
+          uint32_t ent = DROPPED;
+          if (p < p1) ent = load_entry(adj, eid, p, K, mirror, eb, m_half);
+          const unsigned bal = __ballot_sync(IGMC_FULL, ent != DROPPED);
+          if (ent != DROPPED) lbuf[o + __popc(bal & ((1u << lane) - 1u))] = ent;
+          o += __popc(bal);
+        }
+      }
+    } else {
+      const int e_lo = ptr[nb + lo];
+      for (int i = tid; i < total; i += NT) lbuf[i] = __ldg(adj + e_lo + i);
+    }
   }
   __syncthreads();
   return Ls;
 }
 
-// Relation-space aggregate of the warp's nodes [base, base+cnt) (cnt <= GN, base relative to the own range)
-// into its staging rows stg[s][r*inp + k] (row stride SS): 8-lane group s walks node base+s, float4 per lane.
-__device__ __forceinline__ void zero_stage(float* __restrict__ stg, int SS, int lane) {
+// Relation-space aggregate of the segments [sg0, sg1) of one chunk into their staging rows
+// stage[row][r*inp + k] (row stride SS): one 8-lane group per segment, float4 per lane.
+// `K` is only consulted for unstaged lists (dropout draws evaluated per edge).
+__device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, int sg0, int sg1, int warp, int nwarps,
+                                                int lane, const float* __restrict__ feat, float* __restrict__ stage,
+                                                int SS, int inp) {
+  const int q = lane & 7, gq = lane >> 3;
+  const int fo = 4 * q;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int i = lane * 4; i < GN * SS; i += 128) *reinterpret_cast<float4*>(stg + i) = z4;
-  __syncwarp();
-}
-
-__device__ __forceinline__ void gather_staged(const uint32_t* __restrict__ lst, const int* __restrict__ lptr, int lbase,
-                                              int cnt, int lane, const float* __restrict__ feat,
-                                              float* __restrict__ stg, int SS, int inp) {
-  zero_stage(stg, SS, lane);
-  const int q = lane & 7, s = lane >> 3;
-  const int fo = 4 * q;
-  int p = 0, p1 = 0;
-  if (s < cnt && fo < inp) { p = lptr[lbase + s]; p1 = lptr[lbase + s + 1]; }
-  float* row = stg + s * SS + fo;
-  for (; p < p1; ++p) {
-    const uint32_t ent = lst[p];
-    const int src = (int)(ent & 0xffffu);
-    const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
-    float4* d = reinterpret_cast<float4*>(row + (int)(ent >> 16) * inp);
-    float4 t = *d;
-    t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
-    *d = t;
+  const int per = nwarps * 4;
+  const int iters = (sg1 - sg0 + per - 1) / per;
+  for (int it = 0; it < iters; ++it) {
+    const int sg = sg0 + it * per + warp * 4 + gq;
+    const bool valid = sg < sg1;
+    float* rowb = stage;
+    int p = 0, p1 = 0;
+    if (valid) {
+      rowb = stage + (size_t)Ls.seg_row[sg] * SS;
+      for (int i = q * 4; i < SS; i += 32) *reinterpret_cast<float4*>(rowb + i) = z4;
+      if (fo < inp) { p = Ls.seg_p0[sg]; p1 = Ls.seg_p1[sg]; }
+    }
+    __syncwarp();
+    float* row = rowb + fo;
+    if (Ls.lst) {
+      const uint32_t* lst = Ls.lst;
+      for (; p < p1; ++p) {
+        const uint32_t ent = lst[p];
+        const int src = (int)(ent & 0xffffu);
+        const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
+        float4* d = reinterpret_cast<float4*>(row + (int)(ent >> 16) * inp);
+        float4 t = *d;
+        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+        *d = t;
+      }
+    } else {
+      for (; p < p1; ++p) {
+        const uint32_t ent = load_entry(Ls.adj, Ls.eid, p, K, Ls.mirror, Ls.eb, Ls.m_half);
+        if (ent == DROPPED) continue;
+        const int src = (int)(ent & 0xffffu);
+        const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
+        float4* d = reinterpret_cast<float4*>(row + (int)((ent >> 16) & 0xffu) * inp);
+        float4 t = *d;
+        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+        *d = t;
+      }
+    }
+    __syncwarp();
   }
-  __syncwarp();
-}
-
-// fallback: lists read from global memory, dropout draws evaluated per edge
-__device__ __forceinline__ void gather_global(const Lists& Ls, const Keep& K, int nb, int gbase, int cnt, int lane,
-                                              const float* __restrict__ feat, float* __restrict__ stg, int SS, int inp) {
-  zero_stage(stg, SS, lane);
-  const int q = lane & 7, s = lane >> 3;
-  const int fo = 4 * q;
-  int p = 0, p1 = 0;
-  if (s < cnt && fo < inp) { p = Ls.ptr[nb + gbase + s]; p1 = Ls.ptr[nb + gbase + s + 1]; }
-  float* row = stg + s * SS + fo;
-  for (; p < p1; ++p) {
-    const uint32_t ent = load_entry(Ls.adj, Ls.eid, p, K, Ls.mirror, Ls.eb, Ls.m_half);
-    if (ent == DROPPED) continue;
-    const int src = (int)(ent & 0xffffu);
-    const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
-    float4* d = reinterpret_cast<float4*>(row + (int)((ent >> 16) & 0xffu) * inp);
-    float4 t = *d;
-    t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
-    *d = t;
-  }
-  __syncwarp();
 }
 
 // ---- tensor-core tiles: mma.sync m16n8k8 TF32 with 3xTF32 error compensation (fp32-level accuracy) ----------
@@ -202,13 +266,22 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// x = hi + lo with hi, lo representable in tf32;  a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (small terms first)
+// x = hi + lo:  hi = x with the 13 low mantissa bits cleared (exactly a tf32 value), lo = x - hi (exact in fp32;
+// the tensor core reads its top 10 mantissa bits).  a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (small terms first);
+// the dropped lo*lo term and the truncation of lo are O(2^-21) relative.  cvt.rna.tf32 is NOT used: on sm_100a it
+// expands to ~16 SASS instructions per value, which made the split dominate the tile loop (profiles/).
 __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const float (&af)[4], const float (&bf)[2]) {
   uint32_t ah[4], al[4], bh[2], bl[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) { ah[i] = f2tf32(af[i]); al[i] = f2tf32(af[i] - __uint_as_float(ah[i])); }
+  for (int i = 0; i < 4; ++i) {
+    ah[i] = __float_as_uint(af[i]) & 0xffffe000u;
+    al[i] = __float_as_uint(af[i] - __uint_as_float(ah[i]));
+  }
 #pragma unroll
-  for (int i = 0; i < 2; ++i) { bh[i] = f2tf32(bf[i]); bl[i] = f2tf32(bf[i] - __uint_as_float(bh[i])); }
+  for (int i = 0; i < 2; ++i) {
+    bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
+    bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i]));
+  }
   mma_tf32(d, al, bh);
   mma_tf32(d, ah, bl);
   mma_tf32(d, ah, bh);
@@ -227,7 +300,7 @@ __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
 }
 __host__ __device__ __forceinline__ int own_cap_of(int n_cap, int CL) { return ((n_cap + CL - 1) / CL + GN - 1) / GN * GN; }
 
-#define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 32 + (i_)] = clock64(); } while (0)
+#define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // per-step weight preparation.  slab(l, dir) = Bn[n][KS]  (n = output channel, KS = Ktot + 4):
@@ -297,13 +370,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   float* Hbuf0 = smem;                               // [n_cap][32]
   float* Hbuf1 = Hbuf0 + (size_t)n_cap * HID;        // [n_cap][32]
   float* Wn = Hbuf1 + (size_t)n_cap * HID;           // [32][KS]
-  float* stage = Wn + (size_t)HID * KSmax;           // [chunk][SSmax]
-  float* bias_s = stage + (size_t)chunk * SSmax;
+  float* stage = Wn + (size_t)HID * KSmax;           // [chunk + XR][SSmax]
+  float* bias_s = stage + (size_t)(chunk + XR) * SSmax;
   float* invdeg = bias_s + HID;                      // [n_cap]
   float* feat_s = invdeg + a4(n_cap);
   float* hid_s = feat_s + a4(F);
-  int* lptr = reinterpret_cast<int*>(hid_s + L1O);              // [own_cap+1]
-  uint32_t* lbuf = reinterpret_cast<uint32_t*>(lptr + a4(own_cap + 1));   // [lcap]
+  int* ibuf = reinterpret_cast<int*>(hid_s + L1O);              // list offsets + segment table
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));   // [lcap]
   __shared__ int s_t[2];
   __shared__ int ws[34];
 
@@ -331,7 +404,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   // in-lists of the own nodes -> shared memory; kept in-degree (dropout_adj is applied once, models.py:193)
   const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap,
-                               lptr, ws, invdeg, S.inv_deg);
+                               ibuf, own_cap, chunk, ws, invdeg, S.inv_deg);
   const int tu = s_t[0], ti = s_t[1];
   if (tu >= n || ti >= n) {
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
@@ -345,30 +418,37 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     copy_f4(Wn, S.wprep + (size_t)l * 2 * wprep_slab(R), HID * KS);
     if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
     __syncthreads();
-    IGMC_STAMP(2 + 4 * l);
+    IGMC_STAMP(2 + 6 * l);
     for (int c0 = 0; c0 < n_own; c0 += chunk) {
       const int crow = min(chunk, n_own - c0);
-      // ---- aggregate the chunk's nodes (warp = 4 nodes), scale by 1/deg, keep a copy for backward ----
-      for (int lb = warp * GN; lb < crow; lb += nwarps * GN) {
-        const int cnt = min(GN, crow - lb);
-        float* stg = stage + (size_t)lb * SS;
-        if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, c0 + lb, cnt, lane, H, stg, SS, inp);
-        else gather_global(Ls, K, nb, own.lo + c0 + lb, cnt, lane, H, stg, SS, inp);
-        for (int s2 = 0; s2 < cnt; ++s2) {
-          const int v = own.lo + c0 + lb + s2;
+      // ---- aggregate: one 8-lane group per list segment ----
+      gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], warp, nwarps, lane, H, stage, SS, inp);
+      __syncthreads();
+      // ---- fold the extra segments of long lists into their node row, scale by 1/deg, keep a copy for backward ----
+      {
+        const int kq = K1 >> 2, SS4 = SS >> 2;
+        float4* st4 = reinterpret_cast<float4*>(stage);
+        for (int r = warp; r < crow; r += nwarps) {
+          const int v = own.lo + c0 + r;
           const float id2 = invdeg[v];
-          float4* row = reinterpret_cast<float4*>(stg + s2 * SS);
+          const int e = Ls.ex[c0 + r], x0 = e & 0xffff, nex = e >> 16;
           float4* zs = S.zsave ? reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID))
                                : nullptr;
-          for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) {
-            float4 t = row[k4];
+          for (int k4 = lane; k4 < kq; k4 += 32) {
+            float4 t = st4[(size_t)r * SS4 + k4];
+            for (int j = 0; j < nex; ++j) {
+              const float4 u = st4[(size_t)(crow + x0 + j) * SS4 + k4];
+              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+            }
             t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
-            row[k4] = t;
+            st4[(size_t)r * SS4 + k4] = t;
             if (zs) zs[k4] = t;
           }
         }
       }
+      IGMC_STAMP(3 + 6 * l);
       __syncthreads();
+      IGMC_STAMP(4 + 6 * l);
       // ---- dense transform on tensor cores: out[16x8 tiles] = [AGG' | h] . [W_r ; root] ----
       const int mt = (crow + 15) >> 4;
       for (int tile = warp; tile < mt * 4; tile += nwarps) {
@@ -410,11 +490,12 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
           }
         }
       }
+      IGMC_STAMP(5 + 6 * l);
       __syncthreads();
     }
-    IGMC_STAMP(3 + 4 * l);
+    IGMC_STAMP(6 + 6 * l);
     if (CL > 1) cluster.sync();
-    IGMC_STAMP(5 + 4 * l);
+    IGMC_STAMP(7 + 6 * l);
     float* t = H; H = Hn; Hn = t;
     // concat_states rows of the two target nodes (models.py:203-207), all rows are local now
     if (rank == 0 && tid < 2 * HID) {
@@ -429,11 +510,19 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
   if (tid == 0) { S.target[2 * g] = nb + tu; S.target[2 * g + 1] = nb + ti; }
   const float* W1 = params + M.off_lin1_w;
-  for (int o = warp; o < L1O; o += nwarps) {
-    float s = 0.f;
-    for (int i = lane; i < F; i += 32) s = fmaf(W1[(size_t)o * F + i], feat_s[i], s);
-    s = warp_sum_f(s);
-    if (lane == 0) {
+  for (int ob = warp * 4; ob < L1O; ob += nwarps * 4) {   // 4 outputs per warp with independent load streams
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = lane; i < F; i += 32) {
+      const float f = feat_s[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] = fmaf(__ldg(W1 + (size_t)(ob + u) * F + i), f, s4[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s4[u] = warp_sum_f(s4[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (lane == u) {
+      const int o = ob + u;
+      const float s = s4[u];
       float h = fmaxf(s + params[M.off_lin1_b + o], 0.f);
       float scale = 1.f;
       if (training && (D.hidden_dropout > 0.f || D.hidden_keep)) {
@@ -467,7 +556,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       }
     }
   }
-  IGMC_STAMP(2 + 4 * L);
+  IGMC_STAMP(2 + 6 * L);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,14 +584,14 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* DP = DH1 + (size_t)n_cap * HID;                // [own_cap16][DPS_] dpre of the own rows (zero padded)
   float* Wn = DP + (size_t)own_cap16 * DPS_;            // [32][KS]
   float* dW = Wn + (size_t)HID * KSmax;                 // [KRp][32]
-  float* stage = dW + (size_t)KRmax * HID;              // [chunk][SSmax]  |  weight-gradient tile [rows][TS]
-  float* att_s = stage + (size_t)chunk * SSmax;
+  float* stage = dW + (size_t)KRmax * HID;              // [chunk + XR][SSmax]  |  weight-gradient tile [rows][TS]
+  float* att_s = stage + (size_t)(chunk + XR) * SSmax;
   float* invdeg = att_s + a4(R * NB);
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
   float* dB = dhid_s + L1O;                              // [32]
-  int* lptr = reinterpret_cast<int*>(dB + HID);          // [own_cap+1]
-  uint32_t* lbuf = reinterpret_cast<uint32_t*>(lptr + a4(own_cap + 1));   // [lcap]
+  int* ibuf = reinterpret_cast<int*>(dB + HID);          // list offsets + segment table
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));   // [lcap]
   __shared__ int ws[34];
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
@@ -520,7 +609,8 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   IGMC_STAMP(0);
   // out-lists of the own nodes (symmetric batches: the in-lists with mirrored edge ids)
   const Lists Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb,
-                               own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap, lptr, ws, nullptr, nullptr);
+                               own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap, ibuf, own_cap, chunk, ws, nullptr,
+                               nullptr);
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
   const float dp = dpred[g];
@@ -532,12 +622,21 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   for (int v = tid; v < n; v += NT) invdeg[v] = S.inv_deg[nb + v];
   __syncthreads();
   {
+    // d feat[i] = sum_o W1[o][i] d hid[o]: thread slice p of NT/F takes every (NT/F)-th o, partials in `stage`
     const float* W1 = params + M.off_lin1_w;
-    for (int i = tid; i < F; i += NT) {
+    const int parts = max(1, NT / F);
+    const int i = tid % F, part = tid / F;
+    if (part < parts) {
       float s = 0.f;
 #pragma unroll 8
-      for (int o = 0; o < L1O; ++o) s = fmaf(W1[(size_t)o * F + i], dhid_s[o], s);
-      dfeat[i] = s;
+      for (int o = part; o < L1O; o += parts) s = fmaf(__ldg(W1 + (size_t)o * F + i), dhid_s[o], s);
+      stage[part * F + i] = s;
+    }
+    __syncthreads();
+    for (int j = tid; j < F; j += NT) {
+      float s = 0.f;
+      for (int q = 0; q < parts; ++q) s += stage[q * F + j];
+      dfeat[j] = s;
     }
   }
   __syncthreads();
@@ -559,7 +658,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   for (int l = L - 1; l >= 0; --l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), KRp = K1p + inpp;
-    const int sb = 2 + 5 * (L - 1 - l);
+    const int sb = 2 + 8 * (L - 1 - l);
     float* DPS = (l & 1) ? DH1 : DH0;                    // d h_l on entry, dpre/deg after step (0)
     float* DHn = (l & 1) ? DH0 : DH1;                    // d h_{l-1} (written here and by the peers)
     // (0) d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows (padded with zeros)
@@ -588,13 +687,27 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       const int SS = K1p + 4, KS = KRp + 4;
       for (int c0 = 0; c0 < n_own; c0 += chunk) {
         const int crow = min(chunk, n_own - c0);
-        for (int lb = warp * GN; lb < crow; lb += nwarps * GN) {
-          const int cnt = min(GN, crow - lb);
-          float* stg = stage + (size_t)lb * SS;
-          if (Ls.lst) gather_staged(Ls.lst, Ls.lptr, c0 + lb, cnt, lane, DPS, stg, SS, HID);
-          else gather_global(Ls, K, nb, own.lo + c0 + lb, cnt, lane, DPS, stg, SS, HID);
-        }
+        gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], warp, nwarps, lane, DPS, stage, SS, HID);
         __syncthreads();
+        {   // fold the extra segments of long lists into their node row
+          const int kq = K1 >> 2, SS4 = SS >> 2;
+          float4* st4 = reinterpret_cast<float4*>(stage);
+          for (int r = warp; r < crow; r += nwarps) {
+            const int e = Ls.ex[c0 + r], x0 = e & 0xffff, nex = e >> 16;
+            if (nex == 0) continue;
+            for (int k4 = lane; k4 < kq; k4 += 32) {
+              float4 t = st4[(size_t)r * SS4 + k4];
+              for (int j = 0; j < nex; ++j) {
+                const float4 u = st4[(size_t)(crow + x0 + j) * SS4 + k4];
+                t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
+              }
+              st4[(size_t)r * SS4 + k4] = t;
+            }
+          }
+        }
+        IGMC_STAMP(sb + 5);
+        __syncthreads();
+        IGMC_STAMP(sb + 6);
         const int mt = (crow + 15) >> 4;
         for (int tile = warp; tile < mt * 4; tile += nwarps) {
           const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
@@ -642,7 +755,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     //     A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | h_{l-1}[v,k] ]  ->  M = KRp rows, N = 32, K = own nodes
     {
       const int TS = KRp + 8;                              // tile row stride (== 8 mod 32: conflict-free A^T frags)
-      int trows = (int)(((size_t)chunk * SSmax) / TS) & ~7;   // node rows of one tile pass
+      int trows = (int)(((size_t)(chunk + XR) * SSmax) / TS) & ~7;   // node rows of one tile pass
       if (trows > a8(n_own)) trows = a8(n_own);
       const int mtiles = KRp >> 4;                          // KRp is a multiple of 8; odd multiples handled below
       const int mt = (KRp + 15) >> 4;
@@ -657,26 +770,31 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       float accb = 0.f;
       for (int t0 = 0; t0 < a8(n_own) && trows > 0; t0 += trows) {
         const int rows = min(trows, a8(n_own) - t0);        // multiple of 8, rows beyond n_own are zero
-        for (int r_ = warp; r_ < rows; r_ += nwarps) {
-          const int v = own.lo + t0 + r_;
-          float* dst = stage + (size_t)r_ * TS;
-          if (t0 + r_ < n_own) {
-            const float4* src = reinterpret_cast<const float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID));
-            for (int k4 = lane; k4 < (K1 >> 2); k4 += 32) reinterpret_cast<float4*>(dst)[k4] = src[k4];
-            for (int kk = K1 + lane; kk < K1p; kk += 32) dst[kk] = 0.f;
-            if (lane < inpp) {
-              float hv = 0.f;
-              if (lane < in) {
-                if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + lane);
-                else hv = (lane == (int)node_label[nb + v]) ? 1.f : 0.f;
-              }
-              dst[K1p + lane] = hv;
+        {   // tile[r][0..K1) = saved aggregate, [K1..K1p) = 0, [K1p..KRp) = h_{l-1}; rows beyond n_own are zero
+          const int kq = K1 >> 2, TS4 = TS >> 2;
+          float4* t4 = reinterpret_cast<float4*>(stage);
+          for (int idx = tid; idx < rows * kq; idx += NT) {
+            const int r_ = idx / kq, k4 = idx - r_ * kq;
+            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t0 + r_ < n_own)
+              val = __ldg(reinterpret_cast<const float4*>(S.zsave + ((size_t)l * S.node_cap + nb + own.lo + t0 + r_) * (size_t)(R * HID)) + k4);
+            t4[(size_t)r_ * TS4 + k4] = val;
+          }
+          const int tail = KRp - K1;   // zero padding of the aggregate + the h_{l-1} columns
+          for (int idx = tid; idx < rows * tail; idx += NT) {
+            const int r_ = idx / tail, q = idx - r_ * tail, kk = K1 + q;
+            float hv = 0.f;
+            const int k = kk - K1p;
+            if (k >= 0 && k < in && t0 + r_ < n_own) {
+              const int v = own.lo + t0 + r_;
+              if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + k);
+              else hv = (k == (int)node_label[nb + v]) ? 1.f : 0.f;
             }
-          } else {
-            for (int kk = lane; kk < KRp; kk += 32) dst[kk] = 0.f;
+            stage[(size_t)r_ * TS + kk] = hv;
           }
         }
         __syncthreads();
+        IGMC_STAMP(sb + 7);
 #pragma unroll
         for (int i = 0; i < MAXT; ++i) {
           const int tile = warp + i * nwarps;
@@ -711,7 +829,9 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       if (warp == nwarps - 1) dB[lane] = accb;
       __syncthreads();
       IGMC_STAMP(sb + 2);
-      const float* bs = params + M.off_basis[l];
+      copy_f4(stage, params + M.off_basis[l], NB * in * HID);   // basis of this layer -> shared (tile is done)
+      __syncthreads();
+      const float* bs = stage;
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
       for (int row = warp; row < NB * in; row += nwarps) {
         const int b = row / in, k = row - b * in;
@@ -742,13 +862,14 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
 size_t fwd_base_fl(int n_cap, int R, int L, int CL) {   // everything except the stage rows and the list buffer
   const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL);
-  return 2 * (size_t)n_cap * HID + HID * KSmax + HID + a4(n_cap) + a4((int)F) + L1O + a4((int)own_cap + 1);
+  return 2 * (size_t)n_cap * HID + HID * KSmax + HID + a4(n_cap) + a4((int)F) + L1O + a4(list_ints((int)own_cap)) +
+         (size_t)XR * ((size_t)R * HID + 4);
 }
 size_t bwd_base_fl(int n_cap, int R, int NB, int L, int CL) {
   const size_t KSmax = (size_t)(R + 1) * HID + 4, KRmax = (size_t)(R + 1) * HID, F = 2 * HID * L;
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL), own_cap16 = (size_t)a16((int)own_cap);
   return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + KRmax * HID + a4(R * NB) + a4(n_cap) +
-         a4((int)F) + L1O + HID + a4((int)own_cap + 1);
+         a4((int)F) + L1O + HID + a4(list_ints((int)own_cap)) + (size_t)XR * ((size_t)R * HID + 4);
 }
 
 }  // namespace rs

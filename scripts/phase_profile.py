@@ -18,7 +18,7 @@ for plan in (2, 1):
     m.kernel_plan = plan
     m._plans.clear(); m._ws.clear()
     grid = B * plan
-    m._prof_buf = torch.zeros(grid * 32, dtype=torch.int64, device="cuda")
+    m._prof_buf = torch.zeros(grid * 64, dtype=torch.int64, device="cuda")
     for it in range(3):
         b = d.extract_batch(rng.choice(len(tu), B, replace=False))
         m._step += 1
@@ -26,11 +26,11 @@ for plan in (2, 1):
         m._prof_buf.zero_()
         _, saved = m._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / B)
         torch.cuda.synchronize()
-        f = m._prof_buf.view(grid, 32).cpu().numpy().copy()
+        f = m._prof_buf.view(grid, 64).cpu().numpy().copy()
         m._prof_buf.zero_()
         m._launch_backward(b, drop, saved, saved["ws"]["dpred"])
         torch.cuda.synchronize()
-        bw = m._prof_buf.view(grid, 32).cpu().numpy().copy()
+        bw = m._prof_buf.view(grid, 64).cpu().numpy().copy()
     def show(name, a, labels):
         a = a.astype(np.float64)
         t0 = a[:, 0:1]
@@ -45,12 +45,28 @@ for plan in (2, 1):
             mean = col[ok].mean()
             print("  %-28s t=%9.0f cyc (%6.1f us)  +%8.0f   max=%9.0f" % (lab, mean, mean / 1965.0, mean - prev, col[ok].max()))
             prev = mean
-    fl = ["start", "init+stage lists"]
+    def show2(name, a, labels):
+        a = a.astype(np.float64)
+        print("== %s plan=%d (us since kernel start at 1.965 GHz, mean / max over CTAs)" % (name, plan))
+        order = sorted(labels.items(), key=lambda kv: a[:, kv[0]][a[:, kv[0]] > 0].mean() if (a[:, kv[0]] > 0).any() else 1e30)
+        prev = 0.0
+        for i, lab in order:
+            ok = a[:, i] > 0
+            if not ok.any():
+                continue
+            col = (a[:, i] - a[:, 0])[ok]
+            print("  %-34s t=%7.1f us  +%6.1f   max=%7.1f" % (lab, col.mean() / 1965.0, (col.mean() - prev) / 1965.0, col.max() / 1965.0))
+            prev = col.mean()
+    fl = {0: "start", 1: "init+stage lists"}
     for l in range(4):
-        fl += ["L%d weights copied" % l, "L%d groups done (thread0)" % l, "L%d block synced" % l, "L%d cluster exchanged" % l]
-    fl += ["readout done"]
-    show("forward", f, fl)
-    bl = ["start", "stage+readout bwd"]
-    for l in (3, 2, 1, 0):
-        bl += ["L%d dpre+Wt ready" % l, "L%d data-grad done" % l, "L%d wgrad done" % l, "L%d chain rule done" % l, "L%d cluster synced" % l]
-    show("backward", bw, bl)
+        fl.update({2 + 6 * l: "L%d weights copied" % l, 3 + 6 * l: "L%d gather done (warp0)" % l, 4 + 6 * l: "L%d gather synced" % l,
+                   5 + 6 * l: "L%d mma done (warp0)" % l, 6 + 6 * l: "L%d mma synced" % l, 7 + 6 * l: "L%d cluster synced" % l})
+    fl[26] = "readout done"
+    show2("forward", f, fl)
+    bl = {0: "start", 1: "stage+readout bwd"}
+    for i, l in enumerate((3, 2, 1, 0)):
+        sb = 2 + 8 * i
+        bl.update({sb: "L%d dpre+W ready" % l, sb + 5: "L%d dgrad gather done (warp0)" % l, sb + 6: "L%d dgrad gather synced" % l,
+                   sb + 1: "L%d dgrad mma done" % l, sb + 7: "L%d wgrad tile loaded" % l, sb + 2: "L%d wgrad done" % l,
+                   sb + 3: "L%d chain rule done" % l, sb + 4: "L%d cluster synced" % l})
+    show2("backward", bw, bl)
