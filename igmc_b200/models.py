@@ -226,7 +226,7 @@ class IGMC(nn.Module):
                       hid_gscale=torch.empty(B, 128, **f32), pred=torch.empty(B, **f32),
                       target=torch.empty(B, 2, dtype=torch.int32, device=dev),
                       dpred=torch.zeros(B, **f32), sqerr=torch.zeros(B, **f32), loss=torch.zeros(1, **f32),
-                      reg_ws=torch.zeros(_lib.MAX_LAYERS + 1, **f32), cluster=cl)
+                      reg_ws=torch.zeros(_lib.MAX_LAYERS * 256 + 4, **f32), cluster=cl)
             if train:
                 zdim = max(NB, self.num_relations if cl > 0 else 0) * HID
                 ws.update(zsave=torch.empty(L, ncap, zdim, **f32),
@@ -373,7 +373,7 @@ class FusedAdam(torch.optim.Optimizer):
         n = model.flat_params.numel()
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_count = torch.zeros(2, dtype=torch.int64, device=dev)   # [step | completion ticket of the kernel]
         for (o, k, s), p in zip(model._layout, params):
             self.state[p] = dict(step=self.step_count[0], exp_avg=self.exp_avg[o:o + k].view(s),
                                  exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
@@ -386,7 +386,7 @@ class FusedAdam(torch.optim.Optimizer):
                 st = self.state[p]
                 self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
                 self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
-                self.step_count.fill_(int(st["step"]))
+                self.step_count[0] = int(st["step"])
                 self.state[p] = dict(step=self.step_count[0], exp_avg=self.exp_avg[o:o + k].view(s),
                                      exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
 

@@ -154,6 +154,73 @@ class TrainEngine(object):
             self._launch(nb, G)
             self.eager_done.add(key)
 
+    # ---- software pipeline: extract batch k+1 on a side stream while the model trains on batch k ------------
+    # (what the reference's DataLoader workers do, train_eval.py:40-45, as two branches of one CUDA graph)
+    def pipelined(self):
+        return hasattr(self.dataset, "extractor") and not hasattr(self.dataset, "slices")
+
+    def _launch_pipe(self, nb, G, slot, nb_next):
+        B, buf = self.B, self.stepbuf_dev
+        main = torch.cuda.current_stream()
+        if nb_next > 0:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                self.batches[slot ^ 1] = self.dataset.extractor.extract(idx=buf[:nb_next], seed_dev=buf[B:B + 1],
+                                                                        reuse=True, slot=slot ^ 1)
+        if nb > 0:
+            loss = self.model.fused_step(self.batches[slot], ARR=self.ARR / self.world, global_num_graphs=G,
+                                         seed_dev=buf[B + 1:B + 2])
+        else:
+            self.model.flat_grad.zero_()
+            loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        if self.world > 1:
+            dist.all_reduce(self.model.flat_grad)
+        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev)
+        self.last_loss.copy_(loss)
+        self.loss_acc.add_(loss * float(G))
+        if nb_next > 0:
+            main.wait_stream(self.side)
+
+    def prime(self, idx, epoch=0, G=None):
+        """extract the first batch of a pipelined sequence (no model work)."""
+        if not hasattr(self, "side"):
+            self.side = torch.cuda.Stream()
+            self.batches = [None, None]
+        G = len(idx) * self.world if G is None else int(G)
+        nb = self.stage(idx, epoch, G)
+        self.slot = 0
+        if nb > 0:
+            self.batches[0] = self.dataset.extractor.extract(idx=self.stepbuf_dev[:nb],
+                                                             seed_dev=self.stepbuf_dev[self.B:self.B + 1], reuse=True,
+                                                             slot=0)
+        self.cur = (nb, G)
+
+    def step_pipe(self, next_idx=None, epoch=0, next_G=None, staged=False):
+        """train on the batch extracted by the previous call (or prime) while extracting ``next_idx``.
+        One H2D copy of the next indices + one graph replay."""
+        nb, G = self.cur
+        self.steps += 1
+        nb_next = 0
+        if next_idx is not None:
+            next_G = len(next_idx) * self.world if next_G is None else int(next_G)
+            nb_next = len(next_idx) if staged else self.stage(next_idx, epoch, next_G)
+        else:
+            self.stage(np.zeros(0, np.int64), epoch, 0)    # still refresh the dropout seed of this step
+        key = (nb, G, self.slot, nb_next)
+        if self.use_graph and key in self.graphs:
+            self.graphs[key].replay()
+        elif self.use_graph and key in self.eager_done:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._launch_pipe(nb, G, self.slot, nb_next)
+            self.graphs[key] = g
+            g.replay()
+        else:
+            self._launch_pipe(nb, G, self.slot, nb_next)
+            self.eager_done.add(key)
+        self.slot ^= 1
+        self.cur = (nb_next, next_G if next_idx is not None else 0)
+
     def check(self):
         code = int(self.dataset.extractor.err.item()) if hasattr(self.dataset, "extractor") else 0
         if code:
@@ -217,8 +284,18 @@ def train(model, optimizer, loader, device, regression=False, ARR=0, show_progre
     rank, world = _dist_info()
     perm = torch.randperm(len(dataset), generator=generator).numpy()
     engine.loss_acc.zero_()
-    for idx, G in shard_batches(perm, engine.B, rank, world):
-        engine.step(idx, epoch=0 if epoch is None else int(epoch), G=G)
+    ep = 0 if epoch is None else int(epoch)
+    batches = shard_batches(perm, engine.B, rank, world)
+    if engine.pipelined() and len(batches) > 0:
+        engine.prime(batches[0][0], ep, batches[0][1])
+        for k in range(len(batches)):
+            if k + 1 < len(batches):
+                engine.step_pipe(batches[k + 1][0], ep, batches[k + 1][1])
+            else:
+                engine.step_pipe(None, ep)
+    else:
+        for idx, G in batches:
+            engine.step(idx, epoch=ep, G=G)
     acc = engine.loss_acc.clone()
     if world > 1:
         dist.all_reduce(acc)

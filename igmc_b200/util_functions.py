@@ -291,9 +291,9 @@ class SubgraphExtractor(object):
         self._ws_c = _lib.ExtractWS(*[self.ws[k].data_ptr() for k in ("nodes_u", "nodes_v", "n_u", "n_v",
                                                                           "row_cnt", "m_cnt", "col_cnt")])
 
-    def _alloc_out(self, B, reuse=False):
-        if reuse and B in self._out_cache:
-            return self._out_cache[B]
+    def _alloc_out(self, B, reuse=False, slot=0):
+        if reuse and (B, slot) in self._out_cache:
+            return self._out_cache[(B, slot)]
         dev = self.device
         ncap, ecap = B * 2 * self.cap, max(B * (self.edge_cap // self.max_batch), 2)
         o = dict(x=torch.empty(ncap, self.feat_dim, dtype=torch.float32, device=dev) if self.emit_x else None,
@@ -314,11 +314,11 @@ class SubgraphExtractor(object):
                  err=self.err)
         o["_caps"] = (ncap, ecap)
         if reuse:
-            self._out_cache[B] = o
+            self._out_cache[(B, slot)] = o
         return o
 
     def extract(self, idx=None, pairs=None, pair_ids=None, out=None, inject=None, seed=None, seed_dev=None,
-                reuse=False):
+                reuse=False, slot=0):
         """Extract + collate.  ``idx``: int64 tensor/array of dataset indices (device tensor preferred),
         or ``pairs=(u, v, label)`` explicit arrays.  ``inject=(nodes_u, nodes_v, n_u, n_v)`` supplies the
         per-graph node lists ([B,cap] int32, target first) instead of sampling (parity tests).
@@ -346,7 +346,7 @@ class SubgraphExtractor(object):
                            self.links_label.data_ptr(), None)
             keep += [idx]
         self._reserve(B)
-        o = out if out is not None else self._alloc_out(B, reuse)
+        o = out if out is not None else self._alloc_out(B, reuse, slot)
         ncap, ecap = o["_caps"]
         O = _lib.BatchOut(ncap, ecap, self.feat_dim, _lib.ptr(o["x"]), o["node_label"].data_ptr(),
                           o["batch"].data_ptr(), o["node_gid"].data_ptr(), o["edge_index"].data_ptr(),

@@ -192,15 +192,16 @@ int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* nod
 
 /* grad[p] = sum over gpart rows (conv) ; lin1/lin2 gradients from (dhid, feat, hid, dpred) ;
  * + ARR * d/dW sum_l sum_r ||W_{r+1}-W_r||^2 (train_eval.py:167-174).  Also writes
- * loss_out[0] = sum_g sqerr[g]*loss_scale + ARR*reg  when loss_out != NULL.  `reg_ws` is a scratch of
- * IGMC_MAX_LAYERS+1 floats (+1 int ticket) used to add the per-layer regulariser values in a fixed order. */
+ * loss_out[0] = sum_g sqerr[g]*loss_scale + ARR*reg  when loss_out != NULL.  `reg_ws` is a zero-initialised
+ * scratch of IGMC_MAX_LAYERS*256 + 1 floats (per-(layer,relation) regulariser values + an int ticket). */
 int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, int gpart_rows, const float* gpart,
                      const float* dhid, const float* feat, const float* hid, const float* dpred,
                      const float* sqerr, float loss_scale, float arr, float grad_scale,
                      float* grad, float* loss_out, float* reg_ws, void* stream);
 
 /* torch.optim.Adam step (train_eval.py:54,177; lr/weight_decay semantics of torch 1.4 Adam, eps outside
- * the sqrt, no amsgrad) on the flat buffers.  `step_count` is a device int64 incremented by the kernel;
+ * the sqrt, no amsgrad) on the flat buffers.  `step_count` points at TWO device int64 words: the step
+ * counter (incremented by the kernel) and a zero-initialised completion ticket;
  * grad is multiplied by grad_mul first (1/world after an NCCL sum); `lr_dev` (optional device float)
  * overrides `lr` so LR decay does not invalidate a captured graph. */
 int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq,

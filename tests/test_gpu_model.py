@@ -188,3 +188,16 @@ def test_determinism_and_graph_replay():
         outs.append(m.flat_params.clone())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
     assert torch.isfinite(outs[0]).all()
+    # pipelined engine (extraction of batch k+1 on a side stream / second graph branch): same parameters
+    for use_graph in (False, True):
+        d = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, 10, None, None, ds["class_values"])
+        torch.manual_seed(0)
+        m = IGMC(d, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=0.2).cuda()
+        opt = FusedAdam(m, lr=1e-3)
+        eng = TrainEngine(d, m, opt, 8, ARR=0.001, use_graph=use_graph)
+        eng.prime(np.arange(0, 8), epoch=1)
+        for s in range(6):
+            eng.step_pipe(np.arange((s + 1) * 8, (s + 1) * 8 + 8) if s < 5 else None, epoch=1)
+        eng.check()
+        torch.cuda.synchronize()
+        assert torch.equal(m.flat_params, outs[0]), "pipelined engine diverged (graph=%s)" % use_graph
