@@ -256,7 +256,7 @@ def run_ours(args):
     G = B * world
     rng = np.random.default_rng(1000)
     perm = rng.permutation(len(tu))
-    steps_idx = [perm[(s * G + rank * B):(s * G + rank * B + B)] for s in range(W + 3 * K + 4)]
+    steps_idx = [perm[(s * G + rank * B):(s * G + rank * B + B)] for s in range(W + 3 * K + 16)]
     cursor = [0]
 
     def next_idx():
