@@ -302,27 +302,34 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
         ei0[e1] = un; ei1[e1] = vn; O.edge_type[e1] = r;
         ei0[e2] = vn; ei1[e2] = un; O.edge_type[e2] = r;
         if (want_adj) {
-          // user a's list: edge item->user is the mirrored copy e2; entry sits at the edge's first-half slot
-          O.adj_in[e1] = (uint32_t)(nu + b) | ((uint32_t)r << 16);
-          O.adj_eid[e1] = (int32_t)e2;
-          // item b's list: edge user->item is e1; unordered placement, sorted below
+          // key = type | neighbour | edge id : lists are rank-sorted by (type, neighbour) below.
+          // user a's list (slots [rowoff[a], +cnt)): in-edge item->user is the mirrored copy e2
+          O.adj_tmp[e1] = ((uint64_t)r << 56) | ((uint64_t)(nu + b) << 32) | (uint64_t)(uint32_t)e2;
+          // item b's list: in-edge user->item is e1; unordered placement
           const int slot = atomicAdd(&colfill[b], 1);
-          O.adj_tmp[(size_t)2 * Mbase + m + slot] = ((uint64_t)a << 40) | ((uint64_t)r << 32) | (uint64_t)(uint32_t)e1;
+          O.adj_tmp[(size_t)2 * Mbase + m + slot] = ((uint64_t)r << 56) | ((uint64_t)a << 32) | (uint64_t)(uint32_t)e1;
         }
       }
       seen += __popc(bal);
     }
   }
-  if (want_adj) {   // deterministic item lists: rank-sort by user index (lists are short)
+  if (want_adj) {   // deterministic lists sorted by (type, neighbour): rank-sort (lists are short)
     __syncthreads();
-    for (int b = warp; b < nv; b += nwarps) {
-      const int k = col_cnt[(size_t)g * cap + b];
-      const size_t beg = (size_t)2 * Mbase + m + (colfill[b] - k);
+    for (int v = warp; v < n; v += nwarps) {
+      int k;
+      size_t beg;
+      if (v < nu) {
+        k = row_cnt[(size_t)g * cap + v] & 0x7fffffff;
+        beg = (size_t)2 * Mbase + rowoff[v];
+      } else {
+        k = col_cnt[(size_t)g * cap + (v - nu)];
+        beg = (size_t)2 * Mbase + m + (colfill[v - nu] - k);
+      }
       for (int i = lane; i < k; i += 32) {
         const uint64_t key = O.adj_tmp[beg + i];
         int rank = 0;
         for (int q = 0; q < k; ++q) rank += (O.adj_tmp[beg + q] < key) ? 1 : 0;
-        O.adj_in[beg + rank] = (uint32_t)(key >> 40) | ((uint32_t)((key >> 32) & 0xffu) << 16);
+        O.adj_in[beg + rank] = (uint32_t)((key >> 32) & 0xffffu) | ((uint32_t)(key >> 56) << 16);
         O.adj_eid[beg + rank] = (int32_t)(uint32_t)(key & 0xffffffffu);
       }
     }

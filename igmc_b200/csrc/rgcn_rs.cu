@@ -227,14 +227,32 @@ __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, 
     __syncwarp();
     float* row = rowb + fo;
     if (Ls.lst) {
+      // lists arrive sorted by (type, neighbour): sum each type run in registers, touch the staging row once
+      // per run (still a read-modify-write, so any order stays correct - unsorted lists just flush more often)
       const uint32_t* lst = Ls.lst;
+      float4 acc = z4;
+      int cur = -1;
       for (; p < p1; ++p) {
         const uint32_t ent = lst[p];
-        const int src = (int)(ent & 0xffffu);
+        const int src = (int)(ent & 0xffffu), ty = (int)(ent >> 16);
         const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
-        float4* d = reinterpret_cast<float4*>(row + (int)(ent >> 16) * inp);
+        if (ty != cur) {
+          if (cur >= 0) {
+            float4* d = reinterpret_cast<float4*>(row + cur * inp);
+            float4 t = *d;
+            t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
+            *d = t;
+          }
+          acc = a;
+          cur = ty;
+        } else {
+          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+      }
+      if (cur >= 0) {
+        float4* d = reinterpret_cast<float4*>(row + cur * inp);
         float4 t = *d;
-        t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+        t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
         *d = t;
       }
     } else {
@@ -270,7 +288,7 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // the tensor core reads its top 10 mantissa bits).  a*b ~= lo_a*hi_b + hi_a*lo_b + hi_a*hi_b  (small terms first);
 // the dropped lo*lo term and the truncation of lo are O(2^-21) relative.  cvt.rna.tf32 is NOT used: on sm_100a it
 // expands to ~16 SASS instructions per value, which made the split dominate the tile loop (profiles/).
-__device__ __forceinline__ void mma_3xtf32(float (&d)[4], const float (&af)[4], const float (&bf)[2]) {
+__device__ __forceinline__ void mma_3xtf32(float (&d)[4], float (&dsm)[4], const float (&af)[4], const float (&bf)[2]) {
   uint32_t ah[4], al[4], bh[2], bl[2];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -282,8 +300,10 @@ __device__ __forceinline__ void mma_3xtf32(float (&d)[4], const float (&af)[4], 
     bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
     bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i]));
   }
-  mma_tf32(d, al, bh);
-  mma_tf32(d, ah, bl);
+  // the two cross terms go to a separate accumulator: shorter dependency chains (and the small terms are summed
+  // among themselves before meeting the large one)
+  mma_tf32(dsm, al, bh);
+  mma_tf32(dsm, ah, bl);
   mma_tf32(d, ah, bh);
 }
 
@@ -453,25 +473,37 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       const int mt = (crow + 15) >> 4;
       for (int tile = warp; tile < mt * 4; tile += nwarps) {
         const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
-        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+        float e[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};   // cross-term accumulators
         const float* a0p = stage + (size_t)(m0 + gq) * SS + tq;
         const float* a1p = a0p + 8 * SS;
         const float* bp = Wn + (size_t)(n0 + gq) * KS + tq;
-        for (int k0 = 0; k0 < K1p; k0 += 8) {
+        int k0 = 0;
+        for (; k0 + 16 <= K1p; k0 += 16) {                  // two independent accumulator sets per iteration
           const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
           const float bf[2] = {bp[k0], bp[k0 + 4]};
-          mma_3xtf32(d, af, bf);
+          const float ag[4] = {a0p[k0 + 8], a1p[k0 + 8], a0p[k0 + 12], a1p[k0 + 12]};
+          const float bg[2] = {bp[k0 + 8], bp[k0 + 12]};
+          mma_3xtf32(d, e, af, bf);
+          mma_3xtf32(d2, e2, ag, bg);
+        }
+        for (; k0 < K1p; k0 += 8) {
+          const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
+          const float bf[2] = {bp[k0], bp[k0 + 4]};
+          mma_3xtf32(d, e, af, bf);
         }
         const int r0 = c0 + m0 + gq, r1 = r0 + 8;           // rows relative to the own range
         const int v0 = own.lo + min(r0, n_own - 1), v1 = own.lo + min(r1, n_own - 1);
         const float* h0 = H + (v0 << 5);
         const float* h1 = H + (v1 << 5);
         const int sw0 = (v0 & 7) << 2, sw1 = (v1 & 7) << 2;
-        for (int k0 = 0; k0 < inpp; k0 += 8) {
+        for (k0 = 0; k0 < inpp; k0 += 8) {
           const float af[4] = {h0[(k0 + tq) ^ sw0], h1[(k0 + tq) ^ sw1], h0[(k0 + tq + 4) ^ sw0], h1[(k0 + tq + 4) ^ sw1]};
           const float bf[2] = {bp[K1p + k0], bp[K1p + k0 + 4]};
-          mma_3xtf32(d, af, bf);
+          mma_3xtf32(d2, e2, af, bf);
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = (d[i] + d2[i]) + (e[i] + e2[i]);
         const int cc = n0 + 2 * tq;
         const float b0 = bias_s[cc], b1 = bias_s[cc + 1];
 #pragma unroll
@@ -711,23 +743,35 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         const int mt = (crow + 15) >> 4;
         for (int tile = warp; tile < mt * 4; tile += nwarps) {
           const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
-          float d[4] = {0.f, 0.f, 0.f, 0.f};
+          float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+          float e[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
           const float* a0p = stage + (size_t)(m0 + gq) * SS + tq;
           const float* a1p = a0p + 8 * SS;
           const float* bp = Wn + (size_t)(n0 + gq) * KS + tq;
-          for (int k0 = 0; k0 < K1p; k0 += 8) {
+          int k0 = 0;
+          for (; k0 + 16 <= K1p; k0 += 16) {
             const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
             const float bf[2] = {bp[k0], bp[k0 + 4]};
-            mma_3xtf32(d, af, bf);
+            const float ag[4] = {a0p[k0 + 8], a1p[k0 + 8], a0p[k0 + 12], a1p[k0 + 12]};
+            const float bg[2] = {bp[k0 + 8], bp[k0 + 12]};
+            mma_3xtf32(d, e, af, bf);
+            mma_3xtf32(d2, e2, ag, bg);
+          }
+          for (; k0 < K1p; k0 += 8) {
+            const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
+            const float bf[2] = {bp[k0], bp[k0 + 4]};
+            mma_3xtf32(d, e, af, bf);
           }
           const int r0 = c0 + m0 + gq, r1 = r0 + 8;
           const float* p0 = DP + (size_t)min(r0, own_cap16 - 1) * DPS_ + tq;
           const float* p1 = DP + (size_t)min(r1, own_cap16 - 1) * DPS_ + tq;
-          for (int k0 = 0; k0 < HID; k0 += 8) {
+          for (k0 = 0; k0 < HID; k0 += 8) {
             const float af[4] = {p0[k0], p1[k0], p0[k0 + 4], p1[k0 + 4]};
             const float bf[2] = {bp[K1p + k0], bp[K1p + k0 + 4]};
-            mma_3xtf32(d, af, bf);
+            mma_3xtf32(d2, e2, af, bf);
           }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d[i] = (d[i] + d2[i]) + (e[i] + e2[i]);
           const int cc = n0 + 2 * tq;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -762,11 +806,11 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       (void)mtiles;
       // accumulators live across node passes: tile list per warp is fixed (<= 2 tiles per warp for R <= 7 at 32 warps)
       constexpr int MAXT = 4;
-      float acc[MAXT][4];
+      float acc[MAXT][4], acs[MAXT][4];
 #pragma unroll
       for (int i = 0; i < MAXT; ++i)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+        for (int c = 0; c < 4; ++c) { acc[i][c] = 0.f; acs[i][c] = 0.f; }
       float accb = 0.f;
       for (int t0 = 0; t0 < a8(n_own) && trows > 0; t0 += trows) {
         const int rows = min(trows, a8(n_own) - t0);        // multiple of 8, rows beyond n_own are zero
@@ -795,20 +839,20 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         }
         __syncthreads();
         IGMC_STAMP(sb + 7);
+        // node (k) loop outside, the warp's tiles inside: independent accumulator chains interleave
+        for (int k0 = 0; k0 < rows; k0 += 8) {
 #pragma unroll
-        for (int i = 0; i < MAXT; ++i) {
-          const int tile = warp + i * nwarps;
-          if (tile < mt * 4) {
-            const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
-            // A^T fragment: row = kk (m0+g), col = node (k0+t);  B: k = node, n = channel
-            const bool hi_ok = (m0 + 8) < KRp;               // KRp may be an odd multiple of 8
-            const float* ap = stage + (size_t)tq * TS + m0 + gq;
-            const float* bp = DP + (size_t)(t0 + tq) * DPS_ + n0 + gq;
-            for (int k0 = 0; k0 < rows; k0 += 8) {
-              const float* a = ap + (size_t)k0 * TS;
+          for (int i = 0; i < MAXT; ++i) {
+            const int tile = warp + i * nwarps;
+            if (tile < mt * 4) {
+              const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
+              // A^T fragment: row = kk (m0+g), col = node (k0+t);  B: k = node, n = channel
+              const bool hi_ok = (m0 + 8) < KRp;               // KRp may be an odd multiple of 8
+              const float* a = stage + (size_t)(k0 + tq) * TS + m0 + gq;
+              const float* bp = DP + (size_t)(t0 + k0 + tq) * DPS_ + n0 + gq;
               const float af[4] = {a[0], hi_ok ? a[8] : 0.f, a[4 * TS], hi_ok ? a[4 * TS + 8] : 0.f};
-              const float bf[2] = {bp[(size_t)k0 * DPS_], bp[(size_t)(k0 + 4) * DPS_]};
-              mma_3xtf32(acc[i], af, bf);
+              const float bf[2] = {bp[0], bp[4 * DPS_]};
+              mma_3xtf32(acc[i], acs[i], af, bf);
             }
           }
         }
@@ -822,8 +866,11 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         const int tile = warp + i * nwarps;
         if (tile < mt * 4) {
           const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3, cc = n0 + 2 * tq;
-          *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq) * HID + cc) = make_float2(acc[i][0], acc[i][1]);
-          if (m0 + 8 < KRp) *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq + 8) * HID + cc) = make_float2(acc[i][2], acc[i][3]);
+          *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq) * HID + cc) =
+              make_float2(acc[i][0] + acs[i][0], acc[i][1] + acs[i][1]);
+          if (m0 + 8 < KRp)
+            *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq + 8) * HID + cc) =
+                make_float2(acc[i][2] + acs[i][2], acc[i][3] + acs[i][3]);
         }
       }
       if (warp == nwarps - 1) dB[lane] = accb;
