@@ -232,22 +232,33 @@ __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, 
       const uint32_t* lst = Ls.lst;
       float4 acc = z4;
       int cur = -1;
+#define IGMC_HROW(e_) (*reinterpret_cast<const float4*>(feat + (((int)((e_) & 0xffffu)) << 5) + (fo ^ ((((int)(e_)) & 7) << 2))))
+#define IGMC_STEP(e_, a_)                                                            \
+      do {                                                                           \
+        const int ty_ = (int)((e_) >> 16);                                           \
+        if (ty_ != cur) {                                                            \
+          if (cur >= 0) {                                                            \
+            float4* d_ = reinterpret_cast<float4*>(row + cur * inp);                 \
+            float4 t_ = *d_;                                                         \
+            t_.x += acc.x; t_.y += acc.y; t_.z += acc.z; t_.w += acc.w;              \
+            *d_ = t_;                                                                \
+          }                                                                          \
+          acc = (a_);                                                                \
+          cur = ty_;                                                                 \
+        } else {                                                                     \
+          acc.x += (a_).x; acc.y += (a_).y; acc.z += (a_).z; acc.w += (a_).w;        \
+        }                                                                            \
+      } while (0)
+      // four edges in flight: the entry and source-row loads of a batch are independent
+      for (; p + 4 <= p1; p += 4) {
+        const uint32_t e0 = lst[p], e1 = lst[p + 1], e2 = lst[p + 2], e3 = lst[p + 3];
+        const float4 a0 = IGMC_HROW(e0), a1 = IGMC_HROW(e1), a2 = IGMC_HROW(e2), a3 = IGMC_HROW(e3);
+        IGMC_STEP(e0, a0); IGMC_STEP(e1, a1); IGMC_STEP(e2, a2); IGMC_STEP(e3, a3);
+      }
       for (; p < p1; ++p) {
-        const uint32_t ent = lst[p];
-        const int src = (int)(ent & 0xffffu), ty = (int)(ent >> 16);
-        const float4 a = *reinterpret_cast<const float4*>(feat + (src << 5) + (fo ^ ((src & 7) << 2)));
-        if (ty != cur) {
-          if (cur >= 0) {
-            float4* d = reinterpret_cast<float4*>(row + cur * inp);
-            float4 t = *d;
-            t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
-            *d = t;
-          }
-          acc = a;
-          cur = ty;
-        } else {
-          acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
-        }
+        const uint32_t e0 = lst[p];
+        const float4 a0 = IGMC_HROW(e0);
+        IGMC_STEP(e0, a0);
       }
       if (cur >= 0) {
         float4* d = reinterpret_cast<float4*>(row + cur * inp);
@@ -255,6 +266,8 @@ __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, 
         t.x += acc.x; t.y += acc.y; t.z += acc.z; t.w += acc.w;
         *d = t;
       }
+#undef IGMC_STEP
+#undef IGMC_HROW
     } else {
       for (; p < p1; ++p) {
         const uint32_t ent = load_entry(Ls.adj, Ls.eid, p, K, Ls.mirror, Ls.eb, Ls.m_half);
@@ -430,6 +443,11 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
     return;
   }
+  if (S.prof && tid == 0) {   // debug: staging facts
+    long long* pp = S.prof + (size_t)blockIdx.x * 64;
+    pp[60] = Ls.lst != nullptr; pp[61] = n_own > 0 ? Ls.lptr[n_own] : 0; pp[62] = Ls.segbase[n_own]; pp[63] = lcap;
+    pp[59] = chunk; pp[58] = n_own;
+  }
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
   for (int l = 0; l < L; ++l) {
@@ -442,8 +460,12 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     for (int c0 = 0; c0 < n_own; c0 += chunk) {
       const int crow = min(chunk, n_own - c0);
       // ---- aggregate: one 8-lane group per list segment ----
+#define IGMC_STAMP_T(t_, i_) do { if (S.prof && l == 1 && threadIdx.x == (t_)) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
+      IGMC_STAMP_T(0, 39); IGMC_STAMP_T(992, 49);
       gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], warp, nwarps, lane, H, stage, SS, inp);
+      IGMC_STAMP_T(0, 40); IGMC_STAMP_T(992, 43); IGMC_STAMP_T(480, 46);
       __syncthreads();
+      IGMC_STAMP_T(0, 41); IGMC_STAMP_T(992, 44);
       // ---- fold the extra segments of long lists into their node row, scale by 1/deg, keep a copy for backward ----
       {
         const int kq = K1 >> 2, SS4 = SS >> 2;
@@ -466,6 +488,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
           }
         }
       }
+      IGMC_STAMP_T(0, 42); IGMC_STAMP_T(992, 45);
       IGMC_STAMP(3 + 6 * l);
       __syncthreads();
       IGMC_STAMP(4 + 6 * l);

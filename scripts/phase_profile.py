@@ -61,8 +61,12 @@ for plan in (2, 1):
     for l in range(4):
         fl.update({2 + 6 * l: "L%d weights copied" % l, 3 + 6 * l: "L%d gather done (warp0)" % l, 4 + 6 * l: "L%d gather synced" % l,
                    5 + 6 * l: "L%d mma done (warp0)" % l, 6 + 6 * l: "L%d mma synced" % l, 7 + 6 * l: "L%d cluster synced" % l})
+    fl.update({39: "L1 w0 gather start", 49: "L1 w31 gather start", 40: "L1 w0 gather_segments done", 43: "L1 w31 gather_segments done", 46: "L1 w15 gather_segments done",
+               41: "L1 w0 after sync", 44: "L1 w31 after sync", 42: "L1 w0 fold done", 45: "L1 w31 fold done"})
     fl[26] = "readout done"
     show2("forward", f, fl)
+    print("  staging facts (fwd): staged=%s entries=%s segs=%s lcap=%s chunk=%s n_own=%s" % tuple(
+        sorted(set(f[:, c].tolist()))[:6] for c in (60, 61, 62, 63, 59, 58)))
     bl = {0: "start", 1: "stage+readout bwd"}
     for i, l in enumerate((3, 2, 1, 0)):
         sb = 2 + 8 * i
