@@ -372,6 +372,11 @@ def run_ours(args):
         kern_ms = {n: acc[n] / reps for n in names}
         dom = max(("extract", "forward", "backward"), key=lambda n: kern_ms[n])
         peak, peak_src = peaks()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            with open(tp) as f:
+                traffic = json.load(f).get(dom)
         per_launch_bytes = ab[dom] / nb_batches
         achieved = per_launch_bytes / (kern_ms[dom] * 1e-3) / 1e9
         step_bytes = ab["step"] / nb_batches
@@ -397,7 +402,7 @@ def run_ours(args):
             "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
                         "note": "same steps back to back without the L2 flush (informative)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": per_launch_bytes,
                          "kernel_ms": kern_ms, "step_algorithmic_bytes": step_bytes,
                          "step_frac": (step_bytes / (dev_ms / K * 1e-3) / 1e9) / peak},
