@@ -411,8 +411,12 @@ def run_ours(args):
             "wall_s_timed_region": wall,
         }
     if world > 1:
+        # NCCL communicators that were captured into CUDA graphs do not tear down reliably
+        # (destroy_process_group was observed to hang): drop the graphs, align the ranks, and let main() leave
+        # through os._exit after the JSON line is flushed.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        eng.graphs.clear()
     return out
 
 
@@ -451,6 +455,9 @@ def main():
     out = run_ours(args)
     if out is not None:
         print(json.dumps(out))
+    sys.stdout.flush()
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        os._exit(0)
 
 
 if __name__ == "__main__":
