@@ -48,6 +48,11 @@ class BatchOut(C.Structure):
                 ("counts", vp), ("adj_in_ptr", vp), ("adj_in", vp), ("adj_eid", vp), ("adj_tmp", vp)]
 
 
+class Store(C.Structure):
+    _fields_ = [(k, vp) for k in ("node_off", "edge_off", "node_label", "node_gid", "edge_src", "edge_dst",
+                                  "edge_type", "y", "graph_nu", "adj_ptr", "adj_in", "adj_eid")]
+
+
 class Adj(C.Structure):
     _fields_ = [("in_ptr", vp), ("in_adj", vp), ("in_eid", vp), ("out_ptr", vp), ("out_adj", vp),
                 ("out_eid", vp), ("tmp", vp), ("symmetric", C.c_int32)]
@@ -76,6 +81,7 @@ class Saved(C.Structure):
 _SIGS = {
     "igmc_extract_batch": [C.POINTER(CSR), C.POINTER(Pairs), C.c_int, C.c_int, C.c_double, C.c_uint64, vp, C.c_int,
                            vp, vp, vp, vp, C.POINTER(ExtractWS), vp, C.POINTER(BatchOut), vp, vp],
+    "igmc_assemble_batch": [C.POINTER(Store), vp, C.c_int, C.POINTER(BatchOut), vp, vp],
     "igmc_batch_ptrs": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
     "igmc_batch_prepare": [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Adj), vp, vp],
     "igmc_forward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),

@@ -336,6 +336,61 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
   }
 }
 
+
+// Batch assembly from the static store (one CTA per output graph).
+__global__ void __launch_bounds__(256)
+k_assemble(igmc_store_t S, const int64_t* __restrict__ idx, int B, igmc_batch_out_t O, int* err) {
+  __shared__ int ws[34];
+  const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  int nsum = 0, esum = 0;
+  for (int q = tid; q < g; q += nt) {
+    const int64_t s = idx[q];
+    nsum += S.node_off[s + 1] - S.node_off[s];
+    esum += S.edge_off[s + 1] - S.edge_off[s];
+  }
+  const int Nbase = block_sum_i(nsum, ws);
+  const int Ebase = block_sum_i(esum, ws);
+  const int64_t s = idx[g];
+  const int n0 = S.node_off[s], n = S.node_off[s + 1] - n0;
+  const int e0 = S.edge_off[s], e = S.edge_off[s + 1] - e0;
+  if (g == B - 1 && tid == 0) {
+    O.counts[0] = Nbase + n;
+    O.counts[1] = Ebase + e;
+    O.node_ptr[B] = Nbase + n;
+    O.edge_ptr[B] = Ebase + e;
+    if (O.adj_in_ptr && Nbase + n <= O.node_cap) O.adj_in_ptr[Nbase + n] = Ebase + e;
+  }
+  if (tid == 0) { O.node_ptr[g] = Nbase; O.edge_ptr[g] = Ebase; }
+  if (Nbase + n > O.node_cap || Ebase + e > O.edge_cap) {
+    if (tid == 0) igmc_set_err(err, (Nbase + n > O.node_cap) ? IGMC_ERR_NODE_TOTAL : IGMC_ERR_EDGE_CAP);
+    return;
+  }
+  if (tid == 0) { O.y[g] = S.y[s]; O.graph_nu[g] = S.graph_nu[s]; }
+  const int32_t* aptr = S.adj_ptr + n0 + s;   // per graph n+1 entries -> offset n0 + s
+  for (int t = tid; t < n; t += nt) {
+    const size_t row = (size_t)Nbase + t;
+    const int label = S.node_label[n0 + t];
+    O.node_label[row] = (uint8_t)label;
+    O.batch[row] = g;
+    O.node_gid[row] = S.node_gid[n0 + t];
+    if (O.x)
+      for (int f = 0; f < O.feat_dim; ++f) O.x[row * O.feat_dim + f] = (f == label) ? 1.0f : 0.0f;
+    if (O.adj_in_ptr) O.adj_in_ptr[row] = Ebase + aptr[t];
+  }
+  int64_t* ei0 = O.edge_index;
+  int64_t* ei1 = O.edge_index + O.edge_cap;
+  for (int t = tid; t < e; t += nt) {
+    const size_t k = (size_t)Ebase + t;
+    ei0[k] = (int64_t)Nbase + S.edge_src[e0 + t];
+    ei1[k] = (int64_t)Nbase + S.edge_dst[e0 + t];
+    O.edge_type[k] = S.edge_type[e0 + t];
+    if (O.adj_in_ptr) {
+      O.adj_in[k] = S.adj_in[e0 + t];
+      O.adj_eid[k] = Ebase + S.adj_eid[e0 + t];
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int max_nodes_per_hop,
@@ -359,6 +414,14 @@ extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, in
   IGMC_CUDA_CHECK_LAUNCH();
   k_extract_fill<<<B, EX_THREADS, smemB, st>>>(*G, *P, B, cap, W->nodes_u, W->nodes_v, W->n_u, W->n_v,
                                                W->row_cnt, W->m_cnt, W->col_cnt, class_values, *O, err);
+  IGMC_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+extern "C" int igmc_assemble_batch(const igmc_store_t* S, const int64_t* idx, int B, const igmc_batch_out_t* O, int* err,
+                                   void* stream) {
+  if (B <= 0) return 0;
+  k_assemble<<<B, 256, 0, (cudaStream_t)stream>>>(*S, idx, B, *O, err);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
 }

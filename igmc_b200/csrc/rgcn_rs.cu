@@ -343,37 +343,32 @@ __host__ __device__ __forceinline__ int own_cap_of(int n_cap, int CL) { return (
 // ------------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ size_t wprep_slab(int R) { return (size_t)HID * ((size_t)(R + 1) * HID + 4); }
 
+// grid = L * 2 * 32 blocks: block (l, dir, n) writes row n of slab (l, dir); one thread per K position.
 __global__ void __launch_bounds__(256)
 k_prep_weights(igmc_model_t M, const float* __restrict__ params, float* __restrict__ wprep) {
-  const int l = blockIdx.x >> 1, dir = blockIdx.x & 1;
+  const int n = blockIdx.x & 31, ld = blockIdx.x >> 5, l = ld >> 1, dir = ld & 1;
   const int R = M.num_relations, NB = M.num_bases;
   const int in = l == 0 ? M.in_dim0 : HID, inp = a4(in);
   const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), KS = K1p + inpp + 4;
+  if (dir == 1 && l == 0) return;
   const float* bs = params + M.off_basis[l];
   const float* at = params + M.off_att[l];
   const float* rt = params + M.off_root[l];
-  float* out = wprep + ((size_t)l * 2 + dir) * wprep_slab(R);
-  __shared__ float att_s[256];
-  __shared__ float bas_s[IGMC_MAX_BASES * HID * HID];
-  for (int i = threadIdx.x; i < R * NB && i < 256; i += 256) att_s[i] = at[i];
-  for (int i = threadIdx.x; i < NB * in * HID; i += 256) bas_s[i] = bs[i];
-  __syncthreads();
-  if (dir == 1 && l == 0) return;
-  for (int idx = threadIdx.x; idx < HID * KS; idx += 256) {
-    const int n = idx / KS, kk = idx - n * KS;
+  float* out = wprep + ((size_t)l * 2 + dir) * wprep_slab(R) + (size_t)n * KS;
+  for (int kk = threadIdx.x; kk < KS; kk += 256) {
     float w = 0.f;
     if (kk < K1) {
       const int r = kk / inp, q = kk - r * inp;
       if (q < in) {
         // dir 0: W_r[k=q][n] ; dir 1: W_r[k=n][j=q]
         const int k = dir == 0 ? q : n, j = dir == 0 ? n : q;
-        for (int b = 0; b < NB; ++b) w = fmaf(att_s[r * NB + b], bas_s[(b * in + k) * HID + j], w);
+        for (int b = 0; b < NB; ++b) w = fmaf(__ldg(at + r * NB + b), __ldg(bs + (b * in + k) * HID + j), w);
       }
     } else if (kk >= K1p && kk < K1p + inp) {
       const int q = kk - K1p;
-      if (q < in) w = dir == 0 ? rt[q * HID + n] : rt[n * HID + q];
+      if (q < in) w = dir == 0 ? __ldg(rt + q * HID + n) : __ldg(rt + n * HID + q);
     }
-    out[idx] = w;
+    out[kk] = w;
   }
 }
 
@@ -1020,7 +1015,7 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
 }
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st) {
-  rs::k_prep_weights<<<M->num_layers * 2, 256, 0, st>>>(*M, params, wprep);
+  rs::k_prep_weights<<<M->num_layers * 2 * 32, 256, 0, st>>>(*M, params, wprep);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e + 1000;
 }

@@ -427,11 +427,127 @@ class MyDynamicDataset(object):
         return self.get(int(idx))
 
 
+class StaticStore(object):
+    """Device-resident store of pre-extracted subgraphs + batch assembly (igmc_assemble_batch).  Has the
+    ``extract`` / ``err`` / ``cap`` surface of ``SubgraphExtractor`` so that the train engine treats both alike."""
+
+    def __init__(self, extractor, num_graphs, chunk=512):
+        self.lib = _lib.load()
+        self.device = dev = extractor.device
+        self.feat_dim, self.emit_x = extractor.feat_dim, extractor.emit_x
+        parts = {k: [] for k in ("node_label", "node_gid", "edge_src", "edge_dst", "edge_type", "y", "graph_nu",
+                                 "adj_ptr", "adj_in", "adj_eid", "ncnt", "ecnt")}
+        for s0 in range(0, num_graphs, chunk):
+            idx = np.arange(s0, min(s0 + chunk, num_graphs), dtype=np.int64)
+            b = extractor.extract(idx=idx)
+            b.check()
+            nptr, eptr = b._priv["node_ptr"].long(), b._priv["edge_ptr"].long()
+            N, E = int(nptr[-1]), int(eptr[-1])
+            gi_n = b.batch[:N]
+            ei = b.edge_index
+            gi_e = gi_n[ei[0]] if E else torch.zeros(0, dtype=torch.int64, device=dev)
+            adj = b._adj[1]
+            parts["node_label"].append(b.node_label[:N].clone())
+            parts["node_gid"].append(b.node_gid[:N].clone())
+            parts["edge_src"].append((ei[0] - nptr[gi_e]).int())
+            parts["edge_dst"].append((ei[1] - nptr[gi_e]).int())
+            parts["edge_type"].append(b.edge_type[:E].to(torch.uint8))
+            parts["y"].append(b.y.clone())
+            parts["graph_nu"].append(b._priv["graph_nu"][:len(idx)].clone())
+            # adjacency: list offsets / edge ids relative to the graph; positions coincide with the edge slots
+            ap = adj["adj_in_ptr"][:N + 1].long()
+            loc = ap[:N] - eptr[gi_n]
+            ends = (eptr[1:] - eptr[:-1])                      # per graph: last offset = its edge count
+            # interleave: for graph g its n offsets followed by its total
+            cnt_n = (nptr[1:] - nptr[:-1])
+            out = torch.empty(N + len(idx), dtype=torch.int32, device=dev)
+            pos = torch.arange(N, device=dev) + gi_n              # node t of graph g sits at t + g
+            out[pos] = loc.int()
+            out[nptr[1:] + torch.arange(len(idx), device=dev)] = ends.int()
+            parts["adj_ptr"].append(out)
+            parts["adj_in"].append(adj["adj_in"][:E].clone())
+            parts["adj_eid"].append((adj["adj_eid"][:E].long() - eptr[gi_e]).int())   # list slot e belongs to graph gi_e
+            parts["ncnt"].append(cnt_n)
+            parts["ecnt"].append(ends)
+        cat = {k: torch.cat(v) for k, v in parts.items()}
+        z = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.node_off = torch.cat([z, torch.cumsum(cat["ncnt"], 0)]).int()
+        self.edge_off = torch.cat([z, torch.cumsum(cat["ecnt"], 0)]).int()
+        self.t = {k: cat[k] for k in ("node_label", "node_gid", "edge_src", "edge_dst", "edge_type", "y", "graph_nu",
+                                       "adj_ptr", "adj_in", "adj_eid")}
+        for k, v in self.t.items():   # valid pointers even for empty stores
+            if v.numel() == 0:
+                self.t[k] = torch.zeros(1, dtype=v.dtype, device=dev)
+        self.num_graphs = num_graphs
+        self.max_n = int(cat["ncnt"].max()) if num_graphs else 2
+        self.max_e = int(cat["ecnt"].max()) if num_graphs else 2
+        self.cap = (self.max_n + 1) // 2 + 1          # n_cap = 2*cap >= max_n (the model plans by 2*cap)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._c = _lib.Store(self.node_off.data_ptr(), self.edge_off.data_ptr(),
+                             *[self.t[k].data_ptr() for k in ("node_label", "node_gid", "edge_src", "edge_dst",
+                                                              "edge_type", "y", "graph_nu", "adj_ptr", "adj_in",
+                                                              "adj_eid")])
+        self._out_cache = {}
+
+    def _alloc_out(self, B, reuse=False, slot=0):
+        if reuse and (B, slot) in self._out_cache:
+            return self._out_cache[(B, slot)]
+        dev = self.device
+        ncap, ecap = max(B * self.max_n, 2), max(B * self.max_e, 2)
+        o = dict(x=torch.empty(ncap, self.feat_dim, dtype=torch.float32, device=dev) if self.emit_x else None,
+                 node_label=torch.empty(ncap, dtype=torch.uint8, device=dev),
+                 batch=torch.empty(ncap, dtype=torch.int64, device=dev),
+                 node_gid=torch.empty(ncap, dtype=torch.int32, device=dev),
+                 edge_index=torch.empty(2, ecap, dtype=torch.int64, device=dev),
+                 edge_type=torch.empty(ecap, dtype=torch.int64, device=dev),
+                 y=torch.empty(B, dtype=torch.float32, device=dev),
+                 node_ptr=torch.zeros(B + 1, dtype=torch.int32, device=dev),
+                 edge_ptr=torch.zeros(B + 1, dtype=torch.int32, device=dev),
+                 graph_nu=torch.zeros(B, dtype=torch.int32, device=dev),
+                 counts=torch.zeros(2, dtype=torch.int32, device=dev),
+                 adj_in_ptr=torch.zeros(ncap + 1, dtype=torch.int32, device=dev),
+                 adj_in=torch.empty(ecap, dtype=torch.int32, device=dev),
+                 adj_eid=torch.empty(ecap, dtype=torch.int32, device=dev),
+                 adj_tmp=torch.empty(1, dtype=torch.int64, device=dev),
+                 err=self.err)
+        o["_caps"] = (ncap, ecap)
+        if reuse:
+            self._out_cache[(B, slot)] = o
+        return o
+
+    def extract(self, idx=None, seed_dev=None, reuse=False, slot=0, **unused):
+        dev = self.device
+        if not torch.is_tensor(idx):
+            idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+        idx = idx.to(device=dev, dtype=torch.int64)
+        B = int(idx.numel())
+        o = self._alloc_out(B, reuse, slot)
+        ncap, ecap = o["_caps"]
+        O = _lib.BatchOut(ncap, ecap, self.feat_dim, _lib.ptr(o["x"]), o["node_label"].data_ptr(),
+                          o["batch"].data_ptr(), o["node_gid"].data_ptr(), o["edge_index"].data_ptr(),
+                          o["edge_type"].data_ptr(), o["y"].data_ptr(), o["node_ptr"].data_ptr(),
+                          o["edge_ptr"].data_ptr(), o["graph_nu"].data_ptr(), o["counts"].data_ptr(),
+                          o["adj_in_ptr"].data_ptr(), o["adj_in"].data_ptr(), o["adj_eid"].data_ptr(),
+                          o["adj_tmp"].data_ptr())
+        _lib.check(self.lib.igmc_assemble_batch(C.byref(self._c), idx.data_ptr(), B, C.byref(O), self.err.data_ptr(),
+                                                _stream_ptr()), "igmc_assemble_batch")
+        b = Batch(B, dev, y=o["y"])
+        b._lazy = o
+        b._err = self.err
+        b._keep = [idx]
+        b._priv = dict(node_label=o["node_label"], node_ptr=o["node_ptr"], edge_ptr=o["edge_ptr"], node_cap=ncap,
+                       edge_cap=ecap, n_cap=2 * self.cap, symmetric=1, edge_row_stride=ecap, graph_nu=o["graph_nu"],
+                       counts=o["counts"])
+        b._adj = (_lib.Adj(o["adj_in_ptr"].data_ptr(), o["adj_in"].data_ptr(), o["adj_eid"].data_ptr(), None, None,
+                           None, o["adj_tmp"].data_ptr(), 1), o)
+        return b
+
+
 class MyDataset(MyDynamicDataset):
-    """Static variant (reference util_functions.py:69-110): every subgraph is extracted ONCE (in large
-    GPU batches instead of an mp.Pool) and kept device-resident in the reference's ``(data, slices)``
-    form — per-graph LOCAL node ids, boundaries in ``slices``; mini-batches are
-    assembled from the slices."""
+    """Static variant (reference util_functions.py:69-110): every subgraph is extracted ONCE (in large GPU batches
+    instead of an mp.Pool) and kept device-resident in the reference's ``(data, slices)`` spirit — per-graph LOCAL
+    node ids + per-graph boundaries (SURVEY.md A.5b), in compact types, with the message-passing adjacency;
+    mini-batches are assembled from it by one kernel (igmc_assemble_batch)."""
 
     def __init__(self, root, A, links, labels, h, sample_ratio, max_nodes_per_hop, u_features, v_features,
                  class_values, max_num=None, parallel=True, seed=0, chunk=512):
@@ -445,52 +561,13 @@ class MyDataset(MyDynamicDataset):
         return ["data.pt"]
 
     def process(self, chunk=512):
-        xs, eis, ets, ys = [], [], [], []
-        nptr, eptr = [torch.zeros(1, dtype=torch.int64)], [torch.zeros(1, dtype=torch.int64)]
-        n_tot = e_tot = 0
-        for s in range(0, len(self), chunk):
-            b = self.extractor.extract(idx=np.arange(s, min(s + chunk, len(self)), dtype=np.int64))
-            np_, ep_ = b._priv["node_ptr"].to(torch.int64), b._priv["edge_ptr"].to(torch.int64)
-            xs.append(b.x.clone())
-            # back to per-graph local ids (what InMemoryDataset.collate stores)
-            ei = b.edge_index.clone()
-            gid_of_edge = b.batch[ei[0]] if ei.shape[1] else torch.zeros(0, dtype=torch.int64, device=ei.device)
-            ei -= np_[gid_of_edge].unsqueeze(0)
-            eis.append(ei)
-            ets.append(b.edge_type.clone())
-            ys.append(b.y.clone())
-            nptr.append((np_[1:] + n_tot).cpu())
-            eptr.append((ep_[1:] + e_tot).cpu())
-            n_tot += int(np_[-1])
-            e_tot += int(ep_[-1])
-        dev = self.extractor.device
-        self.data = Data(torch.cat(xs, 0), torch.cat(eis, 1), edge_type=torch.cat(ets), y=torch.cat(ys))
-        self.slices = dict(x=torch.cat(nptr).to(dev), edge_index=torch.cat(eptr).to(dev))
-        self.slices["edge_type"] = self.slices["edge_index"]
-        self.slices["y"] = torch.arange(len(self) + 1, device=dev)
-
-    def get(self, idx):
-        n0, n1 = int(self.slices["x"][idx]), int(self.slices["x"][idx + 1])
-        e0, e1 = int(self.slices["edge_index"][idx]), int(self.slices["edge_index"][idx + 1])
-        return Data(self.data.x[n0:n1], self.data.edge_index[:, e0:e1], edge_type=self.data.edge_type[e0:e1],
-                    y=self.data.y[idx:idx + 1])
+        self.dynamic_extractor = self.extractor
+        self.store = StaticStore(self.dynamic_extractor, len(self), chunk)
+        self.extractor = self.store          # the train / eval loops batch through the store from now on
 
     def extract_batch(self, indices):
-        """batch assembly from the stored slices (device-side gather + offset add)."""
-        dev = self.extractor.device
-        idx = torch.as_tensor(np.asarray(indices) if not torch.is_tensor(indices) else indices).to(dev).long()
-        sx, se = self.slices["x"], self.slices["edge_index"]
-        n0, n1, e0, e1 = sx[idx], sx[idx + 1], se[idx], se[idx + 1]
-        ncnt, ecnt = n1 - n0, e1 - e0
-        nptr = torch.zeros(len(idx) + 1, dtype=torch.int64, device=dev)
-        eptr = torch.zeros(len(idx) + 1, dtype=torch.int64, device=dev)
-        nptr[1:] = torch.cumsum(ncnt, 0)
-        eptr[1:] = torch.cumsum(ecnt, 0)
-        N, E = int(nptr[-1]), int(eptr[-1])
-        gb = torch.repeat_interleave(torch.arange(len(idx), device=dev), ncnt, output_size=N)
-        node_src = torch.arange(N, device=dev) - nptr[gb] + n0[gb]
-        ge = torch.repeat_interleave(torch.arange(len(idx), device=dev), ecnt, output_size=E)
-        edge_src = torch.arange(E, device=dev) - eptr[ge] + e0[ge]
-        ei = self.data.edge_index[:, edge_src] + nptr[ge].unsqueeze(0)
-        return Batch.from_arrays(self.data.x[node_src], ei, self.data.edge_type[edge_src], gb,
-                                 self.data.y[idx], len(idx), dev)
+        return self.store.extract(idx=indices)
+
+    def get(self, idx):
+        b = self.store.extract(idx=np.asarray([idx], dtype=np.int64))
+        return Data(b.x, b.edge_index, edge_type=b.edge_type, y=b.y)

@@ -93,6 +93,30 @@ int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int ma
                        const igmc_extract_ws_t* W, const float* class_values,
                        const igmc_batch_out_t* O, int* err, void* stream);
 
+/* Device-resident store of pre-extracted subgraphs: the reference's static `MyDataset` keeps
+ * `(data, slices)` = every graph's tensors concatenated WITHOUT node offsets plus per-graph boundaries
+ * (util_functions.py:92,108-109).  Same content here, in compact types, plus the adjacency. */
+typedef struct {
+  const int32_t* node_off;    /* [G+1] */
+  const int32_t* edge_off;    /* [G+1] directed edges */
+  const uint8_t* node_label;  /* [sum n] */
+  const int32_t* node_gid;    /* [sum n] */
+  const int32_t* edge_src;    /* [sum e] graph-local node ids */
+  const int32_t* edge_dst;    /* [sum e] */
+  const uint8_t* edge_type;   /* [sum e] */
+  const float* y;             /* [G] */
+  const int32_t* graph_nu;    /* [G] */
+  const int32_t* adj_ptr;     /* [sum n + G] per graph n+1 graph-local list offsets */
+  const uint32_t* adj_in;     /* [sum e] */
+  const int32_t* adj_eid;     /* [sum e] graph-local directed edge ids */
+} igmc_store_t;
+
+/* Mini-batch assembly from the store for graphs idx[0..B): what InMemoryDataset.get + Batch.from_data_list do
+ * for the static dataset (train_eval.py:46-51): concat, node-offset edge_index, build `batch`; outputs are the
+ * same buffers igmc_extract_batch fills (adjacency included, symmetric form).  One CTA per graph, no host sync. */
+int igmc_assemble_batch(const igmc_store_t* S, const int64_t* idx, int B, const igmc_batch_out_t* O, int* err,
+                        void* stream);
+
 /* Graph offsets of a foreign (PyG-collated) batch: node_ptr from `batch`, edge_ptr from the graph
  * of each edge's source.  Replaces what Batch.from_data_list knows implicitly. */
 int igmc_batch_ptrs(const int64_t* batch, const int64_t* edge_src, int N, int E, int B,
