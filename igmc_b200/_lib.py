@@ -91,7 +91,7 @@ _SIGS = {
     "igmc_grad_reduce": [C.POINTER(Model), vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                          C.c_float, vp, vp, vp, vp],
     "igmc_adam_step": [vp, vp, vp, vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_float,
-                       C.c_float, vp],
+                       C.c_float, vp, vp, C.c_float, vp],
     "igmc_prep_weights": [C.POINTER(Model), vp, vp, vp],
     "igmc_build_info": [],
     "igmc_model_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int],

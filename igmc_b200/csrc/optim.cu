@@ -154,8 +154,10 @@ k_grad_reduce(igmc_model_t M, const float* __restrict__ params, int B, int rows,
 __global__ void k_adam(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int64_t* __restrict__ step_count, int* __restrict__ ticket, int n,
                        float lr_val, const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd,
-                       float grad_mul) {
+                       float grad_mul, const float* __restrict__ loss_in, float* __restrict__ loss_acc,
+                       float loss_weight) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0 && loss_acc) loss_acc[0] += loss_in[0] * loss_weight;   // epoch loss bookkeeping (train_eval.py:176)
   const int64_t step_i = step_count[0] + 1;
   if (i < n) {
     const float lr = lr_dev ? *lr_dev : lr_val;
@@ -205,12 +207,13 @@ extern "C" int igmc_grad_reduce(const igmc_model_t* M, const float* params, int 
 
 extern "C" int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
                               int64_t* step_count, int n, float lr, const float* lr_dev, float beta1, float beta2,
-                              float eps, float weight_decay, float grad_mul, void* stream) {
+                              float eps, float weight_decay, float grad_mul, const float* loss_in, float* loss_acc,
+                              float loss_weight, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   // step_count points at [int64 step | int32 ticket]: the word after the counter is the kernel's completion ticket
   int* ticket = reinterpret_cast<int*>(step_count + 1);
   k_adam<<<(n + 255) / 256, 256, 0, st>>>(params, grad, exp_avg, exp_avg_sq, step_count, ticket, n, lr, lr_dev, beta1,
-                                          beta2, eps, weight_decay, grad_mul);
+                                          beta2, eps, weight_decay, grad_mul, loss_in, loss_acc, loss_weight);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
 }

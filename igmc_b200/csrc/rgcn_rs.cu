@@ -12,6 +12,7 @@
 // a K=n weight-gradient tile GEMM, and the (att,basis) chain rule applied to the per-CTA dW_r.
 // No float atomics; every reduction has a fixed order (bitwise run-to-run deterministic).
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "../../include/igmc_b200.h"
@@ -381,7 +382,8 @@ __device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024, 1)
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
 k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
              int lcap, int chunk, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y,
@@ -614,7 +616,8 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
 // ------------------------------------------------------------------------------------------------
 constexpr int DPS_ = 40;   // row stride of the own-rows dpre copy (B operand of the weight-gradient tiles)
 
-__global__ void __launch_bounds__(1024, 1)
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
 k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
               const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
               int lcap, int chunk, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred,
@@ -962,7 +965,15 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
   size_t left = limit - base - rows * SSmax * 4;
   size_t lc = left / 4;
   if (lc > 16384) lc = 16384;
-  *threads = 1024;
+  {
+    // 1024 threads (64 registers) or 512 threads (128 registers: no address rematerialisation, fewer instructions)
+    static int nt_env = -1;
+    if (nt_env < 0) {
+      const char* e = getenv("IGMC_RS_THREADS");
+      nt_env = e ? atoi(e) : 0;
+    }
+    *threads = (nt_env == 512 || nt_env == 1024) ? nt_env : 1024;
+  }
   *chunk = (int)rows;
   *lcap = (int)lc;
   *smem = base + rows * SSmax * 4 + lc * 4;
@@ -997,7 +1008,10 @@ int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_l
   size_t smem;
   int rc = rs_plan(M, n_cap, cluster, 0, &threads, &smem, &lcap, &chunk);
   if (rc) return rc;
-  return launch_cluster(rs::k_forward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
+  if (threads == 512)
+    return launch_cluster(rs::k_forward_rs<512>, B * cluster, threads, smem, cluster, st, *M, params, node_label,
+                          node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, err);
+  return launch_cluster(rs::k_forward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
                         edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, err);
 }
 
@@ -1010,7 +1024,10 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
   size_t smem;
   int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem, &lcap, &chunk);
   if (rc) return rc;
-  return launch_cluster(rs::k_backward_rs, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
+  if (threads == 512)
+    return launch_cluster(rs::k_backward_rs<512>, B * cluster, threads, smem, cluster, st, *M, params, node_label,
+                          node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, err);
+  return launch_cluster(rs::k_backward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
                         edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, err);
 }
 

@@ -391,7 +391,7 @@ class FusedAdam(torch.optim.Optimizer):
                                      exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
 
     @torch.no_grad()
-    def step(self, grad_mul=1.0, lr_dev=None):
+    def step(self, grad_mul=1.0, lr_dev=None, loss_in=None, loss_acc=None, loss_weight=0.0):
         lib = _lib.load()
         g = self.param_groups[0]
         m = self.model
@@ -400,7 +400,8 @@ class FusedAdam(torch.optim.Optimizer):
                                       m.flat_params.numel(), float(g["lr"]), _lib.ptr(lr_dev),
                                       float(g["betas"][0]),
                                       float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
-                                      float(grad_mul), _stream_ptr()), "igmc_adam_step")
+                                      float(grad_mul), _lib.ptr(loss_in), _lib.ptr(loss_acc) if loss_in is not None else None,
+                                      float(loss_weight), _stream_ptr()), "igmc_adam_step")
 
     def zero_grad(self, set_to_none=False):
         pass  # flat_grad is fully overwritten by every fused_step

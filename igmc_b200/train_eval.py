@@ -103,18 +103,16 @@ class TrainEngine(object):
             loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         if self.world > 1:
             dist.all_reduce(self.model.flat_grad)
-        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev)
-        self.last_loss.copy_(loss)
-        self.loss_acc.add_(loss * float(G))
+        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
+        self.last_loss = loss
 
     def _launch_static(self, idx, G):
         batch = self.dataset.extract_batch(idx)
         loss = self.model.fused_step(batch, ARR=self.ARR / self.world, global_num_graphs=G)
         if self.world > 1:
             dist.all_reduce(self.model.flat_grad)
-        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev)
-        self.last_loss.copy_(loss)
-        self.loss_acc.add_(loss * float(G))
+        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
+        self.last_loss = loss
 
     def stage(self, idx, epoch, G):
         """fill the next pinned slot with this step's inputs and enqueue its H2D copy."""
@@ -175,9 +173,8 @@ class TrainEngine(object):
             loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         if self.world > 1:
             dist.all_reduce(self.model.flat_grad)
-        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev)
-        self.last_loss.copy_(loss)
-        self.loss_acc.add_(loss * float(G))
+        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
+        self.last_loss = loss
         if nb_next > 0:
             main.wait_stream(self.side)
 

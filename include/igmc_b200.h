@@ -227,10 +227,13 @@ int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, int gpar
  * the sqrt, no amsgrad) on the flat buffers.  `step_count` points at TWO device int64 words: the step
  * counter (incremented by the kernel) and a zero-initialised completion ticket;
  * grad is multiplied by grad_mul first (1/world after an NCCL sum); `lr_dev` (optional device float)
- * overrides `lr` so LR decay does not invalidate a captured graph. */
+ * overrides `lr` so LR decay does not invalidate a captured graph.  Optional bookkeeping of the reference's
+ * `total_loss += loss.item() * num_graphs` (train_eval.py:176) without a host sync: loss_acc[0] += loss_in[0] *
+ * loss_weight. */
 int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_avg_sq,
                    int64_t* step_count, int n, float lr, const float* lr_dev, float beta1, float beta2,
-                   float eps, float weight_decay, float grad_mul, void* stream);
+                   float eps, float weight_decay, float grad_mul, const float* loss_in, float* loss_acc,
+                   float loss_weight, void* stream);
 
 /* Version / build info: returns the compiled SM arch (100) so the host can refuse stale builds. */
 int igmc_build_info(void);
