@@ -972,7 +972,11 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
       const char* e = getenv("IGMC_RS_THREADS");
       nt_env = e ? atoi(e) : 0;
     }
-    *threads = (nt_env == 512 || nt_env == 1024) ? nt_env : 1024;
+    // default: 512 threads when the weight-gradient tiles fit 4 per warp with 16 warps (R <= 7); measured 4 % faster
+    // per step than 1024 threads at R = 5 (profiles/README.md)
+    int nt = (nt_env == 512 || nt_env == 1024) ? nt_env : 512;
+    if ((tiles + (nt >> 5) - 1) / (nt >> 5) > 4) nt = 1024;
+    *threads = nt;
   }
   *chunk = (int)rows;
   *lcap = (int)lc;
