@@ -65,7 +65,7 @@ class Model(C.Structure):
                 ("off_root", C.c_int32 * MAX_LAYERS), ("off_bias", C.c_int32 * MAX_LAYERS),
                 ("off_lin1_w", C.c_int32), ("off_lin1_b", C.c_int32), ("off_lin2_w", C.c_int32),
                 ("off_lin2_b", C.c_int32), ("conv_param_count", C.c_int32), ("param_count", C.c_int32),
-                ("multiply_by", C.c_float)]
+                ("multiply_by", C.c_float), ("readout", C.c_int32)]
 
 
 class Dropout(C.Structure):
@@ -76,6 +76,17 @@ class Dropout(C.Structure):
 class Saved(C.Structure):
     _fields_ = [("states", vp), ("zsave", vp), ("inv_deg", vp), ("feat", vp), ("hid", vp),
                 ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp), ("wprep", vp), ("prof", vp)]
+
+
+class SortPool(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("k", "width", "state_stride", "c1", "c2", "kw2", "t1", "t2", "dense_dim",
+                                         "off_conv1_w", "off_conv1_b", "off_conv2_w", "off_conv2_b", "off_lin1_w",
+                                         "off_lin1_b", "off_lin2_w", "off_lin2_b", "param_begin", "param_end")]
+
+
+class SortPoolSaved(C.Structure):
+    _fields_ = [(k, vp) for k in ("rank", "perm", "act1", "pool", "flat", "hid", "hid_gscale", "pred", "dhid",
+                                  "gpart")]
 
 
 _SIGS = {
@@ -95,6 +106,11 @@ _SIGS = {
     "igmc_prep_weights": [C.POINTER(Model), vp, vp, vp],
     "igmc_build_info": [],
     "igmc_model_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int],
+    "igmc_sortpool_plan": [C.POINTER(SortPool), C.c_int, C.c_int],
+    "igmc_sortpool_forward": [C.POINTER(SortPool), vp, vp, vp, C.c_int, C.c_int, C.POINTER(Dropout), C.c_int,
+                              C.POINTER(SortPoolSaved), vp, C.c_float, vp, vp, vp, vp],
+    "igmc_sortpool_backward": [C.POINTER(SortPool), vp, vp, vp, C.c_int, C.c_int, C.POINTER(SortPoolSaved), vp, vp,
+                               C.c_float, vp, vp, vp],
 }
 
 EXPORTS = tuple(_SIGS)

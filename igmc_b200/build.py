@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libigmc_b200.so")
-SOURCES = ["extract.cu", "batch.cu", "rgcn.cu", "rgcn_rs.cu", "optim.cu"]
+SOURCES = ["extract.cu", "batch.cu", "rgcn.cu", "rgcn_rs.cu", "optim.cu", "sortpool.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-shared", "-DIGMC_SM_ARCH=100"]

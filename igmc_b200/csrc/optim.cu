@@ -78,6 +78,8 @@ k_grad_reduce(igmc_model_t M, const float* __restrict__ params, int B, int rows,
             if (qa >= 0 && qa < R * NB) skip = true;   // written by the ARR block (l, r)
           }
         }
+      } else if (M.readout != 0) {
+        skip = true;   // readout parameters belong to the external readout's gradient kernel
       } else if (p >= M.off_lin1_w && p < M.off_lin1_w + L1O * F) {
         const int q = p - M.off_lin1_w, o = q / F, i = q - o * F;      // lin1.weight[o][i]
         for (int g = 0; g < B; ++g) s = fmaf(dhid[(size_t)g * L1O + o], feat[(size_t)g * F + i], s);

@@ -167,7 +167,7 @@ k_forward(igmc_model_t M, const float* __restrict__ params, const uint8_t* __res
   }
   __syncthreads();
   const int tu = s_t[0], ti = s_t[1];
-  if (tu >= n || ti >= n) {
+  if (M.readout == 0 && (tu >= n || ti >= n)) {
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
     return;
   }
@@ -240,6 +240,7 @@ k_forward(igmc_model_t M, const float* __restrict__ params, const uint8_t* __res
     float* t = HA; HA = HB; HB = t;
   }
 
+  if (M.readout != 0) return;   // concat_states only: an external readout (csrc/sortpool.cu) takes over
   // ---- readout: concat rows of the target user and item (models.py:205-207) ----
   for (int c = tid; c < F; c += MP_THREADS) {
     const int node = c < CW ? tu : ti;
@@ -326,19 +327,22 @@ k_backward(igmc_model_t M, const float* __restrict__ params, const uint8_t* __re
   const uint32_t* oadj = sym ? A.in_adj : A.out_adj;
   const int32_t* oeid = sym ? A.in_eid : A.out_eid;
   const int in0 = M.in_dim0;
-  const int tu = S.target[2 * g] - nb, ti = S.target[2 * g + 1] - nb;
+  const bool ext = M.readout != 0;   // d concat_states comes from an external readout (S.dstate)
+  const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
   float* gp = gpart + (size_t)g * M.conv_param_count;
 
   // ---- readout backward: d hid, d feat (models.py:211-213) ----
-  const float dp = dpred[g];
-  for (int o = tid; o < L1O; o += MP_THREADS) {
-    const float d = dp * params[M.off_lin2_w + o] * S.hid_gscale[(size_t)g * L1O + o];
-    dhid_s[o] = d;
-    dhid_out[(size_t)g * L1O + o] = d;
+  if (!ext) {
+    const float dp = dpred[g];
+    for (int o = tid; o < L1O; o += MP_THREADS) {
+      const float d = dp * params[M.off_lin2_w + o] * S.hid_gscale[(size_t)g * L1O + o];
+      dhid_s[o] = d;
+      dhid_out[(size_t)g * L1O + o] = d;
+    }
   }
   for (int v = tid; v < n; v += MP_THREADS) invdeg[v] = S.inv_deg[nb + v];
   __syncthreads();
-  {
+  if (!ext) {
     const float* W1 = params + M.off_lin1_w;
     for (int i = tid; i < F; i += MP_THREADS) {
       float s = 0.f;
@@ -347,10 +351,11 @@ k_backward(igmc_model_t M, const float* __restrict__ params, const uint8_t* __re
     }
   }
   __syncthreads();
-  // d h_L : only the two target rows receive gradient from the readout
+  // d h_L : only the two target rows receive gradient from the IGMC readout
   for (int idx = tid; idx < n * HID; idx += MP_THREADS) {
     const int v = idx >> 5, c = idx & 31;
     float gval = 0.f;
+    if (ext) gval = S.dstate[(size_t)(nb + v) * CW + (L - 1) * HID + c];
     if (v == tu) gval += dfeat[(L - 1) * HID + c];
     if (v == ti) gval += dfeat[CW + (L - 1) * HID + c];
     GA[hix(v, c)] = gval;
@@ -367,6 +372,7 @@ k_backward(igmc_model_t M, const float* __restrict__ params, const uint8_t* __re
       float hp, gval = 0.f;
       if (l > 0) {
         hp = S.states[(size_t)(nb + v) * CW + (l - 1) * HID + c];
+        if (ext) gval = S.dstate[(size_t)(nb + v) * CW + (l - 1) * HID + c];
         if (v == tu) gval += dfeat[(l - 1) * HID + c];
         if (v == ti) gval += dfeat[CW + (l - 1) * HID + c];
       } else {
@@ -573,6 +579,7 @@ int check_model(const igmc_model_t* M) {
   if (M->num_bases != 2 && M->num_bases != 4) return -11;
   if (M->num_relations < 1 || M->num_relations > 256) return -12;
   if (M->in_dim0 < 1 || M->in_dim0 > HID) return -13;
+  if (M->readout != 0 && M->readout != 1) return -19;
   return 0;
 }
 
@@ -587,8 +594,8 @@ int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_l
                int* err, cudaStream_t st);
 int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                 const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
-                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, float* dstate, int cluster,
-                int* err, cudaStream_t st);
+                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, int cluster, int* err,
+                cudaStream_t st);
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st);
 
@@ -652,12 +659,13 @@ extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const u
   int rc = check_model(M);
   if (rc) return rc;
   if (!S->zsave) return -14;
+  if (M->readout != 0 && !S->dstate) return -17;
   cudaStream_t st = (cudaStream_t)stream;
   if (cluster > 0) {
     if (!rs_supported(M)) return -16;
-    if (!S->dstate || !S->wprep) return -17;
-    return rs_backward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, dpred, gpart, dhid, S->dstate,
-                       cluster, err, st);
+    if (!S->wprep) return -17;
+    return rs_backward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, dpred, gpart, dhid, cluster, err,
+                       st);
   }
   const size_t smem = bwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
   if (smem > 227 * 1024) return -3;

@@ -435,8 +435,9 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   // in-lists of the own nodes -> shared memory; kept in-degree (dropout_adj is applied once, models.py:193)
   const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap,
                                ibuf, own_cap, chunk, ws, invdeg, S.inv_deg);
+  const bool ext = M.readout != 0;   // concat_states only: an external readout (csrc/sortpool.cu) takes over
   const int tu = s_t[0], ti = s_t[1];
-  if (tu >= n || ti >= n) {
+  if (!ext && (tu >= n || ti >= n)) {
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
     return;
   }
@@ -550,13 +551,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     IGMC_STAMP(7 + 6 * l);
     float* t = H; H = Hn; Hn = t;
     // concat_states rows of the two target nodes (models.py:203-207), all rows are local now
-    if (rank == 0 && tid < 2 * HID) {
+    if (rank == 0 && !ext && tid < 2 * HID) {
       const int node = tid < HID ? tu : ti, c = tid & 31;
       feat_s[(tid < HID ? 0 : CW) + l * HID + c] = H[hix(node, c)];
     }
   }
 
-  if (rank != 0) return;
+  if (rank != 0 || ext) return;
   // ---- readout (models.py:205-215), one CTA of the cluster ----
   __syncthreads();
   for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
@@ -657,7 +658,8 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const bool sym = A.symmetric != 0;
   const Split own = own_range(n, rank, CL);
   const int n_own = own.hi - own.lo;
-  const int tu = S.target[2 * g] - nb, ti = S.target[2 * g + 1] - nb;
+  const bool ext = M.readout != 0;   // d concat_states comes from an external readout (S.dstate)
+  const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
   float* gp = gpart + ((size_t)g * CL + rank) * M.conv_param_count;
   IGMC_STAMP(0);
   // out-lists of the own nodes (symmetric batches: the in-lists with mirrored edge ids)
@@ -666,15 +668,17 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
                                nullptr);
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
-  const float dp = dpred[g];
-  for (int o = tid; o < L1O; o += NT) {
-    const float d = dp * params[M.off_lin2_w + o] * S.hid_gscale[(size_t)g * L1O + o];
-    dhid_s[o] = d;
-    if (rank == 0) dhid_out[(size_t)g * L1O + o] = d;
+  if (!ext) {
+    const float dp = dpred[g];
+    for (int o = tid; o < L1O; o += NT) {
+      const float d = dp * params[M.off_lin2_w + o] * S.hid_gscale[(size_t)g * L1O + o];
+      dhid_s[o] = d;
+      if (rank == 0) dhid_out[(size_t)g * L1O + o] = d;
+    }
   }
   for (int v = tid; v < n; v += NT) invdeg[v] = S.inv_deg[nb + v];
   __syncthreads();
-  {
+  if (!ext) {
     // d feat[i] = sum_o W1[o][i] d hid[o]: thread slice p of NT/F takes every (NT/F)-th o, partials in `stage`
     const float* W1 = params + M.off_lin1_w;
     const int parts = max(1, NT / F);
@@ -699,6 +703,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     for (int idx = tid; idx < n * HID; idx += NT) {
       const int v = idx >> 5, c = idx & 31;
       float dh = 0.f;
+      if (ext) dh = __ldg(S.dstate + (size_t)(nb + v) * CW + (L - 1) * HID + c);
       if (v == tu) dh += dfeat[(L - 1) * HID + c];
       if (v == ti) dh += dfeat[CW + (L - 1) * HID + c];
       DHtop[hix(v, c)] = dh;
@@ -800,6 +805,10 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
             if (r < n_own) {
               const int u = own.lo + r;
               float2 o = make_float2(d[2 * half], d[2 * half + 1]);
+              if (ext) {
+                const float2 sd = __ldg(reinterpret_cast<const float2*>(S.dstate + (size_t)(nb + u) * CW + (l - 1) * HID + cc));
+                o.x += sd.x; o.y += sd.y;
+              }
               if (u == tu) { o.x += dfeat[(l - 1) * HID + cc]; o.y += dfeat[(l - 1) * HID + cc + 1]; }
               if (u == ti) { o.x += dfeat[CW + (l - 1) * HID + cc]; o.y += dfeat[CW + (l - 1) * HID + cc + 1]; }
               const int off = hix(u, cc);
@@ -1021,9 +1030,8 @@ int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_l
 
 int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                 const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
-                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, float* dstate, int cluster,
-                int* err, cudaStream_t st) {
-  (void)dstate;
+                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, int cluster, int* err,
+                cudaStream_t st) {
   int threads, lcap, chunk;
   size_t smem;
   int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem, &lcap, &chunk);

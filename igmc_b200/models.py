@@ -85,7 +85,7 @@ class _IGMCFunction(torch.autograd.Function):
         model._launch_backward(ctx.batch, ctx.drop, ctx.saved,
                                (grad_out.float() * float(model.multiply_by)).contiguous())
         model._launch_grad_reduce(ctx.batch, ctx.saved, loss_scale=0.0, arr=0.0, with_loss=False)
-        grads = [model.flat_grad[o:o + n].view(s).clone() for (o, n, s) in model._layout]
+        grads = [model._pview(model.flat_grad, e).clone() for e in model._layout]
         return (None, None, None, None) + tuple(grads)
 
 
@@ -133,18 +133,29 @@ class IGMC(nn.Module):
         yield ("lin2_w", 0, self.lin2.weight)
         yield ("lin2_b", 0, self.lin2.bias)
 
+    def _slot(self, kind, l, p):
+        """(floats reserved in the bucket, padded shape or None) of one parameter."""
+        return p.numel(), None
+
+    @staticmethod
+    def _pview(buf, e):
+        """view of layout entry ``e`` = (offset, slot size, shape[, padded shape]) inside a flat buffer."""
+        o, n, s = e[:3]
+        if len(e) == 3:
+            return buf[o:o + n].view(s)
+        return buf[o:o + n].view(e[3])[..., :s[-1]]   # padded along the last (output channel) dimension
+
     def _flatten(self):
         """(re)create flat_params / flat_grad on the parameters' device and alias every parameter."""
         items = list(self._named_order())
         dev = items[0][2].device
-        off, layout, m = 0, [], _lib.Model()
+        off, layout, m, offs = 0, [], _lib.Model(), {}
         m.num_layers, m.num_relations, m.num_bases, m.in_dim0 = len(self.convs), self.num_relations, \
             self.num_bases, self.num_features
+        m.conv_param_count = -1
         for kind, l, p in items:
-            n = p.numel()
-            if kind == "lin1_w":
-                m.conv_param_count = off
-            layout.append((off, n, tuple(p.shape)))
+            n, pad = self._slot(kind, l, p)
+            layout.append((off, n, tuple(p.shape)) if pad is None else (off, n, tuple(p.shape), tuple(pad)))
             if kind == "att":
                 m.off_att[l] = off
             elif kind == "basis":
@@ -154,27 +165,32 @@ class IGMC(nn.Module):
             elif kind == "bias":
                 m.off_bias[l] = off
             else:
-                setattr(m, "off_" + kind, off)
+                if m.conv_param_count < 0:
+                    m.conv_param_count = off
+                offs[kind] = off
+                if hasattr(m, "off_" + kind):
+                    setattr(m, "off_" + kind, off)
             off = _align4(off + n)
         m.param_count = off
         m.multiply_by = float(self.multiply_by)
         flat = torch.zeros(off, dtype=torch.float32, device=dev)
         grad = torch.zeros(off, dtype=torch.float32, device=dev)
         with torch.no_grad():
-            for (o, n, s), (_, _, p) in zip(layout, items):
-                flat[o:o + n].copy_(p.data.reshape(-1).float())
-                p.data = flat[o:o + n].view(s)
+            for e, (_, _, p) in zip(layout, items):
+                v = self._pview(flat, e)
+                v.copy_(p.data.float())
+                p.data = v
                 p.grad = None
         self.flat_params, self.flat_grad = flat, grad
-        self._layout, self._cmodel = layout, m
+        self._layout, self._cmodel, self._offs = layout, m, offs
         self._ws = {}
         self._plans = {}
         self._wprep = None
 
     def alias_grads(self):
         """point every ``p.grad`` at its slice of ``flat_grad`` (for stock torch optimizers)."""
-        for (o, n, s), (_, _, p) in zip(self._layout, self._named_order()):
-            p.grad = self.flat_grad[o:o + n].view(s)
+        for e, (_, _, p) in zip(self._layout, self._named_order()):
+            p.grad = self._pview(self.flat_grad, e)
 
     def _apply(self, fn, *a, **kw):
         out = super()._apply(fn, *a, **kw)
@@ -358,6 +374,160 @@ class IGMC(nn.Module):
         return self.__class__.__name__
 
 
+class DGCNN_RS(IGMC):
+    """Drop-in for the reference's ``DGCNN_RS`` (models.py:123-167; constructor chain DGCNN.__init__ models.py:65-85):
+    R-GCN layers with ``latent_dim=[32,32,32,1]``, SortPooling over the last channel, two 1-D convolutions and the
+    dense head, on the same fused kernels as ``IGMC`` plus ``csrc/sortpool.cu`` for the readout.
+
+    The conv kernels run 32-wide layers, so a layer with fewer output channels (the last one) is stored padded in the
+    flat bucket: ``convs[-1].basis/root/bias`` are strided views of a 32-wide slot whose other columns are zero and stay
+    zero (their gradients are exactly zero).  ``state_dict`` keys and shapes are the reference's.
+
+    ``k < 1`` is the reference's percentile rule (models.py:69-73); for datasets above 2000 graphs the node counts are
+    taken from 2000 evenly spaced graphs instead of all of them (the dynamic dataset extracts on access).
+    """
+
+    C1, C2, KW2 = 16, 32, 5   # conv1d_channels and the second kernel width (models.py:75-79)
+
+    def __init__(self, dataset, gconv=RGCNConv, latent_dim=[32, 32, 32, 1], k=30, num_relations=5, num_bases=2,
+                 regression=False, adj_dropout=0.2, force_undirected=False):
+        nn.Module.__init__(self)
+        if not regression:
+            raise NotImplementedError("igmc_b200.DGCNN_RS implements the regression head (x[:, 0], models.py:165)")
+        if force_undirected:
+            raise NotImplementedError("force_undirected edge dropout is not on the hot path")
+        latent_dim = [int(d) for d in latent_dim]
+        if not (1 <= len(latent_dim) <= _lib.MAX_LAYERS) or any(d != HID for d in latent_dim[:-1]) \
+                or not (1 <= latent_dim[-1] <= HID):
+            raise NotImplementedError("latent_dim must be [32, ..., 32, d] with 1 <= d <= 32")
+        if num_bases not in (2, 4):
+            raise NotImplementedError("num_bases must be 2 or 4")
+        self.regression, self.adj_dropout, self.force_undirected = regression, adj_dropout, force_undirected
+        self.side_features, self.multiply_by = False, 1
+        num_features = dataset if isinstance(dataset, int) else dataset.num_features
+        self.num_features = int(num_features)
+        if self.num_features > HID:
+            raise NotImplementedError("node feature width > 32")
+        if k < 1:   # transform percentile to number (models.py:69-73)
+            if isinstance(dataset, int):
+                raise ValueError("a percentile k needs the dataset")
+            n = len(dataset)
+            idxs = range(n) if n <= 2000 else [int(round(i * (n - 1) / 1999.0)) for i in range(2000)]
+            node_nums = sorted(int(dataset[i].num_nodes) for i in idxs)
+            k = node_nums[int(math.ceil(k * len(node_nums))) - 1]
+            k = max(10, k)
+        self.k = int(k)
+        self.num_relations, self.num_bases = int(num_relations), int(num_bases)
+        self.latent_dim = latent_dim
+        dims = [self.num_features] + latent_dim
+        self.convs = nn.ModuleList([RGCNConv(dims[l], dims[l + 1], num_relations, num_bases)
+                                    for l in range(len(latent_dim))])
+        self.total_latent_dim = sum(latent_dim)
+        self.conv1d_params1 = nn.Conv1d(1, self.C1, self.total_latent_dim, self.total_latent_dim)
+        self.maxpool1d = nn.MaxPool1d(2, 2)
+        self.conv1d_params2 = nn.Conv1d(self.C1, self.C2, self.KW2, 1)
+        dense_dim = int((self.k - 2) / 2 + 1)
+        self.dense_dim = (dense_dim - self.KW2 + 1) * self.C2
+        if self.dense_dim <= 0:
+            raise ValueError("k = %d is too small for the 1-D convolutions" % self.k)
+        self.lin1 = nn.Linear(self.dense_dim, 128)
+        self.lin2 = nn.Linear(128, 1)
+        self.drop_seed = 0x1234ABCD
+        self._step = 0
+        self._ws = {}
+        self._flatten()
+
+    def _named_order(self):
+        for l, c in enumerate(self.convs):
+            yield ("att", l, c.att)
+            yield ("basis", l, c.basis)
+            yield ("root", l, c.root)
+            yield ("bias", l, c.bias)
+        yield ("conv1_w", 0, self.conv1d_params1.weight)
+        yield ("conv1_b", 0, self.conv1d_params1.bias)
+        yield ("conv2_w", 0, self.conv1d_params2.weight)
+        yield ("conv2_b", 0, self.conv1d_params2.bias)
+        yield ("lin1_w", 0, self.lin1.weight)
+        yield ("lin1_b", 0, self.lin1.bias)
+        yield ("lin2_w", 0, self.lin2.weight)
+        yield ("lin2_b", 0, self.lin2.bias)
+
+    def _slot(self, kind, l, p):
+        if kind in ("basis", "root", "bias") and p.shape[-1] != HID:
+            pad = tuple(p.shape[:-1]) + (HID,)
+            return int(torch.Size(pad).numel()), pad
+        return p.numel(), None
+
+    def _flatten(self):
+        super()._flatten()
+        self._cmodel.readout = 1
+        o, sp = self._offs, _lib.SortPool()
+        sp.k, sp.width, sp.state_stride = self.k, self.total_latent_dim, HID * len(self.convs)
+        sp.c1, sp.c2, sp.kw2 = self.C1, self.C2, self.KW2
+        sp.t1 = self.k // 2
+        sp.t2 = sp.t1 - self.KW2 + 1
+        sp.dense_dim = self.dense_dim
+        assert sp.dense_dim == sp.c2 * sp.t2
+        sp.off_conv1_w, sp.off_conv1_b, sp.off_conv2_w, sp.off_conv2_b = o["conv1_w"], o["conv1_b"], o["conv2_w"], \
+            o["conv2_b"]
+        sp.off_lin1_w, sp.off_lin1_b, sp.off_lin2_w, sp.off_lin2_b = o["lin1_w"], o["lin1_b"], o["lin2_w"], o["lin2_b"]
+        sp.param_begin, sp.param_end = self._cmodel.conv_param_count, self._cmodel.param_count
+        self._csort = sp
+
+    def reset_parameters(self):
+        for c in self.convs:
+            c.reset_parameters()
+        self.conv1d_params1.reset_parameters()
+        self.conv1d_params2.reset_parameters()
+        self.lin1.reset_parameters()
+        self.lin2.reset_parameters()
+
+    def _workspace(self, batch, train):
+        ws = super()._workspace(batch, train)
+        if "sp" not in ws:
+            lib = _lib.load()
+            p, sp, B = batch._priv, self._csort, batch.num_graphs
+            for bw in (0, 1):
+                if lib.igmc_sortpool_plan(C.byref(sp), p["n_cap"], bw) <= 0:
+                    raise RuntimeError("igmc_b200: the SortPooling readout (k = %d) does not fit in shared memory" % self.k)
+            dev = self.flat_params.device
+            f32, i32 = dict(dtype=torch.float32, device=dev), dict(dtype=torch.int32, device=dev)
+            gp = sp.c1 * sp.width + sp.c1 + sp.c2 * sp.c1 * sp.kw2 + sp.c2
+            d = dict(rank=torch.zeros(p["node_cap"], **i32), perm=torch.zeros(B, sp.k, **i32),
+                     act1=torch.empty(B, sp.c1, sp.k, **f32), pool=torch.empty(B, sp.c1, sp.t1, **f32),
+                     flat=torch.empty(B, sp.dense_dim, **f32), hid=torch.empty(B, 128, **f32),
+                     hid_gscale=torch.empty(B, 128, **f32), pred=torch.empty(B, **f32),
+                     dhid=torch.empty(B, 128, **f32), gpart=torch.zeros(B, gp, **f32))
+            d["S"] = _lib.SortPoolSaved(*[d[k].data_ptr() for k in ("rank", "perm", "act1", "pool", "flat", "hid",
+                                                                    "hid_gscale", "pred", "dhid", "gpart")])
+            ws["sp"] = d
+        return ws
+
+    def _launch_forward(self, batch, training, drop, y=None, loss_scale=0.0):
+        lib = _lib.load()
+        _, saved = super()._launch_forward(batch, training, drop, y=None)    # concat_states only (readout = 1)
+        ws, p = saved["ws"], batch._priv
+        d, keep = drop
+        _lib.check(lib.igmc_sortpool_forward(C.byref(self._csort), self.flat_params.data_ptr(),
+                                             ws["states"].data_ptr(), p["node_ptr"].data_ptr(), batch.num_graphs,
+                                             p["n_cap"], C.byref(d), int(training), C.byref(ws["sp"]["S"]),
+                                             _lib.ptr(y), float(loss_scale),
+                                             ws["dpred"].data_ptr() if y is not None else None,
+                                             ws["sqerr"].data_ptr() if y is not None else None,
+                                             batch._err.data_ptr(), _stream_ptr()), "igmc_sortpool_forward")
+        return ws["sp"]["pred"], saved
+
+    def _launch_backward(self, batch, drop, saved, dpred):
+        lib = _lib.load()
+        ws, p = saved["ws"], batch._priv
+        _lib.check(lib.igmc_sortpool_backward(C.byref(self._csort), self.flat_params.data_ptr(),
+                                              ws["states"].data_ptr(), p["node_ptr"].data_ptr(), batch.num_graphs,
+                                              p["n_cap"], C.byref(ws["sp"]["S"]), dpred.data_ptr(),
+                                              ws["dstate"].data_ptr(), 1.0, self.flat_grad.data_ptr(),
+                                              batch._err.data_ptr(), _stream_ptr()), "igmc_sortpool_backward")
+        super()._launch_backward(batch, drop, saved, dpred)
+
+
 class FusedAdam(torch.optim.Optimizer):
     """``torch.optim.Adam`` semantics (train_eval.py:54) as ONE kernel over the flat bucket.
 
@@ -374,21 +544,21 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(2, dtype=torch.int64, device=dev)   # [step | completion ticket of the kernel]
-        for (o, k, s), p in zip(model._layout, params):
-            self.state[p] = dict(step=self.step_count[0], exp_avg=self.exp_avg[o:o + k].view(s),
-                                 exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
+        for e, p in zip(model._layout, params):
+            self.state[p] = dict(step=self.step_count[0], exp_avg=model._pview(self.exp_avg, e),
+                                 exp_avg_sq=model._pview(self.exp_avg_sq, e))
 
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
         params = [p for (_, _, p) in self.model._named_order()]
         with torch.no_grad():
-            for (o, k, s), p in zip(self.model._layout, params):
+            for e, p in zip(self.model._layout, params):
                 st = self.state[p]
-                self.exp_avg[o:o + k].copy_(st["exp_avg"].reshape(-1))
-                self.exp_avg_sq[o:o + k].copy_(st["exp_avg_sq"].reshape(-1))
+                ea, es = self.model._pview(self.exp_avg, e), self.model._pview(self.exp_avg_sq, e)
+                ea.copy_(st["exp_avg"])
+                es.copy_(st["exp_avg_sq"])
                 self.step_count[0] = int(st["step"])
-                self.state[p] = dict(step=self.step_count[0], exp_avg=self.exp_avg[o:o + k].view(s),
-                                     exp_avg_sq=self.exp_avg_sq[o:o + k].view(s))
+                self.state[p] = dict(step=self.step_count[0], exp_avg=ea, exp_avg_sq=es)
 
     @torch.no_grad()
     def step(self, grad_mul=1.0, lr_dev=None, loss_in=None, loss_acc=None, loss_weight=0.0):

@@ -154,6 +154,9 @@ typedef struct {
   int32_t conv_param_count;  /* params before off_lin1_w */
   int32_t param_count;
   float multiply_by;
+  int32_t readout;           /* 0: IGMC target-row readout inside igmc_forward/igmc_backward (models.py:203-215);
+                              * 1: none - igmc_forward stops at concat_states, igmc_backward takes S.dstate =
+                              *    d loss / d concat_states from an external readout (igmc_sortpool_*) */
 } igmc_model_t;
 
 /* Dropout draws of one step.  edge_keep/hidden_keep (uint8, 1 = keep) inject explicit draws
@@ -178,7 +181,8 @@ typedef struct {
   float* pred;      /* [B] */
   int32_t* target;  /* [B*2] batch-global index of the target user / item node */
   int32_t node_cap; /* row count of one zsave / dstate layer slab */
-  float* dstate;    /* [L * node_cap * 32] d h_l rows exchanged between the CTAs of a cluster (backward) */
+  float* dstate;    /* [node_cap * 32*L] d loss / d concat_states written by an external readout; read by
+                     * igmc_backward when readout = 1, unused otherwise */
   const float* wprep; /* [L * 2 * 32*((R+1)*32+4)] per-step prepared weights (igmc_prep_weights), cluster plans only */
   long long* prof;    /* optional debug: [grid][32] clock64() stamps of the kernel phases (cluster plans), or NULL */
 } igmc_saved_t;
@@ -234,6 +238,54 @@ int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_
                    int64_t* step_count, int n, float lr, const float* lr_dev, float beta1, float beta2,
                    float eps, float weight_decay, float grad_mul, const float* loss_in, float* loss_acc,
                    float loss_weight, void* stream);
+
+/* ---- SortPooling + 1-D convolution readout of DGCNN_RS (models.py:123-167 over DGCNN.__init__ models.py:65-85) ----
+ * Consumes the concat_states a readout=1 igmc_forward produced.  latent_dim = [32,...,32,1] is run by the conv
+ * kernels as 32-wide layers whose unused output columns have zero weights, so a states row has `state_stride` =
+ * 32*L floats of which the first `width` = sum(latent_dim) are real and the sort key is column width-1.
+ * Parameters (same flat bucket, reference state_dict names):
+ *   conv1d_params1.weight [c1,1,width] .bias [c1] | conv1d_params2.weight [c2,c1,kw2] .bias [c2] |
+ *   lin1.weight [128, dense_dim] .bias [128] | lin2.weight [1,128] .bias [1],  dense_dim = c2 * (k/2 - kw2 + 1). */
+typedef struct {
+  int32_t k, width, state_stride;
+  int32_t c1, c2, kw2;       /* 16, 32, 5 (models.py:75-79) */
+  int32_t t1, t2, dense_dim; /* k/2 ; t1 - kw2 + 1 ; c2 * t2 */
+  int32_t off_conv1_w, off_conv1_b, off_conv2_w, off_conv2_b, off_lin1_w, off_lin1_b, off_lin2_w, off_lin2_b;
+  int32_t param_begin, param_end;   /* the readout parameters' range in the flat bucket */
+} igmc_sortpool_t;
+
+typedef struct {
+  int32_t* rank;      /* [node_cap] position of every node in its graph's order (last channel descending, ties by index) */
+  int32_t* perm;      /* [B*k] batch-global node at position t, -1 = padding (graph smaller than k) */
+  float* act1;        /* [B*c1*k]  relu(conv1) */
+  float* pool;        /* [B*c1*t1] maxpool */
+  float* flat;        /* [B*dense_dim] relu(conv2), channel-major (x.view(len(x), -1), models.py:161) */
+  float* hid;         /* [B*128] relu(lin1) after dropout scaling */
+  float* hid_gscale;  /* [B*128] */
+  float* pred;        /* [B] */
+  float* dhid;        /* [B*128] backward */
+  float* gpart;       /* [B * (c1*width + c1 + c2*c1*kw2 + c2)] per-graph partial gradients of the two Conv1d */
+} igmc_sortpool_saved_t;
+
+/* Dynamic shared memory (bytes) of the readout kernels for graphs of up to n_cap nodes, negative if the
+ * description is inconsistent or does not fit in 227 KB. */
+int igmc_sortpool_plan(const igmc_sortpool_t* P, int n_cap, int backward);
+
+/* global_sort_pool (PyG 1.4.2) -> Conv1d -> ReLU -> MaxPool1d(2,2) -> Conv1d -> ReLU -> flatten -> lin1 ->
+ * ReLU -> Dropout(0.5) -> lin2 -> [:,0] (models.py:155-165), one CTA per graph.  With y != NULL also
+ * dpred[g] = d(mean squared error)/d pred and sqerr[g]. */
+int igmc_sortpool_forward(const igmc_sortpool_t* P, const float* params, const float* states,
+                          const int32_t* node_ptr, int B, int n_cap, const igmc_dropout_t* D, int training,
+                          const igmc_sortpool_saved_t* S, const float* y, float loss_scale, float* dpred,
+                          float* sqerr, int* err, void* stream);
+
+/* Backward of igmc_sortpool_forward: writes dstate [N * state_stride] (= d loss / d concat_states, zero for nodes
+ * that were not pooled and for the padding columns) for igmc_backward, and the readout parameters' gradients
+ * (times grad_scale) into grad[param_begin, param_end). */
+int igmc_sortpool_backward(const igmc_sortpool_t* P, const float* params, const float* states,
+                           const int32_t* node_ptr, int B, int n_cap, const igmc_sortpool_saved_t* S,
+                           const float* dpred, float* dstate, float grad_scale, float* grad, int* err,
+                           void* stream);
 
 /* Version / build info: returns the compiled SM arch (100) so the host can refuse stale builds. */
 int igmc_build_info(void);

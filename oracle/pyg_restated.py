@@ -14,6 +14,7 @@ outputs or checkpoints.  This file restates the published PyG 1.4.2 algorithms
 * ``IGMC.forward``  models.py:190-217 (concat of tanh layer outputs, target-row
   readout, lin1 -> relu -> dropout(0.5) -> lin2).
 * train-step loss  train_eval.py:157-175 (MSE mean + ARR * sum_r ||W_{r+1}-W_r||^2).
+* ``global_sort_pool``  call site models.py:155 and the ``DGCNN_RS`` readout models.py:156-167.
 
 The message function deliberately uses the reference-era formulation
 (``index_select`` of a per-edge weight + ``bmm`` + scatter-mean): it is the CPU
@@ -114,6 +115,74 @@ class IGMCRef(nn.Module):
             else:
                 z = F.dropout(z, p=0.5, training=True)
         out = self.lin2(z)[:, 0] * self.multiply_by
+        return (out, cs) if return_states else out
+
+
+def global_sort_pool(x, batch, k, num_graphs=None):
+    """PyG 1.4.2 ``global_sort_pool`` (call site models.py:108,155): dense batch padded with
+    ``x.min()-1``, rows of every graph sorted by the LAST channel descending, first k rows kept (padded if the
+    graph is smaller), padding set to 0, flattened to [B, k*D].  torch's sort is not stable; ties are resolved
+    here in favour of the lower node index (``stable=True``), which is what the CUDA path does too."""
+    B = int(batch.max()) + 1 if num_graphs is None else int(num_graphs)
+    D = x.shape[1]
+    fill = float(x.detach().min()) - 1.0
+    counts = torch.bincount(batch, minlength=B)
+    nmax = int(counts.max())
+    start = torch.cumsum(counts, 0) - counts
+    pos = torch.arange(x.shape[0]) - start[batch]
+    dense = torch.full((B, nmax, D), fill, dtype=x.dtype)
+    dense[batch, pos] = x
+    _, perm = torch.sort(dense[:, :, -1], dim=-1, descending=True, stable=True)
+    dense = torch.gather(dense, 1, perm.unsqueeze(-1).expand(-1, -1, D))
+    if nmax >= k:
+        dense = dense[:, :k]
+    else:
+        dense = torch.cat([dense, torch.full((B, k - nmax, D), fill, dtype=x.dtype)], 1)
+    dense = torch.where(dense == fill, torch.zeros_like(dense), dense)
+    return dense.reshape(B, k * D)
+
+
+class DGCNN_RSRef(nn.Module):
+    """Restated ``DGCNN_RS`` (models.py:123-167 on top of ``DGCNN.__init__`` models.py:65-85): R-GCN layers with
+    latent_dim [32,32,32,1], SortPooling, Conv1d(1,16,97,97) / MaxPool1d(2,2) / Conv1d(16,32,5,1), dense head."""
+
+    def __init__(self, num_features=4, latent_dim=(32, 32, 32, 1), k=30, num_relations=5, num_bases=2,
+                 adj_dropout=0.2, aggr="mean_all"):
+        super().__init__()
+        self.adj_dropout, self.k = adj_dropout, int(k)
+        dims = [num_features] + list(latent_dim)
+        self.convs = nn.ModuleList(
+            [RGCNConvRef(dims[l], dims[l + 1], num_relations, num_bases, aggr) for l in range(len(latent_dim))])
+        self.total_latent_dim = sum(latent_dim)
+        self.conv1d_params1 = nn.Conv1d(1, 16, self.total_latent_dim, self.total_latent_dim)
+        self.maxpool1d = nn.MaxPool1d(2, 2)
+        self.conv1d_params2 = nn.Conv1d(16, 32, 5, 1)
+        dense_dim = int((self.k - 2) / 2 + 1)
+        self.dense_dim = (dense_dim - 5 + 1) * 32
+        self.lin1 = nn.Linear(self.dense_dim, 128)
+        self.lin2 = nn.Linear(128, 1)
+
+    def forward(self, x, edge_index, edge_type, batch, edge_keep=None, hidden_keep=None, num_graphs=None,
+                return_states=False):
+        if self.training and self.adj_dropout > 0:
+            edge_index, edge_type = dropout_adj(edge_index, edge_type, self.adj_dropout, True, edge_keep)
+        states = []
+        for conv in self.convs:
+            x = torch.tanh(conv(x, edge_index, edge_type))
+            states.append(x)
+        cs = torch.cat(states, 1)
+        z = global_sort_pool(cs, batch, self.k, num_graphs).unsqueeze(1)
+        z = F.relu(self.conv1d_params1(z))
+        z = self.maxpool1d(z)
+        z = F.relu(self.conv1d_params2(z))
+        z = z.view(len(z), -1)
+        z = F.relu(self.lin1(z))
+        if self.training:
+            if hidden_keep is not None:
+                z = z * hidden_keep.to(z.dtype) * 2.0
+            else:
+                z = F.dropout(z, p=0.5, training=True)
+        out = self.lin2(z)[:, 0]
         return (out, cs) if return_states else out
 
 
