@@ -31,6 +31,9 @@ WORKLOADS = {
                            "adj_dropout=0, ARR=0.001, Adam lr 1e-3"),
     "ml_100k": ("ml_100k", 50, "ml_100k* synthetic 943x1682 nnz 80000, mnph=200, batch=50/GPU, adj_dropout=0.2"),
     "ml_1m_r02": ("ml_1m_r02", 256, "ml_1m* ratio 0.2 synthetic nnz 216045, mnph=100, batch=256/GPU"),
+    "flixster": ("flixster", 50, "flixster* synthetic 3000x3000 nnz 23556, R=10, no node cap, STATIC pre-extracted "
+                                 "subgraphs (device-resident store + batch-assembly kernel), batch=50/GPU, "
+                                 "adj_dropout=0.2"),
 }
 ARR = 0.001
 LR = 1e-3
@@ -114,7 +117,7 @@ class CpuReference(object):
     """The reference's CPU train path: per-pair extraction in a process pool (DataLoader workers,
     train_eval.py:40-45) + PyG-1.4.2-formulation model step on all host threads."""
 
-    def __init__(self, ds, batch, cores=None):
+    def __init__(self, ds, batch, cores=None, model_kind="igmc", k=30):
         import multiprocessing as mp
         import torch
         from oracle import pyg_restated
@@ -126,10 +129,21 @@ class CpuReference(object):
                                                  ds["max_nodes_per_hop"]))
         self.threads = min(self.cores, 16)
         torch.set_num_threads(self.threads)
-        torch.manual_seed(1)
-        self.model = pyg_restated.IGMCRef(4, (32, 32, 32, 32), ds["num_relations"], 4, ds["adj_dropout"]).train()
-        self.opt = torch.optim.Adam(self.model.parameters(), lr=LR)
         self.pyg = pyg_restated
+        self.build_model(model_kind, k)
+
+    def build_model(self, model_kind, k):
+        import torch
+        from oracle import pyg_restated
+        ds = self.ds
+        torch.manual_seed(1)
+        if model_kind == "dgcnn_rs":
+            self.model = pyg_restated.DGCNN_RSRef(4, (32, 32, 32, 1), k, ds["num_relations"], 4,
+                                                  ds["adj_dropout"]).train()
+        else:
+            self.model = pyg_restated.IGMCRef(4, (32, 32, 32, 32), ds["num_relations"], 4, ds["adj_dropout"]).train()
+        self.model_kind = model_kind
+        self.opt = torch.optim.Adam(self.model.parameters(), lr=LR)
 
     def extract(self, idx):
         from oracle import extract_np
@@ -141,7 +155,12 @@ class CpuReference(object):
     def model_step(self, nb):
         tb = self.pyg.to_torch_batch(nb)
         self.opt.zero_grad()
-        loss, _ = self.pyg.train_loss(self.model, tb, ARR)
+        if self.model_kind == "dgcnn_rs":
+            import torch.nn.functional as F
+            out = self.model(tb["x"], tb["edge_index"], tb["edge_type"], tb["batch"], num_graphs=tb["num_graphs"])
+            loss = F.mse_loss(out, tb["y"].view(-1)) + ARR * self.pyg.arr_regulariser(self.model)
+        else:
+            loss, _ = self.pyg.train_loss(self.model, tb, ARR)
         loss.backward()
         self.opt.step()
         return float(loss)
@@ -158,11 +177,15 @@ def run_reference(args, ds, B, rank):
     overlapped estimate min(extraction, model) are both reported (value = overlapped, as the reference
     overlaps the two with DataLoader workers)."""
     import torch
-    ref = CpuReference(ds, B)
+    ref = CpuReference(ds, B, model_kind=getattr(args, "model", "igmc"), k=getattr(args, "k", None) or 30)
     rng = np.random.default_rng(123)
     n = len(ds["train"][0])
     # give the reference its best thread count for the small per-edge bmm ops (oversubscription hurts it)
     nb0 = ref.extract(rng.choice(n, B, replace=False))
+    static = ds["name"] == "flixster"   # the reference pre-extracts this dataset once (MyDataset): model-bound steps
+    if getattr(args, "model", "igmc") == "dgcnn_rs" and not getattr(args, "k", None):
+        nn_ = np.sort(np.bincount(nb0["batch"], minlength=B))   # percentile rule of models.py:69-73 on one batch
+        ref.build_model("dgcnn_rs", max(10, int(nn_[int(np.ceil(0.6 * len(nn_))) - 1])))
     best = (1e30, ref.threads)
     for th in sorted({8, 16, 32, 64, ref.cores} & set(range(1, ref.cores + 1))):
         torch.set_num_threads(th)
@@ -188,23 +211,26 @@ def run_reference(args, ds, B, rank):
         steps += 1
     ref.close()
     ext_rate, mod_rate = B * steps / t_ext, B * steps / t_mod
-    value = min(ext_rate, mod_rate)
+    value = mod_rate if static else min(ext_rate, mod_rate)
     return dict(value=value, steps=steps, ms_per_step=1000.0 * B / value, cores=ref.cores,
                 extraction_subgraphs_per_s=ext_rate, model_subgraphs_per_s=mod_rate,
                 serial_subgraphs_per_s=B * steps / (t_ext + t_mod),
                 sample="%d steps of %d subgraphs (extraction in a %d-process pool + PyG-1.4.2-formulation "
-                       "fwd/bwd/Adam on %d torch threads, best of {8,16,32,64,all}); value=min(extraction, model) "
-                       "as the reference overlaps them" % (steps, B, ref.cores, ref.threads))
+                       "fwd/bwd/Adam on %d torch threads, best of {8,16,32,64,all}); %s"
+                       % (steps, B, ref.cores, ref.threads,
+                          "value=model rate: the static dataset is pre-extracted once" if static else
+                          "value=min(extraction, model) as the reference overlaps them"))
 
 
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(stats, in_dims=(4, 32, 32, 32)):
-    """SURVEY.md §8(d) compulsory HBM bytes for a batch with the measured totals in `stats`."""
+def algorithmic_bytes(stats, in_dims=(4, 32, 32, 32), static=False, keep=1.0):
+    """SURVEY.md §8(d) compulsory HBM bytes for a batch with the measured totals in `stats`
+    (`keep` = 1 - adj_dropout scales the per-edge terms of the model passes; static: 24 E + 24 n slice read)."""
     n, E, d0, Du, B = stats["n"], stats["E"], stats["d0"], stats["Du"], stats["B"]
-    b_ext = 4 * d0 + 5 * Du + 24 * E + 16 * n + 8 * n + 4 * B
-    b_fwd = sum(9 * E + 4 * n * (i + 32) for i in in_dims) + (4 * 2 * 128 + 4) * B
+    b_ext = (24 * E + 24 * n) if static else (4 * d0 + 5 * Du + 24 * E + 16 * n + 8 * n + 4 * B)
+    b_fwd = sum(9 * keep * E + 4 * n * (i + 32) for i in in_dims) + (4 * 2 * 128 + 4) * B
     return dict(extract=b_ext, forward=b_fwd, backward=2 * b_fwd, step=b_ext + 3 * b_fwd)
 
 
@@ -219,8 +245,10 @@ def batch_stats(ds, engine, idx_list):
     for idx in idx_list:
         b = ex.extract(idx=idx, seed=SAMPLE_SEED)
         cnt = b._priv["counts"].cpu().numpy()
-        nu, nv, cu, cv = ex.node_lists(len(idx))
         tot["n"] += int(cnt[0]); tot["E"] += int(cnt[1]); tot["B"] += len(idx)
+        if not hasattr(ex, "node_lists"):   # static store: the batch is a slice read, no CSR scan
+            continue
+        nu, nv, cu, cv = ex.node_lists(len(idx))
         tot["d0"] += int(rowdeg[tu[idx]].sum() + coldeg[tv[idx]].sum())
         for k in range(len(idx)):
             tot["Du"] += int(rowdeg[nu[k, :cu[k]]].sum())
@@ -231,9 +259,9 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from igmc_b200.data import make_synthetic_dataset
-    from igmc_b200.models import IGMC, FusedAdam
+    from igmc_b200.models import DGCNN_RS, IGMC, FusedAdam
     from igmc_b200.train_eval import TrainEngine
-    from igmc_b200.util_functions import MyDynamicDataset
+    from igmc_b200.util_functions import MyDataset, MyDynamicDataset
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -244,11 +272,19 @@ def run_ours(args):
     preset, B, desc = WORKLOADS[args.workload]
     ds = make_synthetic_dataset(preset, seed=0)
     tu, tv, tl = ds["train"]
-    train = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, ds["max_nodes_per_hop"], None, None,
-                             ds["class_values"], seed=0)
+    static = preset == "flixster"
+    train = (MyDataset if static else MyDynamicDataset)(None, ds["adj_train"], (tu, tv), tl, 1, 1.0,
+                                                        ds["max_nodes_per_hop"], None, None, ds["class_values"],
+                                                        seed=0)
     torch.manual_seed(1)
-    model = IGMC(train, latent_dim=[32, 32, 32, 32], num_relations=ds["num_relations"], num_bases=4,
-                 regression=True, adj_dropout=ds["adj_dropout"]).cuda()
+    if args.model == "dgcnn_rs":
+        model = DGCNN_RS(train, latent_dim=[32, 32, 32, 1], k=0.6, num_relations=ds["num_relations"], num_bases=4,
+                         regression=True, adj_dropout=ds["adj_dropout"]).cuda()
+        args.k = model.k
+        desc = desc.replace("4xRGCN(32)", "DGCNN_RS 4xRGCN(32,32,32,1)") + ", model DGCNN_RS k=%d" % model.k
+    else:
+        model = IGMC(train, latent_dim=[32, 32, 32, 32], num_relations=ds["num_relations"], num_bases=4,
+                     regression=True, adj_dropout=ds["adj_dropout"]).cuda()
     if world > 1:
         dist.broadcast(model.flat_params, 0)
     opt = FusedAdam(model, lr=LR)
@@ -344,7 +380,7 @@ def run_ours(args):
     if rank == 0:
         # ---- per-kernel times (eager launches, CUDA events on the launching stream) + roofline ----
         stats = batch_stats(ds, eng, [steps_idx[value_first + k] for k in range(min(K, 20))])
-        ab = algorithmic_bytes(stats)
+        ab = algorithmic_bytes(stats, static=static, keep=1.0 - ds["adj_dropout"])
         nb_batches = min(K, 20)
         names = ("extract", "forward", "backward", "grad_reduce", "adam")
         acc = {n: 0.0 for n in names}
@@ -383,7 +419,7 @@ def run_ours(args):
         step_bytes = ab["step"] / nb_batches
         cpu = None
         if not args.skip_cpu_baseline:
-            ns = argparse.Namespace(steps=args.cpu_steps, warmup=1)
+            ns = argparse.Namespace(steps=args.cpu_steps, warmup=1, model=args.model, k=getattr(args, "k", 30))
             r = run_reference(ns, ds, B, 0)
             cpu = {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
                    "sample": r["sample"], "extraction_subgraphs_per_s": r["extraction_subgraphs_per_s"],
@@ -399,7 +435,8 @@ def run_ours(args):
             "clocks": clk,
             "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 3) * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K},
-            "gpu_launches": 7 * K,
+            # extract/assemble (2 | 1) + weight prep + forward + backward + grad_reduce + Adam (+ 3 readout launches)
+            "gpu_launches": ((6 if static else 7) + (3 if args.model == "dgcnn_rs" else 0)) * K,
             "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
                         "note": "same steps back to back without the L2 flush (informative)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -428,6 +465,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="ml_1m", choices=sorted(WORKLOADS))
+    ap.add_argument("--model", default="igmc", choices=["igmc", "dgcnn_rs"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=12)

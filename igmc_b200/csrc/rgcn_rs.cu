@@ -630,15 +630,16 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, NT = blockDim.x;
   const int L = M.num_layers, R = M.num_relations, NB = M.num_bases, CW = HID * L, F = 2 * CW;
   const int in0 = M.in_dim0, in0p = a4(in0);
-  const int SSmax = R * HID + 4, KSmax = (R + 1) * HID + 4, KRmax = (R + 1) * HID;
+  const int SSmax = R * HID + 4, KSmax = (R + 1) * HID + 4;
   const int own_cap = own_cap_of(n_cap, CL), own_cap16 = a16(own_cap);
   float* DH0 = smem;                                    // [2][n_cap][32]  d h_l of all nodes, double-buffered by layer
   float* DH1 = DH0 + (size_t)n_cap * HID;               //   parity: peers push d h_{l-1} into one while the other, turned
                                                         //   in place into dpre/deg (the gather source), is being read
   float* DP = DH1 + (size_t)n_cap * HID;                // [own_cap16][DPS_] dpre of the own rows (zero padded)
-  float* Wn = DP + (size_t)own_cap16 * DPS_;            // [32][KS]
-  float* dW = Wn + (size_t)HID * KSmax;                 // [KRp][32]
-  float* stage = dW + (size_t)KRmax * HID;              // [chunk + XR][SSmax]  |  weight-gradient tile [rows][TS]
+  float* Wn = DP + (size_t)own_cap16 * DPS_;            // [32][KS]   prepared weights of the data-gradient tiles (1)
+  float* dW = Wn;                                       // [KRp][32]  weight gradients (2): Wn is dead by then and is
+                                                        //            reloaded at the top of the next layer
+  float* stage = Wn + (size_t)HID * KSmax;              // [chunk + XR][SSmax]  |  weight-gradient tile [rows][TS]
   float* att_s = stage + (size_t)(chunk + XR) * SSmax;
   float* invdeg = att_s + a4(R * NB);
   float* dfeat = invdeg + a4(n_cap);
@@ -943,9 +944,9 @@ size_t fwd_base_fl(int n_cap, int R, int L, int CL) {   // everything except the
          (size_t)XR * ((size_t)R * HID + 4);
 }
 size_t bwd_base_fl(int n_cap, int R, int NB, int L, int CL) {
-  const size_t KSmax = (size_t)(R + 1) * HID + 4, KRmax = (size_t)(R + 1) * HID, F = 2 * HID * L;
+  const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;   // dW [(R+1)*32][32] aliases Wn [32][KSmax]
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL), own_cap16 = (size_t)a16((int)own_cap);
-  return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + KRmax * HID + a4(R * NB) + a4(n_cap) +
+  return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + a4(R * NB) + a4(n_cap) +
          a4((int)F) + L1O + HID + a4(list_ints((int)own_cap)) + (size_t)XR * ((size_t)R * HID + 4);
 }
 

@@ -11,7 +11,7 @@
 
 namespace {
 
-constexpr int SP_THREADS = 256;
+constexpr int SP_THREADS = 1024;   // 50 CTAs of work per batch: parallelism has to come from inside the CTA
 constexpr int SP_WARPS = SP_THREADS / 32;
 constexpr int L1O = IGMC_LIN1_OUT;
 
@@ -151,15 +151,18 @@ k_sortpool_forward(igmc_sortpool_t P, const float* __restrict__ params, const fl
   const float* W1 = params + P.off_lin1_w;
   const uint64_t seed = D.seed_dev ? *D.seed_dev : D.seed;
   for (int o = warp; o < L1O; o += SP_WARPS) {
-    float s0 = 0.f, s1 = 0.f;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     const float* wr = W1 + (size_t)o * P.dense_dim;
     int i = lane;
-    for (; i + 32 < P.dense_dim; i += 64) {
-      s0 = fmaf(__ldg(wr + i), flat[i], s0);
-      s1 = fmaf(__ldg(wr + i + 32), flat[i + 32], s1);
+    for (; i + 96 < P.dense_dim; i += 128) {   // four independent L2 loads in flight per lane
+      const float a0 = __ldg(wr + i), a1 = __ldg(wr + i + 32), a2 = __ldg(wr + i + 64), a3 = __ldg(wr + i + 96);
+      s0 = fmaf(a0, flat[i], s0);
+      s1 = fmaf(a1, flat[i + 32], s1);
+      s2 = fmaf(a2, flat[i + 64], s2);
+      s3 = fmaf(a3, flat[i + 96], s3);
     }
-    if (i < P.dense_dim) s0 = fmaf(__ldg(wr + i), flat[i], s0);
-    const float s = warp_sum_f(s0 + s1);
+    for (; i < P.dense_dim; i += 32) s0 = fmaf(__ldg(wr + i), flat[i], s0);
+    const float s = warp_sum_f((s0 + s1) + (s2 + s3));
     if (lane == 0) {
       const float h = fmaxf(s + params[P.off_lin1_b + o], 0.f);
       float scale = 1.f;
@@ -239,12 +242,16 @@ k_sortpool_backward(igmc_sortpool_t P, const float* __restrict__ params, const f
   {
     const float* W1 = params + P.off_lin1_w;
     for (int i = tid; i < P.dense_dim; i += SP_THREADS) {
-      float s0 = 0.f, s1 = 0.f;
-      for (int o = 0; o < L1O; o += 2) {
-        s0 = fmaf(__ldg(W1 + (size_t)o * P.dense_dim + i), dhid_s[o], s0);
-        s1 = fmaf(__ldg(W1 + (size_t)(o + 1) * P.dense_dim + i), dhid_s[o + 1], s1);
+      float s4[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int o = 0; o < L1O; o += 8) {   // eight independent L2 loads in flight
+        float w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) w[u] = __ldg(W1 + (size_t)(o + u) * P.dense_dim + i);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s4[u] = fmaf(w[u], dhid_s[o + u], s4[u]);
       }
-      dout2[i] = S.flat[(size_t)g * P.dense_dim + i] > 0.f ? s0 + s1 : 0.f;
+      const float s = ((s4[0] + s4[1]) + (s4[2] + s4[3])) + ((s4[4] + s4[5]) + (s4[6] + s4[7]));
+      dout2[i] = S.flat[(size_t)g * P.dense_dim + i] > 0.f ? s : 0.f;
     }
   }
   __syncthreads();

@@ -48,6 +48,7 @@ PRESETS = {
     "ml_100k": (943, 1682, 80000, 5, 200, 0.2),      # u1.base size, testing mode
     "ml_1m": (6040, 3706, 900188, 5, 100, 0.0),      # 1,000,209 - ceil(10%) (C4)
     "ml_1m_r02": (6040, 3706, 216045, 5, 100, 0.0),  # ratio 0.2 (C5)
+    "flixster": (3000, 3000, 23556, 10, 10000, 0.2),  # Monti split sizes, 10 rating levels, no cap
     "tiny": (60, 40, 600, 5, 10, 0.2),
 }
 
