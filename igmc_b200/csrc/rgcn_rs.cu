@@ -379,6 +379,10 @@ __device__ __forceinline__ void copy_f4(float* __restrict__ dst, const float* __
   for (int i = threadIdx.x; i < (nfloats >> 2); i += blockDim.x) d4[i] = __ldg(s4 + i);
 }
 
+// split cluster barrier: work that does not touch peer-written shared memory goes between arrive and wait
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -448,11 +452,17 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
+  // weights of a layer: the [W_r ; root] slab prepared by igmc_prep_weights + bias
+  auto load_weights = [&](int l) {
+    const int inp = l == 0 ? in0p : HID;
+    const int KS = a8(R * inp) + a8(inp) + 4;
+    copy_f4(Wn, S.wprep + (size_t)l * 2 * wprep_slab(R), HID * KS);
+    if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
+  };
+  load_weights(0);
   for (int l = 0; l < L; ++l) {
     const int inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), SS = K1p + 4, KS = K1p + inpp + 4;
-    copy_f4(Wn, S.wprep + (size_t)l * 2 * wprep_slab(R), HID * KS);
-    if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
     __syncthreads();
     IGMC_STAMP(2 + 6 * l);
     for (int c0 = 0; c0 < n_own; c0 += chunk) {
@@ -547,7 +557,10 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       __syncthreads();
     }
     IGMC_STAMP(6 + 6 * l);
-    if (CL > 1) cluster.sync();
+    // the next layer's weights do not depend on the peers: load them while the row pushes of the cluster land
+    if (CL > 1) cluster_arrive();
+    if (l + 1 < L) load_weights(l + 1);
+    if (CL > 1) cluster_wait();
     IGMC_STAMP(7 + 6 * l);
     float* t = H; H = Hn; Hn = t;
     // concat_states rows of the two target nodes (models.py:203-207), all rows are local now
@@ -645,7 +658,8 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
   float* dB = dhid_s + L1O;                              // [32]
-  int* ibuf = reinterpret_cast<int*>(dB + HID);          // list offsets + segment table
+  float* bs_s = dB + HID;                                // [NB][in][32] basis of the current layer (chain rule operand)
+  int* ibuf = reinterpret_cast<int*>(bs_s + (size_t)NB * HID * HID);   // list offsets + segment table
   uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));   // [lcap]
   __shared__ int ws[34];
 
@@ -714,6 +728,14 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
 
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
+  // per-layer operands that do not depend on the peers: att, basis and the [W_r^T ; root^T] slab of the data gradient
+  auto load_weights = [&](int l) {
+    const int in = l == 0 ? in0 : HID;
+    for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
+    copy_f4(bs_s, params + M.off_basis[l], NB * in * HID);
+    if (l > 0) copy_f4(Wn, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), HID * ((R + 1) * HID + 4));
+  };
+  load_weights(L - 1);
   for (int l = L - 1; l >= 0; --l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), KRp = K1p + inpp;
@@ -735,8 +757,6 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       const int r = n_own + (idx >> 3), c4 = (idx & 7) * 4;
       *reinterpret_cast<float4*>(DP + (size_t)r * DPS_ + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
-    if (l > 0) copy_f4(Wn, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), HID * (KRp + 4));
     __syncthreads();
     IGMC_STAMP(sb);
 
@@ -907,9 +927,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       if (warp == nwarps - 1) dB[lane] = accb;
       __syncthreads();
       IGMC_STAMP(sb + 2);
-      copy_f4(stage, params + M.off_basis[l], NB * in * HID);   // basis of this layer -> shared (tile is done)
-      __syncthreads();
-      const float* bs = stage;
+      const float* bs = bs_s;
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
       for (int row = warp; row < NB * in; row += nwarps) {
         const int b = row / in, k = row - b * in;
@@ -931,8 +949,11 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     }
     __syncthreads();
     IGMC_STAMP(sb + 3);
-    // (3) every CTA's DH now holds d h_{l-1} of all nodes once the pushes have landed
-    if (CL > 1) cluster.sync();
+    // (3) every CTA's DH holds d h_{l-1} of all nodes once the pushes have landed; the next layer's operands are
+    //     loaded while they do (dW, which aliases Wn, has been consumed by the chain rule above)
+    if (CL > 1) cluster_arrive();
+    if (l > 0) load_weights(l - 1);
+    if (CL > 1) cluster_wait();
     IGMC_STAMP(sb + 4);
   }
 }
@@ -947,7 +968,8 @@ size_t bwd_base_fl(int n_cap, int R, int NB, int L, int CL) {
   const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;   // dW [(R+1)*32][32] aliases Wn [32][KSmax]
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL), own_cap16 = (size_t)a16((int)own_cap);
   return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + a4(R * NB) + a4(n_cap) +
-         a4((int)F) + L1O + HID + a4(list_ints((int)own_cap)) + (size_t)XR * ((size_t)R * HID + 4);
+         a4((int)F) + L1O + HID + (size_t)NB * HID * HID + a4(list_ints((int)own_cap)) +
+         (size_t)XR * ((size_t)R * HID + 4);
 }
 
 }  // namespace rs

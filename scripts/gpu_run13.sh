@@ -1,0 +1,17 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+timeout 400 python -m pytest tests/test_gpu_model.py tests/test_gpu_dgcnn.py -q -m gpu --tb=short --timeout=180 --timeout-method=thread -p no:cacheprovider -x 2>&1 | tail -5
+IGMC_WPREP=1 timeout 300 python -m pytest tests/test_gpu_model.py -q -m gpu --tb=short --timeout=180 --timeout-method=thread -p no:cacheprovider -x -k "parity" 2>&1 | tail -2
+timeout 200 python scripts/phase_profile.py > gpurun_out/phase13.txt 2>&1; head -66 gpurun_out/phase13.txt
+for w in 0 1; do
+  IGMC_WPREP=$w timeout 300 python bench.py --steps 200 --warmup 10 --skip-cpu-baseline > gpurun_out/bench13_$w.json 2> gpurun_out/bench13_$w.err
+  echo "== wprep=$w rc=$?"; python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/bench13_$w.json"))
+    print(round(d["value"]), round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"]), d["roofline"]["kernel_ms"])
+except Exception as e:
+    print("ERR", e); print(open("gpurun_out/bench13_$w.err").read()[-1500:])
+PY
+done
