@@ -478,22 +478,20 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       {
         const int kq = K1 >> 2, SS4 = SS >> 2;
         float4* st4 = reinterpret_cast<float4*>(stage);
-        for (int r = warp; r < crow; r += nwarps) {
+        for (int idx = tid; idx < crow * kq; idx += NT) {   // flat over (row, float4): independent iterations
+          const int r = idx / kq, k4 = idx - r * kq;
           const int v = own.lo + c0 + r;
           const float id2 = invdeg[v];
           const int e = Ls.ex[c0 + r], x0 = e & 0xffff, nex = e >> 16;
-          float4* zs = S.zsave ? reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID))
-                               : nullptr;
-          for (int k4 = lane; k4 < kq; k4 += 32) {
-            float4 t = st4[(size_t)r * SS4 + k4];
-            for (int j = 0; j < nex; ++j) {
-              const float4 u = st4[(size_t)(crow + x0 + j) * SS4 + k4];
-              t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
-            }
-            t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
-            st4[(size_t)r * SS4 + k4] = t;
-            if (zs) zs[k4] = t;
+          float4 t = st4[(size_t)r * SS4 + k4];
+          for (int j = 0; j < nex; ++j) {
+            const float4 u = st4[(size_t)(crow + x0 + j) * SS4 + k4];
+            t.x += u.x; t.y += u.y; t.z += u.z; t.w += u.w;
           }
+          t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
+          st4[(size_t)r * SS4 + k4] = t;
+          if (S.zsave)
+            reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID))[k4] = t;
         }
       }
       IGMC_STAMP_T(0, 42); IGMC_STAMP_T(992, 45);
@@ -578,6 +576,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const float* W1 = params + M.off_lin1_w;
   for (int ob = warp * 4; ob < L1O; ob += nwarps * 4) {   // 4 outputs per warp with independent load streams
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8   // 32 independent L2 loads in flight per lane (the loop is latency bound)
     for (int i = lane; i < F; i += 32) {
       const float f = feat_s[i];
 #pragma unroll
@@ -700,7 +699,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     const int i = tid % F, part = tid / F;
     if (part < parts) {
       float s = 0.f;
-#pragma unroll 8
+#pragma unroll 16
       for (int o = part; o < L1O; o += parts) s = fmaf(__ldg(W1 + (size_t)o * F + i), dhid_s[o], s);
       stage[part * F + i] = s;
     }
@@ -868,24 +867,44 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         {   // tile[r][0..K1) = saved aggregate, [K1..K1p) = 0, [K1p..KRp) = h_{l-1}; rows beyond n_own are zero
           const int kq = K1 >> 2, TS4 = TS >> 2;
           float4* t4 = reinterpret_cast<float4*>(stage);
-          for (int idx = tid; idx < rows * kq; idx += NT) {
-            const int r_ = idx / kq, k4 = idx - r_ * kq;
-            float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t0 + r_ < n_own)
-              val = __ldg(reinterpret_cast<const float4*>(S.zsave + ((size_t)l * S.node_cap + nb + own.lo + t0 + r_) * (size_t)(R * HID)) + k4);
-            t4[(size_t)r_ * TS4 + k4] = val;
-          }
-          const int tail = KRp - K1;   // zero padding of the aggregate + the h_{l-1} columns
-          for (int idx = tid; idx < rows * tail; idx += NT) {
-            const int r_ = idx / tail, q = idx - r_ * tail, kk = K1 + q;
-            float hv = 0.f;
-            const int k = kk - K1p;
-            if (k >= 0 && k < in && t0 + r_ < n_own) {
-              const int v = own.lo + t0 + r_;
-              if (l > 0) hv = __ldcg(S.states + (size_t)(nb + v) * CW + (l - 1) * HID + k);
-              else hv = (k == (int)node_label[nb + v]) ? 1.f : 0.f;
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          // L2-latency bound: four independent loads in flight per thread, then the four stores
+          const float* zbase = S.zsave + ((size_t)l * S.node_cap + nb + own.lo + t0) * (size_t)(R * HID);
+          for (int base = tid; base < rows * kq; base += 4 * NT) {
+            float4 val[4];
+            int dst[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int idx = base + u * NT;
+              val[u] = z4;
+              dst[u] = -1;
+              if (idx < rows * kq) {
+                const int r_ = idx / kq, k4 = idx - r_ * kq;
+                dst[u] = r_ * TS4 + k4;
+                if (t0 + r_ < n_own) val[u] = __ldg(reinterpret_cast<const float4*>(zbase + (size_t)r_ * (R * HID)) + k4);
+              }
             }
-            stage[(size_t)r_ * TS + kk] = hv;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (dst[u] >= 0) t4[dst[u]] = val[u];
+          }
+          if (l > 0) {   // h_{l-1} columns: one float4 of the states row per item (K1 == K1p for 32-wide inputs)
+            for (int idx = tid; idx < rows * 8; idx += NT) {
+              const int r_ = idx >> 3, c4 = (idx & 7) << 2;
+              float4 hv = z4;
+              if (t0 + r_ < n_own)
+                hv = __ldcg(reinterpret_cast<const float4*>(S.states + (size_t)(nb + own.lo + t0 + r_) * CW + (l - 1) * HID + c4));
+              *reinterpret_cast<float4*>(stage + (size_t)r_ * TS + K1p + c4) = hv;
+            }
+          } else {
+            const int tail = KRp - K1;   // zero padding of the aggregate + the one-hot input columns
+            for (int idx = tid; idx < rows * tail; idx += NT) {
+              const int r_ = idx / tail, q = idx - r_ * tail, kk = K1 + q;
+              float hv = 0.f;
+              const int k = kk - K1p;
+              if (k >= 0 && k < in && t0 + r_ < n_own) hv = (k == (int)node_label[nb + own.lo + t0 + r_]) ? 1.f : 0.f;
+              stage[(size_t)r_ * TS + kk] = hv;
+            }
           }
         }
         __syncthreads();
