@@ -576,6 +576,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const float* W1 = params + M.off_lin1_w;
   for (int ob = warp * 4; ob < L1O; ob += nwarps * 4) {   // 4 outputs per warp with independent load streams
     float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float bias_o = lane < 4 ? __ldg(params + M.off_lin1_b + ob + lane) : 0.f;   // independent of the dot products
 #pragma unroll 8   // 32 independent L2 loads in flight per lane (the loop is latency bound)
     for (int i = lane; i < F; i += 32) {
       const float f = feat_s[i];
@@ -588,7 +589,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     for (int u = 0; u < 4; ++u) if (lane == u) {
       const int o = ob + u;
       const float s = s4[u];
-      float h = fmaxf(s + params[M.off_lin1_b + o], 0.f);
+      float h = fmaxf(s + bias_o, 0.f);
       float scale = 1.f;
       if (training && (D.hidden_dropout > 0.f || D.hidden_keep)) {
         bool keep;
@@ -609,13 +610,14 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   __syncthreads();
   if (warp == 0) {
     float s = 0.f;
+    const float b2 = __ldg(params + M.off_lin2_b), yg = y ? __ldg(y + g) : 0.f;   // issued with the weight loads
     for (int o = lane; o < L1O; o += 32) s = fmaf(params[M.off_lin2_w + o], hid_s[o], s);
     s = warp_sum_f(s);
     if (lane == 0) {
-      const float out = (s + params[M.off_lin2_b]) * M.multiply_by;
+      const float out = (s + b2) * M.multiply_by;
       S.pred[g] = out;
       if (y) {
-        const float diff = out - y[g];
+        const float diff = out - yg;
         if (sqerr) sqerr[g] = diff * diff;
         if (dpred) dpred[g] = 2.f * diff * loss_scale * M.multiply_by;
       }
@@ -657,8 +659,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
   float* dB = dhid_s + L1O;                              // [32]
-  float* bs_s = dB + HID;                                // [NB][in][32] basis of the current layer (chain rule operand)
-  int* ibuf = reinterpret_cast<int*>(bs_s + (size_t)NB * HID * HID);   // list offsets + segment table
+  int* ibuf = reinterpret_cast<int*>(dB + HID);          // list offsets + segment table
   uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));   // [lcap]
   __shared__ int ws[34];
 
@@ -727,11 +728,9 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
 
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
-  // per-layer operands that do not depend on the peers: att, basis and the [W_r^T ; root^T] slab of the data gradient
+  // per-layer operands that do not depend on the peers: att and the [W_r^T ; root^T] slab of the data gradient
   auto load_weights = [&](int l) {
-    const int in = l == 0 ? in0 : HID;
     for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
-    copy_f4(bs_s, params + M.off_basis[l], NB * in * HID);
     if (l > 0) copy_f4(Wn, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), HID * ((R + 1) * HID + 4));
   };
   load_weights(L - 1);
@@ -946,7 +945,9 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       if (warp == nwarps - 1) dB[lane] = accb;
       __syncthreads();
       IGMC_STAMP(sb + 2);
-      const float* bs = bs_s;
+      copy_f4(stage, params + M.off_basis[l], NB * in * HID);   // basis of this layer -> shared (tile is done)
+      __syncthreads();
+      const float* bs = stage;
       // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
       for (int row = warp; row < NB * in; row += nwarps) {
         const int b = row / in, k = row - b * in;
@@ -987,8 +988,7 @@ size_t bwd_base_fl(int n_cap, int R, int NB, int L, int CL) {
   const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;   // dW [(R+1)*32][32] aliases Wn [32][KSmax]
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL), own_cap16 = (size_t)a16((int)own_cap);
   return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + a4(R * NB) + a4(n_cap) +
-         a4((int)F) + L1O + HID + (size_t)NB * HID * HID + a4(list_ints((int)own_cap)) +
-         (size_t)XR * ((size_t)R * HID + 4);
+         a4((int)F) + L1O + HID + a4(list_ints((int)own_cap)) + (size_t)XR * ((size_t)R * HID + 4);
 }
 
 }  // namespace rs
