@@ -81,6 +81,7 @@ struct Lists {
   const int* seg_p0;     // per segment: list range and staging row (relative to its chunk)
   const int* seg_p1;
   const int* seg_row;
+  const int* seg_ord;    // segments of every chunk in order of decreasing length (the order they are handed out in)
   const int* ex;         // per node: first extra row (relative to crow) | number of extra segments << 16
   const uint32_t* adj;   // global fallback
   const int32_t* eid;
@@ -88,7 +89,7 @@ struct Lists {
   int eb, m_half;
 };
 
-__host__ __device__ __forceinline__ int list_ints(int own_cap) { return 3 * (own_cap + 4) + 3 * (own_cap + XR * XCH); }
+__host__ __device__ __forceinline__ int list_ints(int own_cap) { return 3 * (own_cap + 4) + 4 * (own_cap + XR * XCH); }
 
 // Block-wide; ends with a barrier.  `ibuf` has list_ints(own_cap) ints.  invdeg_out/invdeg_glob (optional) get
 // 1/max(kept degree,1) of the own nodes.
@@ -104,7 +105,9 @@ __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t*
   int* seg_p0 = ex + (own_cap + 4);
   int* seg_p1 = seg_p0 + (own_cap + XR * XCH);
   int* seg_row = seg_p1 + (own_cap + XR * XCH);
+  int* seg_ord = seg_row + (own_cap + XR * XCH);
   Lists Ls;
+  Ls.seg_ord = seg_ord;
   Ls.adj = adj; Ls.eid = eid; Ls.mirror = mirror; Ls.eb = eb; Ls.m_half = m_half;
   Ls.lptr = lptr; Ls.segbase = segbase; Ls.ex = ex; Ls.seg_p0 = seg_p0; Ls.seg_p1 = seg_p1; Ls.seg_row = seg_row;
   // ---- pass 1: kept entries per node ----
@@ -201,23 +204,47 @@ __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t*
     }
   }
   __syncthreads();
+  // hand-out order: within every chunk, segments by decreasing length (rank sort, ties by index)
+  {
+    const int nseg = segbase[n_own];
+    for (int sg = tid; sg < nseg; sg += NT) {
+      int c0 = 0;
+      while (c0 + chunk < n_own && segbase[c0 + chunk] <= sg) c0 += chunk;
+      const int s0 = segbase[c0], s1 = segbase[min(c0 + chunk, n_own)];
+      const int len = seg_p1[sg] - seg_p0[sg];
+      int rank = 0;
+      for (int t = s0; t < s1; ++t) {
+        const int lt = seg_p1[t] - seg_p0[t];
+        rank += (lt > len) || (lt == len && t < sg);
+      }
+      seg_ord[s0 + rank] = sg;
+    }
+  }
+  __syncthreads();
   return Ls;
 }
 
 // Relation-space aggregate of the segments [sg0, sg1) of one chunk into their staging rows
 // stage[row][r*inp + k] (row stride SS): one 8-lane group per segment, float4 per lane.
 // `K` is only consulted for unstaged lists (dropout draws evaluated per edge).
-__device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, int sg0, int sg1, int warp, int nwarps,
-                                                int lane, const float* __restrict__ feat, float* __restrict__ stage,
-                                                int SS, int inp) {
-  const int q = lane & 7, gq = lane >> 3;
+// Segments are handed out through a shared-memory ticket (`ticket`, zero on entry, reset by the caller after the
+// barrier that follows) in order of decreasing length (Ls.seg_ord): the four groups of a warp run in lockstep, so
+// segments of similar length taken at the same time keep their lanes busy (a warp-instruction of the edge loop had
+// 14 of 32 lanes active with the node-order assignment, profiles/README.md).  Which group computes a segment does
+// not change its result (own staging row, fixed summation order): the output stays bitwise deterministic.
+__device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, int sg0, int sg1, int lane,
+                                                const float* __restrict__ feat, float* __restrict__ stage, int SS,
+                                                int inp, int* ticket) {
+  const int q = lane & 7;
   const int fo = 4 * q;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int per = nwarps * 4;
-  const int iters = (sg1 - sg0 + per - 1) / per;
-  for (int it = 0; it < iters; ++it) {
-    const int sg = sg0 + it * per + warp * 4 + gq;
-    const bool valid = sg < sg1;
+  for (;;) {
+    int t = 0;
+    if (q == 0) t = sg0 + atomicAdd(ticket, 1);
+    t = __shfl_sync(IGMC_FULL, t, lane & ~7);
+    const bool valid = t < sg1;
+    if (!__any_sync(IGMC_FULL, valid)) break;
+    const int sg = valid ? Ls.seg_ord[t] : 0;
     float* rowb = stage;
     int p = 0, p1 = 0;
     if (valid) {
@@ -439,6 +466,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   // in-lists of the own nodes -> shared memory; kept in-degree (dropout_adj is applied once, models.py:193)
   const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap,
                                ibuf, own_cap, chunk, ws, invdeg, S.inv_deg);
+  if (tid == 0) ws[33] = 0;   // segment ticket of gather_segments (made visible by the barrier at the top of the layer loop)
   const bool ext = M.readout != 0;   // concat_states only: an external readout (csrc/sortpool.cu) takes over
   const int tu = s_t[0], ti = s_t[1];
   if (!ext && (tu >= n || ti >= n)) {
@@ -470,9 +498,10 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       // ---- aggregate: one 8-lane group per list segment ----
 #define IGMC_STAMP_T(t_, i_) do { if (S.prof && l == 1 && threadIdx.x == (t_)) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
       IGMC_STAMP_T(0, 39); IGMC_STAMP_T(992, 49);
-      gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], warp, nwarps, lane, H, stage, SS, inp);
+      gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, H, stage, SS, inp, &ws[33]);
       IGMC_STAMP_T(0, 40); IGMC_STAMP_T(992, 43); IGMC_STAMP_T(480, 46);
       __syncthreads();
+      if (tid == 0) ws[33] = 0;   // re-arm the segment ticket (the next gather is several barriers away)
       IGMC_STAMP_T(0, 41); IGMC_STAMP_T(992, 44);
       // ---- fold the extra segments of long lists into their node row, scale by 1/deg, keep a copy for backward ----
       {
@@ -681,6 +710,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const Lists Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb,
                                own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap, ibuf, own_cap, chunk, ws, nullptr,
                                nullptr);
+  if (tid == 0) ws[33] = 0;   // segment ticket of gather_segments
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
   if (!ext) {
@@ -764,8 +794,9 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       const int SS = K1p + 4, KS = KRp + 4;
       for (int c0 = 0; c0 < n_own; c0 += chunk) {
         const int crow = min(chunk, n_own - c0);
-        gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], warp, nwarps, lane, DPS, stage, SS, HID);
+        gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, DPS, stage, SS, HID, &ws[33]);
         __syncthreads();
+        if (tid == 0) ws[33] = 0;
         {   // fold the extra segments of long lists into their node row
           const int kq = K1 >> 2, SS4 = SS >> 2;
           float4* st4 = reinterpret_cast<float4*>(stage);
