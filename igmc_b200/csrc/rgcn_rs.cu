@@ -74,6 +74,13 @@ constexpr int SEG = 32;        // edges per segment
 constexpr int XR = 16;         // extra staging rows per chunk
 constexpr int XCH = 8;         // chunks that may use extra rows
 
+// staged list entry: type << 24 | swizzled float offset of the neighbour's feature row ((nbr << 5) | ((nbr & 7) << 2)),
+// so that the edge loop gets a lane's address with one LOP3 (offset ^ column) instead of re-deriving the swizzle
+__device__ __forceinline__ uint32_t enc_entry(uint32_t ent) {
+  const uint32_t nbr = ent & 0xffffu;
+  return ((ent >> 16) << 24) | (nbr << 5) | ((nbr & 7u) << 2);
+}
+
 struct Lists {
   const uint32_t* lst;   // staged entries (nullptr: not staged -> adj/eid are read per edge)
   const int* lptr;       // [n_own+1] list offsets (into lst when staged, else absolute positions in adj)
@@ -194,13 +201,13 @@ __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t*
           uint32_t ent = DROPPED;
           if (p < p1) ent = load_entry(adj, eid, p, K, mirror, eb, m_half);
           const unsigned bal = __ballot_sync(IGMC_FULL, ent != DROPPED);
-          if (ent != DROPPED) lbuf[o + __popc(bal & ((1u << lane) - 1u))] = ent;
+          if (ent != DROPPED) lbuf[o + __popc(bal & ((1u << lane) - 1u))] = enc_entry(ent);
           o += __popc(bal);
         }
       }
     } else {
       const int e_lo = ptr[nb + lo];
-      for (int i = tid; i < total; i += NT) lbuf[i] = __ldg(adj + e_lo + i);
+      for (int i = tid; i < total; i += NT) lbuf[i] = enc_entry(__ldg(adj + e_lo + i));
     }
   }
   __syncthreads();
@@ -260,10 +267,10 @@ __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, 
       const uint32_t* lst = Ls.lst;
       float4 acc = z4;
       int cur = -1;
-#define IGMC_HROW(e_) (*reinterpret_cast<const float4*>(feat + (((int)((e_) & 0xffffu)) << 5) + (fo ^ ((((int)(e_)) & 7) << 2))))
+#define IGMC_HROW(e_) (*reinterpret_cast<const float4*>(feat + (((e_) & 0xffffffu) ^ (uint32_t)fo)))
 #define IGMC_STEP(e_, a_)                                                            \
       do {                                                                           \
-        const int ty_ = (int)((e_) >> 16);                                           \
+        const int ty_ = (int)((e_) >> 24);                                           \
         if (ty_ != cur) {                                                            \
           if (cur >= 0) {                                                            \
             float4* d_ = reinterpret_cast<float4*>(row + cur * inp);                 \
