@@ -583,7 +583,6 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
               float* peer = cluster.map_shared_rank(Hn, (rank + pr) % CL);
               *reinterpret_cast<float2*>(peer + off) = o;
             }
-            __stcg(reinterpret_cast<float2*>(S.states + (size_t)(nb + v) * CW + l * HID + cc), o);
           }
         }
       }
@@ -597,6 +596,13 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     if (CL > 1) cluster_wait();
     IGMC_STAMP(7 + 6 * l);
     float* t = H; H = Hn; Hn = t;
+    // concat_states of the own rows -> global, issued after the barrier (whose release fence would otherwise wait
+    // for these stores) and overlapping the next layer's gather; one coalesced 128 B row per 8 threads
+    for (int idx = tid; idx < n_own * 8; idx += NT) {
+      const int v = own.lo + (idx >> 3), c4 = (idx & 7) << 2;
+      __stcg(reinterpret_cast<float4*>(S.states + (size_t)(nb + v) * CW + l * HID + c4),
+             *reinterpret_cast<const float4*>(H + hix(v, c4)));
+    }
     // concat_states rows of the two target nodes (models.py:203-207), all rows are local now
     if (rank == 0 && !ext && tid < 2 * HID) {
       const int node = tid < HID ? tu : ti, c = tid & 31;
@@ -881,6 +887,9 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       }
     }
     IGMC_STAMP(sb + 1);
+    // the pushes of d h_{l-1} are done: arrive now, wait at the end of the layer - the weight-gradient phase below
+    // touches neither peer memory nor the buffer the peers are writing (DHn), so it hides the barrier latency
+    if (CL > 1 && l > 0) cluster_arrive();
 
     // (2) weight gradients over the own nodes on tensor cores:  dW[kk][j] = sum_v A[v][kk] dpre[v][j]
     //     A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | h_{l-1}[v,k] ]  ->  M = KRp rows, N = 32, K = own nodes
@@ -1009,9 +1018,8 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     IGMC_STAMP(sb + 3);
     // (3) every CTA's DH holds d h_{l-1} of all nodes once the pushes have landed; the next layer's operands are
     //     loaded while they do (dW, which aliases Wn, has been consumed by the chain rule above)
-    if (CL > 1) cluster_arrive();
     if (l > 0) load_weights(l - 1);
-    if (CL > 1) cluster_wait();
+    if (CL > 1 && l > 0) cluster_wait();   // nothing is exchanged after layer 0
     IGMC_STAMP(sb + 4);
   }
 }
