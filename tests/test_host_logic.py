@@ -128,3 +128,39 @@ def test_data_parallel_gradient_identity_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert out.get(timeout=5) < 1e-9
+
+
+def test_dgcnn_rs_bucket_layout_and_state_dict():
+    """DGCNN_RS (reference models.py:123-167): reference state_dict keys / shapes, the narrow last R-GCN layer lives
+    padded in the flat bucket (unused columns zero, also after reset_parameters), optimizer state round-trips."""
+    from oracle.pyg_restated import DGCNN_RSRef
+    from igmc_b200.models import DGCNN_RS, FusedAdam
+    torch.manual_seed(0)
+    ref = DGCNN_RSRef(4, (32, 32, 32, 1), 30, 5, 4, 0.2)
+    m = DGCNN_RS(4, latent_dim=[32, 32, 32, 1], k=30, num_relations=5, num_bases=4, regression=True)
+    assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == \
+        {k: tuple(v.shape) for k, v in ref.state_dict().items()}
+    assert m.dense_dim == ref.dense_dim == (30 // 2 - 5 + 1) * 32
+    m.load_state_dict(ref.state_dict())
+    for name, p in m.named_parameters():
+        assert torch.equal(p.detach(), dict(ref.named_parameters())[name].detach()), name
+    padded = [e for e in m._layout if len(e) == 4]
+    assert len(padded) == 3                                   # basis, root, bias of the 32 -> 1 layer
+    m.reset_parameters()
+    for e in padded:
+        slot = m.flat_params[e[0]:e[0] + e[1]].view(e[3])
+        assert float(slot[..., e[2][-1]:].abs().max()) == 0.0
+        assert float(slot[..., :e[2][-1]].abs().max()) > 0.0
+    assert m._cmodel.readout == 1 and m._csort.param_begin == m._cmodel.conv_param_count
+    assert m._csort.param_end == m.flat_params.numel()
+    opt = FusedAdam(m, lr=1e-3)
+    opt.load_state_dict(opt.state_dict())
+    # percentile k (models.py:69-73) on a stand-in dataset
+    class DS(list):
+        num_features = 4
+    class G(object):
+        def __init__(self, n):
+            self.num_nodes = n
+    ds = DS([G(n) for n in (5, 50, 20, 30, 40, 12, 60, 33, 47, 25)])
+    m2 = DGCNN_RS(ds, latent_dim=[32, 32, 32, 1], k=0.6, num_relations=5, num_bases=4, regression=True)
+    assert m2.k == sorted(g.num_nodes for g in ds)[int(np.ceil(0.6 * len(ds))) - 1]
