@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libigmc_b200.so")
 
 MAX_LAYERS = 8
+MAX_HOP = 3
 HIDDEN = 32
 LIN1_OUT = 128
 
@@ -38,7 +39,7 @@ class Pairs(C.Structure):
 
 class ExtractWS(C.Structure):
     _fields_ = [("nodes_u", vp), ("nodes_v", vp), ("n_u", vp), ("n_v", vp), ("row_cnt", vp), ("m_cnt", vp),
-                ("col_cnt", vp)]
+                ("col_cnt", vp), ("hop_off", vp)]
 
 
 class BatchOut(C.Structure):
@@ -90,7 +91,7 @@ class SortPoolSaved(C.Structure):
 
 
 _SIGS = {
-    "igmc_extract_batch": [C.POINTER(CSR), C.POINTER(Pairs), C.c_int, C.c_int, C.c_double, C.c_uint64, vp, C.c_int,
+    "igmc_extract_batch": [C.POINTER(CSR), C.POINTER(Pairs), C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, vp, C.c_int,
                            vp, vp, vp, vp, C.POINTER(ExtractWS), vp, C.POINTER(BatchOut), vp, vp],
     "igmc_assemble_batch": [C.POINTER(Store), vp, C.c_int, C.POINTER(BatchOut), vp, vp],
     "igmc_batch_ptrs": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],

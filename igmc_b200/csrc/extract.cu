@@ -1,4 +1,4 @@
-// Batched enclosing-subgraph extraction (h = 1) over the device-resident rating CSR/CSC.
+// Batched enclosing-subgraph extraction (h = 1..3) over the device-resident rating CSR/CSC.
 //
 // Replaces, for a whole mini-batch in two launches, the reference's per-pair Python path
 //   MyDynamicDataset.get            util_functions.py:138-145
@@ -25,27 +25,32 @@ namespace {
 constexpr int EX_THREADS = 1024;
 constexpr uint16_t NONE16 = 0xFFFF;
 
-// Select the node list of one side: out[0] = target, out[1..] = (sampled) fringe ascending.
-__device__ void select_side(const int32_t* __restrict__ nbr, int len, int target, int mnph, double ratio,
-                            uint64_t state, int32_t* __restrict__ out, int cap, int* n_out,
+// Select the node list of one side and hop from the sorted candidate list `nbr`: with `emit_target` (hop 1)
+// out[0] = target and out[1..] = the (sampled) fringe ascending, the target itself excluded from the candidates;
+// without (hops >= 2: `out` points behind the nodes found so far) out[0..] = the (sampled) fringe ascending.
+__device__ void select_side(const int32_t* __restrict__ nbr, int len, int target, bool emit_target, int mnph,
+                            double ratio, uint64_t state, int32_t* __restrict__ outp, int cap, int* n_out,
                             int* hist, int* ws, int* sh, int* err) {
   const int tid = threadIdx.x, nt = blockDim.x;
+  const int base_ = emit_target ? 1 : 0;
+  int32_t* out = outp + base_ - 1;          // the code below writes the fringe at out[1 + ...]
   if (tid == 0) sh[0] = -1;
   __syncthreads();
-  for (int p = tid; p < len; p += nt)
-    if (nbr[p] == target) sh[0] = p;  // sorted, duplicate-free list: at most one hit
+  if (emit_target)
+    for (int p = tid; p < len; p += nt)
+      if (nbr[p] == target) sh[0] = p;  // sorted, duplicate-free list: at most one hit
   __syncthreads();
   const int pos = sh[0];
   const int d = len - (pos >= 0 ? 1 : 0);
   int k = d;
   if (ratio < 1.0) k = (int)(ratio * (double)d);   // int(sample_ratio*len(fringe)), ref :223-224
   if (mnph >= 0 && mnph < k) k = mnph;             // strict '<', ref :226,:228
-  if (k + 1 > cap) {
-    if (tid == 0) { igmc_set_err(err, IGMC_ERR_NODE_CAP); out[0] = target; *n_out = 1; }
+  if (k + base_ > cap) {
+    if (tid == 0) { igmc_set_err(err, IGMC_ERR_NODE_CAP); if (emit_target) outp[0] = target; *n_out = base_; }
     __syncthreads();
     return;
   }
-  if (tid == 0) { out[0] = target; *n_out = 1 + k; }
+  if (tid == 0) { if (emit_target) outp[0] = target; *n_out = base_ + k; }
   if (k == d) {  // no sampling: ordered copy minus the target
     for (int p = tid; p < len; p += nt) {
       if (p == pos) continue;
@@ -112,6 +117,44 @@ __device__ void select_side(const int32_t* __restrict__ nbr, int len, int target
   __syncthreads();
 }
 
+// ---- hops >= 2 (util_functions.py:216-235): bitmaps over one side's ids in shared memory -------------------------
+// cand |= union of the CSR rows (CSC columns) of `nodes`  (warp per node, coalesced index reads)
+__device__ void mark_neighbours(const int32_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                const int32_t* __restrict__ nodes, int cnt, uint32_t* cand) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int a = warp; a < cnt; a += nwarps) {
+    const int v = nodes[a];
+    for (int p = ptr[v] + lane; p < ptr[v + 1]; p += 32) {
+      const int t = idx[p];
+      atomicOr(&cand[t >> 5], 1u << (t & 31));
+    }
+  }
+}
+// fringe = cand & ~visited; visited |= fringe; list = ids of the fringe ascending.  Returns its length (block-wide).
+__device__ int fringe_to_list(uint32_t* cand, uint32_t* vis, int words, int32_t* list, int* ws) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  int running = 0;
+  for (int base = 0; base < words; base += nt) {
+    const int w = base + tid;
+    uint32_t f = 0;
+    if (w < words) {
+      f = cand[w] & ~vis[w];
+      vis[w] |= f;
+    }
+    int tot;
+    const int ex = block_excl_scan_i(__popc(f), ws, &tot);
+    int o = running + ex;
+    while (f) {
+      const int b = __ffs(f) - 1;
+      list[o++] = (w << 5) + b;
+      f &= f - 1;
+    }
+    running += tot;
+  }
+  __syncthreads();
+  return running;
+}
+
 __device__ __forceinline__ void resolve_pair(const igmc_pairs_t& P, int g, int* i, int* j, int* lab, int64_t* pid) {
   const int64_t src = P.idx ? P.idx[g] : (int64_t)g;
   *i = P.links_u[src];
@@ -128,10 +171,16 @@ k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double rat
                        int32_t* __restrict__ nodes_u, int32_t* __restrict__ nodes_v,
                        int32_t* __restrict__ n_u, int32_t* __restrict__ n_v,
                        int32_t* __restrict__ row_cnt, int32_t* __restrict__ m_cnt, int32_t* __restrict__ col_cnt,
-                       int* err) {
+                       int h, int32_t* __restrict__ hop_off, int* err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* colcnt = reinterpret_cast<int*>(smem_raw);                 // [cap]
   uint16_t* tab = reinterpret_cast<uint16_t*>(colcnt + cap);      // [num_items]
+  // h > 1 only: visited / candidate bitmaps and the ascending fringe list, behind the item table
+  const int wu = (G.num_users + 31) >> 5, wv = (G.num_items + 31) >> 5;
+  uint32_t* vis_u = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)cap * 4 + (size_t)G.num_items * 2 + 15) & ~(size_t)15));
+  uint32_t* vis_v = vis_u + wu;
+  uint32_t* cand = vis_v + wv;
+  int32_t* flist = reinterpret_cast<int32_t*>(cand + max(wu, wv));
   __shared__ int hist[256];
   __shared__ int ws[34];
   __shared__ int sh[4];
@@ -157,12 +206,58 @@ k_extract_select_count(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double rat
     __syncthreads();
   } else {
     // user fringe = users who rated item j (CSC column j); item fringe = items rated by user i (CSR row i)
-    select_side(G.row_idx + G.col_ptr[j], G.col_ptr[j + 1] - G.col_ptr[j], i, mnph, ratio,
+    select_side(G.row_idx + G.col_ptr[j], G.col_ptr[j + 1] - G.col_ptr[j], i, true, mnph, ratio,
                 sample_state(seed, pid, 0, 1), gu, cap, &s_nu, hist, ws, sh, err);
-    select_side(G.col_idx + G.row_ptr[i], G.row_ptr[i + 1] - G.row_ptr[i], j, mnph, ratio,
+    select_side(G.col_idx + G.row_ptr[i], G.row_ptr[i + 1] - G.row_ptr[i], j, true, mnph, ratio,
                 sample_state(seed, pid, 1, 1), gv, cap, &s_nv, hist, ws, sh, err);
   }
   __syncthreads();
+  if (hop_off && tid == 0) {   // nodes within distance d per side: [users 0..3 | items 0..3]
+    int32_t* ho = hop_off + (size_t)g * 2 * (IGMC_MAX_HOP + 1);
+    ho[0] = 1; ho[IGMC_MAX_HOP + 1] = 1;
+    for (int d = 1; d <= IGMC_MAX_HOP; ++d) { ho[d] = s_nu; ho[IGMC_MAX_HOP + 1 + d] = s_nv; }
+  }
+  if (h > 1 && !inj_nodes_u) {
+    // visited = the targets and the WHOLE hop-1 fringes (the reference marks a fringe visited before it samples it,
+    // util_functions.py:220-221)
+    for (int w = tid; w < wu + wv; w += nt) vis_u[w] = 0;   // vis_u and vis_v are contiguous
+    __syncthreads();
+    if (tid == 0) { atomicOr(&vis_u[i >> 5], 1u << (i & 31)); atomicOr(&vis_v[j >> 5], 1u << (j & 31)); }
+    for (int p = G.col_ptr[j] + tid; p < G.col_ptr[j + 1]; p += nt) { const int t = G.row_idx[p]; atomicOr(&vis_u[t >> 5], 1u << (t & 31)); }
+    for (int p = G.row_ptr[i] + tid; p < G.row_ptr[i + 1]; p += nt) { const int t = G.col_idx[p]; atomicOr(&vis_v[t >> 5], 1u << (t & 31)); }
+    __syncthreads();
+    int lo_u = 1, hi_u = s_nu, lo_v = 1, hi_v = s_nv;
+    for (int d = 2; d <= h; ++d) {
+      // both new fringes come from the PREVIOUS fringes (tuple assignment, util_functions.py:217)
+      for (int w = tid; w < wv; w += nt) cand[w] = 0;
+      __syncthreads();
+      mark_neighbours(G.row_ptr, G.col_idx, gu + lo_u, hi_u - lo_u, cand);
+      __syncthreads();
+      int len = fringe_to_list(cand, vis_v, wv, flist, ws);
+      select_side(flist, len, -1, false, mnph, ratio, sample_state(seed, pid, 1, d), gv + hi_v, cap - hi_v, &s_nv,
+                  hist, ws, sh, err);
+      __syncthreads();
+      const int add_v = s_nv;
+      for (int w = tid; w < wu; w += nt) cand[w] = 0;
+      __syncthreads();
+      mark_neighbours(G.col_ptr, G.row_idx, gv + lo_v, hi_v - lo_v, cand);
+      __syncthreads();
+      len = fringe_to_list(cand, vis_u, wu, flist, ws);
+      select_side(flist, len, -1, false, mnph, ratio, sample_state(seed, pid, 0, d), gu + hi_u, cap - hi_u, &s_nu,
+                  hist, ws, sh, err);
+      __syncthreads();
+      const int add_u = s_nu;
+      if (add_u == 0 && add_v == 0) break;        // util_functions.py:230-231
+      lo_u = hi_u; hi_u += add_u; lo_v = hi_v; hi_v += add_v;
+      if (hop_off && tid == 0) {
+        int32_t* ho = hop_off + (size_t)g * 2 * (IGMC_MAX_HOP + 1);
+        for (int dd = d; dd <= IGMC_MAX_HOP; ++dd) { ho[dd] = hi_u; ho[IGMC_MAX_HOP + 1 + dd] = hi_v; }
+      }
+      __syncthreads();
+    }
+    if (tid == 0) { s_nu = hi_u; s_nv = hi_v; }
+    __syncthreads();
+  }
   const int nu = s_nu, nv = s_nv;
   // item-id -> local-id table
   for (int t = tid; t < G.num_items; t += nt) tab[t] = NONE16;
@@ -199,7 +294,7 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
                const int32_t* __restrict__ nodes_u, const int32_t* __restrict__ nodes_v,
                const int32_t* __restrict__ n_u, const int32_t* __restrict__ n_v,
                const int32_t* __restrict__ row_cnt, const int32_t* __restrict__ m_cnt,
-               const int32_t* __restrict__ col_cnt,
+               const int32_t* __restrict__ col_cnt, int h, const int32_t* __restrict__ hop_off,
                const float* __restrict__ class_values, igmc_batch_out_t O, int* err) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* rowoff = reinterpret_cast<int*>(smem_raw);                 // [cap]
@@ -236,9 +331,26 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
     O.y[g] = class_values[lab];
     O.graph_nu[g] = nu;
   }
-  // node labels (h=1): target user 0, target item 1, other users 2, other items 3 (ref :245)
+  // node labels: user at distance d -> 2d, item -> 2d+1 (ref :245); h=1: 0 / 1 targets, 2 / 3 the others
+  int hu[IGMC_MAX_HOP + 1], hv[IGMC_MAX_HOP + 1];   // nodes within distance d, per side
+#pragma unroll
+  for (int d = 0; d <= IGMC_MAX_HOP; ++d) {
+    hu[d] = (h > 1 && hop_off) ? hop_off[(size_t)g * 2 * (IGMC_MAX_HOP + 1) + d] : (d == 0 ? 1 : nu);
+    hv[d] = (h > 1 && hop_off) ? hop_off[(size_t)g * 2 * (IGMC_MAX_HOP + 1) + IGMC_MAX_HOP + 1 + d] : (d == 0 ? 1 : nv);
+  }
   for (int t = tid; t < n; t += nt) {
-    const int label = t < nu ? (t == 0 ? 0 : 2) : (t == nu ? 1 : 3);
+    int label;
+    if (t < nu) {
+      int d = 0;
+#pragma unroll
+      for (int q = 0; q < IGMC_MAX_HOP; ++q) d += (t >= hu[q]) ? 1 : 0;
+      label = 2 * d;
+    } else {
+      int d = 0;
+#pragma unroll
+      for (int q = 0; q < IGMC_MAX_HOP; ++q) d += (t - nu >= hv[q]) ? 1 : 0;
+      label = 2 * d + 1;
+    }
     const size_t row = (size_t)Nbase + t;
     O.node_label[row] = (uint8_t)label;
     O.batch[row] = g;
@@ -287,6 +399,24 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
     const int jfirst = (a != 0 && (row_cnt[(size_t)g * cap + a] < 0)) ? 1 : 0;  // j sorts first (v_local 0)
     const int base = rowoff[a];
     int seen = 0;
+    // h > 1: local item ids ascend with (hop, global id), the row is in global-id order -> a match's rank is the
+    // number of matches of earlier hops plus its position among the matches of its own hop
+    int hop_base[IGMC_MAX_HOP + 1] = {0, 0, 0, 0}, hop_seen[IGMC_MAX_HOP + 1] = {0, 0, 0, 0};
+    if (h > 1) {
+      int c[IGMC_MAX_HOP + 1] = {0, 0, 0, 0};
+      for (int p0 = s; p0 < e; p0 += 32) {
+        const int p = p0 + lane;
+        uint16_t b = NONE16;
+        if (p < e) b = tab[G.col_idx[p]];
+        const bool m_ = (b != NONE16) && b != 0;
+#pragma unroll
+        for (int d = 1; d <= IGMC_MAX_HOP; ++d)
+          c[d] += __popc(__ballot_sync(IGMC_FULL, m_ && (int)b >= hv[d - 1] && (int)b < hv[d]));
+      }
+      hop_base[1] = 0;
+#pragma unroll
+      for (int d = 2; d <= IGMC_MAX_HOP; ++d) hop_base[d] = hop_base[d - 1] + c[d - 1];
+    }
     for (int p0 = s; p0 < e; p0 += 32) {
       const int p = p0 + lane;
       uint16_t b = NONE16;
@@ -294,8 +424,18 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
       const bool match = (b != NONE16) && !(a == 0 && b == 0);
       const bool isj = match && b == 0;
       const unsigned bal = __ballot_sync(IGMC_FULL, match && !isj);
+      int hrank = 0;
+      if (h > 1) {
+#pragma unroll
+        for (int d = 1; d <= IGMC_MAX_HOP; ++d) {
+          const bool in_d = match && !isj && (int)b >= hv[d - 1] && (int)b < hv[d];
+          const unsigned bd = __ballot_sync(IGMC_FULL, in_d);
+          if (in_d) hrank = hop_base[d] + hop_seen[d] + __popc(bd & lt_mask);
+          hop_seen[d] += __popc(bd);
+        }
+      }
       if (match) {
-        const int rank = isj ? 0 : (jfirst + seen + __popc(bal & lt_mask));
+        const int rank = isj ? 0 : (h > 1 ? jfirst + hrank : jfirst + seen + __popc(bal & lt_mask));
         const int64_t r = G.rating[p];
         const size_t e1 = (size_t)2 * Mbase + base + rank, e2 = e1 + m;
         const int64_t un = Nbase + a, vn = Nbase + nu + b;
@@ -393,7 +533,7 @@ k_assemble(igmc_store_t S, const int64_t* __restrict__ idx, int B, igmc_batch_ou
 
 }  // namespace
 
-extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int max_nodes_per_hop,
+extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int h, int max_nodes_per_hop,
                                   double sample_ratio, uint64_t seed, const uint64_t* seed_dev, int cap,
                                   const int32_t* inj_nodes_u, const int32_t* inj_nodes_v,
                                   const int32_t* inj_n_u, const int32_t* inj_n_v,
@@ -401,8 +541,16 @@ extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, in
                                   const igmc_batch_out_t* O, int* err, void* stream) {
   if (B <= 0) return 0;
   if (cap < 1 || cap > 65534) return -2;
+  if (h < 1 || h > IGMC_MAX_HOP) return -4;
+  if (h > 1 && (inj_nodes_u || !W->hop_off)) return -4;   // injected node lists carry no hop boundaries
   cudaStream_t st = (cudaStream_t)stream;
-  const size_t smemA = (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
+  size_t smemA = (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
+  if (h > 1) {   // visited / candidate bitmaps + the fringe list of the larger side
+    const size_t wu = (G->num_users + 31) / 32, wv = (G->num_items + 31) / 32;
+    smemA = ((smemA + 15) & ~(size_t)15) + (wu + wv + (wu > wv ? wu : wv)) * 4 +
+            (size_t)(G->num_users > G->num_items ? G->num_users : G->num_items) * 4;
+    if (smemA > 220 * 1024) return -3;
+  }
   const size_t smemB = 2 * (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
   if (smemB > 220 * 1024) return -3;  // item table does not fit in shared memory
   cudaFuncSetAttribute(k_extract_select_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
@@ -410,10 +558,10 @@ extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, in
   k_extract_select_count<<<B, EX_THREADS, smemA, st>>>(*G, *P, B, max_nodes_per_hop, sample_ratio, seed, seed_dev, cap,
                                                        inj_nodes_u, inj_nodes_v, inj_n_u, inj_n_v,
                                                        W->nodes_u, W->nodes_v, W->n_u, W->n_v, W->row_cnt, W->m_cnt,
-                                                       W->col_cnt, err);
+                                                       W->col_cnt, h, W->hop_off, err);
   IGMC_CUDA_CHECK_LAUNCH();
   k_extract_fill<<<B, EX_THREADS, smemB, st>>>(*G, *P, B, cap, W->nodes_u, W->nodes_v, W->n_u, W->n_v,
-                                               W->row_cnt, W->m_cnt, W->col_cnt, class_values, *O, err);
+                                               W->row_cnt, W->m_cnt, W->col_cnt, h, W->hop_off, class_values, *O, err);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
 }

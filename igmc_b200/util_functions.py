@@ -68,12 +68,15 @@ class RatingGraph(object):
                            self.dev["row_idx"].data_ptr(), self.num_users, self.num_items)
         return self
 
-    def node_cap(self, max_nodes_per_hop):
-        """capacity of one side's node list: target + min(mnph, largest possible fringe)."""
+    def node_cap(self, max_nodes_per_hop, h=1):
+        """capacity of one side's node list: target + per hop min(mnph, largest possible fringe) (hop 1: a row or
+        a column of the matrix; later hops: up to the whole side)."""
         d = max(self.max_row_deg, self.max_col_deg)
+        side = max(self.num_users, self.num_items)
         if max_nodes_per_hop is not None:
             d = min(d, int(max_nodes_per_hop))
-        return 1 + d
+            side = min(side, int(max_nodes_per_hop))
+        return min(1 + d + (int(h) - 1) * side, 1 + max(self.num_users, self.num_items))
 
 
 class Data(object):
@@ -250,15 +253,15 @@ class SubgraphExtractor(object):
 
     def __init__(self, graph, links_u, links_v, labels, class_values, h=1, sample_ratio=1.0,
                  max_nodes_per_hop=None, max_batch=64, seed=0, emit_x=True):
-        if int(h) != 1:
-            raise NotImplementedError("igmc_b200 extraction implements hop=1 (the reference default, Main.py:88)")
+        if not 1 <= int(h) <= _lib.MAX_HOP:
+            raise NotImplementedError("igmc_b200 extraction implements hop = 1..%d (Main.py:88 default 1)" % _lib.MAX_HOP)
         self.lib = _lib.load()
         self.graph = graph
         self.device = graph.device if graph.device is not None else _require_cuda()
         if graph.device is None:
             graph.to(self.device)
         dev = self.device
-        self.h = 1
+        self.h = int(h)
         self.sample_ratio = float(sample_ratio)
         self.mnph = -1 if max_nodes_per_hop is None else int(max_nodes_per_hop)
         self.seed = int(seed)
@@ -267,7 +270,7 @@ class SubgraphExtractor(object):
         self.links_v = torch.as_tensor(np.asarray(links_v), dtype=torch.int32).to(dev)
         self.links_label = torch.as_tensor(np.asarray(labels), dtype=torch.int32).to(dev)
         self.class_values = torch.as_tensor(np.asarray(class_values, dtype=np.float32)).to(dev)
-        self.cap = graph.node_cap(max_nodes_per_hop)
+        self.cap = graph.node_cap(max_nodes_per_hop, self.h)
         self.feat_dim = 2 * self.h + 2
         self.emit_x = emit_x
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)   # shared device error word
@@ -287,9 +290,10 @@ class SubgraphExtractor(object):
         self.ws = dict(nodes_u=torch.empty(B * cap, **i32), nodes_v=torch.empty(B * cap, **i32),
                        n_u=torch.zeros(B, **i32), n_v=torch.zeros(B, **i32),
                        row_cnt=torch.empty(B * cap, **i32), m_cnt=torch.zeros(B, **i32),
-                       col_cnt=torch.empty(B * cap, **i32))
+                       col_cnt=torch.empty(B * cap, **i32),
+                       hop_off=torch.zeros(B * 2 * (_lib.MAX_HOP + 1), **i32))
         self._ws_c = _lib.ExtractWS(*[self.ws[k].data_ptr() for k in ("nodes_u", "nodes_v", "n_u", "n_v",
-                                                                          "row_cnt", "m_cnt", "col_cnt")])
+                                                                          "row_cnt", "m_cnt", "col_cnt", "hop_off")])
 
     def _alloc_out(self, B, reuse=False, slot=0):
         if reuse and (B, slot) in self._out_cache:
@@ -360,7 +364,7 @@ class SubgraphExtractor(object):
             assert inj_t[0].shape == (B, self.cap) and inj_t[1].shape == (B, self.cap)
             inj = [t.data_ptr() for t in inj_t]
             keep += inj_t
-        _lib.check(self.lib.igmc_extract_batch(C.byref(self.graph._c), C.byref(P), B, self.mnph,
+        _lib.check(self.lib.igmc_extract_batch(C.byref(self.graph._c), C.byref(P), B, self.h, self.mnph,
                                                self.sample_ratio, self.seed if seed is None else int(seed),
                                                _lib.ptr(seed_dev), self.cap, inj[0], inj[1], inj[2], inj[3],
                                                C.byref(self._ws_c),

@@ -23,6 +23,7 @@ extern "C" {
 #define IGMC_HIDDEN 32      /* latent_dim entries are hard-coded to 32 in Main.py:391 */
 #define IGMC_MAX_BASES 4    /* num_bases=4 in Main.py:394 (IGMC's default is 2) */
 #define IGMC_LIN1_OUT 128   /* models.py:185 */
+#define IGMC_MAX_HOP 3      /* --hop (Main.py:88, default 1); node features are one-hot of width 2h+2 */
 
 /* Device-resident rating matrix.  Replaces SparseRowIndexer / SparseColIndexer
  * (util_functions.py:20-66): flat CSR + CSC, int32 indices, uint8 rating label (= stored value-1). */
@@ -54,6 +55,7 @@ typedef struct {
   int32_t* row_cnt;  /* [B*cap] */
   int32_t* m_cnt;    /* [B] undirected edges per graph */
   int32_t* col_cnt;  /* [B*cap] matches per item column */
+  int32_t* hop_off;  /* [B*2*(IGMC_MAX_HOP+1)] nodes within distance d per side (users then items); needed for h > 1 */
 } igmc_extract_ws_t;
 
 /* The collated batch in the reference's layout (what construct_pyg_graph + Batch.from_data_list
@@ -73,20 +75,20 @@ typedef struct {
   int32_t* graph_nu;    /* [B] number of user nodes of each graph */
   int32_t* counts;      /* [2] N, E */
   /* optional (all or none): the message-passing adjacency of igmc_adj_t (symmetric form), built in the
-   * same pass so that igmc_batch_prepare is not needed for extracted batches; lists ordered by neighbour */
+   * same pass so that igmc_batch_prepare is not needed for extracted batches; lists sorted by (type, neighbour) */
   int32_t* adj_in_ptr;  /* [node_cap+1] */
   uint32_t* adj_in;     /* [edge_cap] */
   int32_t* adj_eid;     /* [edge_cap] */
   uint64_t* adj_tmp;    /* [edge_cap] scratch */
 } igmc_batch_out_t;
 
-/* Enclosing-subgraph extraction + labelling + graph construction + collate for B pairs (h = 1).
+/* Enclosing-subgraph extraction + labelling + graph construction + collate for B pairs, h = 1..IGMC_MAX_HOP hops.
  * Replaces MyDynamicDataset.get -> subgraph_extraction_labeling -> construct_pyg_graph
  * (util_functions.py:138-145, 208-297) and PyG's Batch.from_data_list.  `max_nodes_per_hop` < 0
- * means None.  `inj_*` (all or none NULL) inject per-graph node lists [B*cap] (test hook: the
- * reference's own random.sample draw).  `seed_dev` (optional, device) overrides `seed` so that a
+ * means None; `cap` bounds one side's node list over all hops.  `inj_*` (all or none NULL) inject per-graph
+ * node lists [B*cap] (test hook: the reference's own random.sample draw; h = 1 only).  `seed_dev` (optional, device) overrides `seed` so that a
  * captured CUDA graph can be replayed with a fresh sampling stream every step. */
-int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int max_nodes_per_hop,
+int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int h, int max_nodes_per_hop,
                        double sample_ratio, uint64_t seed, const uint64_t* seed_dev, int cap,
                        const int32_t* inj_nodes_u, const int32_t* inj_nodes_v,
                        const int32_t* inj_n_u, const int32_t* inj_n_v,
