@@ -31,9 +31,9 @@ WORKLOADS = {
                            "adj_dropout=0, ARR=0.001, Adam lr 1e-3"),
     "ml_100k": ("ml_100k", 50, "ml_100k* synthetic 943x1682 nnz 80000, mnph=200, batch=50/GPU, adj_dropout=0.2"),
     "ml_1m_r02": ("ml_1m_r02", 256, "ml_1m* ratio 0.2 synthetic nnz 216045, mnph=100, batch=256/GPU"),
-    "flixster": ("flixster", 50, "flixster* synthetic 3000x3000 nnz 23556, R=10, no node cap, STATIC pre-extracted "
-                                 "subgraphs (device-resident store + batch-assembly kernel), batch=50/GPU, "
-                                 "adj_dropout=0.2"),
+    "flixster": ("flixster", 50, "flixster (REAL Monti split, 3000x3000, 23556 train ratings, R=10), no node cap, STATIC "
+                                 "pre-extracted subgraphs (device-resident store + batch-assembly kernel), "
+                                 "batch=50/GPU, adj_dropout=0.2"),
 }
 ARR = 0.001
 LR = 1e-3
@@ -429,7 +429,8 @@ def run_ours(args):
         out = {
             "metric": "enclosing-subgraphs/sec (train step)", "value": value, "unit": "subgraphs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "real (tests/golden/flixster_ratings.npz)" if ds.get("real") else "synthetic",
             "config": {"workload": desc, "global_batch": G, "parallelism": "dp%d" % world,
                        "l2": "flushed between timed steps (256 MiB fill), per-step CUDA events summed",
                        "cuda_graph": not args.no_graph,
@@ -497,7 +498,7 @@ def main():
         line = {"impl": "reference", "metric": "enclosing-subgraphs/sec (train step)", "value": r["value"],
                 "unit": "subgraphs/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
+                "dtype": "f32", "data": "real (tests/golden/flixster_ratings.npz)" if ds.get("real") else "synthetic",
                 "config": {"workload": desc, "global_batch": B, "parallelism": "cpu"},
                 "cpu_baseline": {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
                                  "sample": r["sample"],

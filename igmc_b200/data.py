@@ -7,6 +7,8 @@ The *output contract* is the reference's: ``adj_train`` is a scipy CSR float32
 whose stored value is ``rating_label + 1`` (preprocessing.py:190-197) plus
 ``(u_indices, v_indices, labels)`` triples and the sorted ``class_values``.
 """
+import os
+
 import numpy as np
 import scipy.sparse as ssp
 
@@ -53,6 +55,24 @@ PRESETS = {
 }
 
 
+FLIXSTER_FIXTURE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                                "flixster_ratings.npz")
+
+
+def load_flixster():
+    """The REAL Monti et al. flixster split (3000 x 3000, 23 556 train / 2 617 test ratings, 10 rating levels
+    0.5..5), extracted once from the reference's raw_data/flixster/training_test_dataset.mat by
+    tests/golden/make_flixster_fixture.py (split logic of preprocessing.py:203-330, testing mode).  Same dict layout
+    as ``make_synthetic_dataset``; max_nodes_per_hop 10000 never samples (max degree 153)."""
+    z = np.load(FLIXSTER_FIXTURE)
+    nu, nv = int(z["num_users"]), int(z["num_items"])
+    tu, tv, tl = z["train_u"], z["train_v"], z["train_l"]
+    return dict(name="flixster", adj_train=build_adj(tu, tv, tl, nu, nv), train=(tu, tv, tl),
+                test=(z["test_u"], z["test_v"], z["test_l"]), class_values=z["class_values"].astype(np.float32),
+                num_users=nu, num_items=nv, max_nodes_per_hop=10000, adj_dropout=0.2,
+                num_relations=len(z["class_values"]), real=True)
+
+
 def make_synthetic_dataset(name="ml_1m", seed=0, num_test=2000):
     """Returns dict(adj_train, train=(u,v,labels), test=(u,v,labels), class_values, ...).
 
@@ -60,6 +80,8 @@ def make_synthetic_dataset(name="ml_1m", seed=0, num_test=2000):
     in the matrix and removes the target edge per subgraph, util_functions.py:238);
     test pairs are additional pairs NOT in adj_train.
     """
+    if name == "flixster" and os.path.exists(FLIXSTER_FIXTURE):
+        return load_flixster()          # the one BASELINE config whose real data is small enough to ship as a fixture
     nu, nv, nnz, R, mnph, adj_dropout = PRESETS[name]
     num_test = max(0, min(num_test, (nu * nv - nnz) // 2))   # unique pairs must exist (tiny presets)
     u, v, lab = synth_ratings(nu, nv, nnz + num_test, R, seed)

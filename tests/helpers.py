@@ -83,3 +83,17 @@ def batch_equal(b, ob):
     out["y"] = np.array_equal(b.y.cpu().numpy(), ob["y"].astype(np.float32))
     out["node_label"] = np.array_equal(b.node_label.cpu().numpy().astype(np.int64), ob["node_labels"])
     return out
+
+
+def load_flixster_cases():
+    """(dataset dict, pairs [3,n], list of canonical dicts) of tests/golden/flixster_cases.npz: outputs of the
+    reference's own subgraph_extraction_labeling on 64 pairs of the REAL flixster split (h=1, no sampling)."""
+    from igmc_b200.data import load_flixster
+    ds = load_flixster()
+    z = np.load(os.path.join(GOLDEN, "flixster_cases.npz"))
+    cases = []
+    for c in range(z["pairs"].shape[1]):
+        d = {k: z[k][z[k + "_off"][c]:z[k + "_off"][c + 1]] for k in KEYS}
+        d["y"] = float(z["y"][c])
+        cases.append(d)
+    return ds, z["pairs"], cases

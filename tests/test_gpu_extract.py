@@ -175,3 +175,35 @@ def test_full_size_vs_oracle_and_properties(name, mnph, B):
             assert m == sub.nnz - (1 if A[tu[idx[k]], tv[idx[k]]] != 0 else 0)
         if name != "ml_1m_r02":
             assert (np.diff(nptr) > 2).all()
+
+
+def test_flixster_real_data():
+    """REAL flixster split: the CUDA extractor against the reference-produced vectors (64 pairs) and, for the whole
+    test set, against the oracle; static store == dynamic extraction"""
+    from igmc_b200.util_functions import MyDataset, MyDynamicDataset
+    from tests.helpers import load_flixster_cases
+    ds, pairs, cases = load_flixster_cases()
+    d = MyDynamicDataset(None, ds["adj_train"], (pairs[0], pairs[1]), pairs[2], 1, 1.0, 10000, None, None,
+                         ds["class_values"])
+    b = d.extract_batch(np.arange(pairs.shape[1]))
+    g = extract_np.RatingCSR(ds["adj_train"])
+    graphs = []
+    for c, want in enumerate(cases):
+        graphs.append(extract_np.construct_graph(dict(u_nodes=want["u_nodes"], v_nodes=want["v_nodes"], u=want["u"],
+                                                      v=want["v"], r=want["r"], node_labels=want["node_labels"]),
+                                                 want["y"], 1))
+    ob = extract_np.collate(graphs)
+    res = batch_equal(b, ob)
+    assert all(res.values()), res
+    b.check()
+    eu, ev, el = ds["test"]
+    idx = np.arange(0, len(eu), 9)
+    dt = MyDynamicDataset(None, ds["adj_train"], (eu, ev), el, 1, 1.0, 10000, None, None, ds["class_values"])
+    bt = dt.extract_batch(idx)
+    obt = extract_np.extract_batch(g, eu[idx], ev[idx], el[idx], ds["class_values"], 1, 1.0, 10000, pair_ids=idx)
+    res = batch_equal(bt, obt)
+    assert all(res.values()), res
+    st = MyDataset(None, ds["adj_train"], (eu[idx], ev[idx]), el[idx], 1, 1.0, 10000, None, None, ds["class_values"])
+    bs = st.extract_batch(np.arange(len(idx)))
+    res = batch_equal(bs, obt)
+    assert all(res.values()), res

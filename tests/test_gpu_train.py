@@ -122,3 +122,35 @@ def test_static_dataset_trains_like_dynamic():
         assert all(math.isfinite(l) for l in losses)
         outs.append(m.flat_params.clone())
     assert float((outs[0] - outs[1]).abs().max()) <= 1e-6
+
+
+def test_ensemble_eval_matches_oracle(tmp_path):
+    """test_once(..., ensemble=True, checkpoints=[...]) (reference train_eval.py:114-139,208-245): predictions of the
+    checkpoints are averaged, then the RMSE is taken; compared with the same average through the oracle models"""
+    from igmc_b200.models import IGMC
+    from igmc_b200.train_eval import test_once
+    from igmc_b200.util_functions import MyDynamicDataset
+    ds = _tiny()
+    eu, ev, el = ds["test"]
+    n = 110
+    test = MyDynamicDataset(None, ds["adj_train"], (eu[:n], ev[:n]), el[:n], 1, 1.0, 10, None, None,
+                            ds["class_values"], seed=4)
+    model = IGMC(test, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=0.2).cuda()
+    g = extract_np.RatingCSR(ds["adj_train"])
+    ob = extract_np.extract_batch(g, eu[:n], ev[:n], el[:n], ds["class_values"], 1, 1.0, 10, seed=4,
+                                  pair_ids=np.arange(n))
+    tb = pyg_restated.to_torch_batch(ob)
+    ckpts, preds = [], []
+    for k in range(3):
+        torch.manual_seed(100 + k)
+        ref = pyg_restated.IGMCRef(4, (32, 32, 32, 32), 5, 4, 0.2).eval()
+        path = tmp_path / "model_checkpoint{}.pth".format(k)
+        torch.save(ref.state_dict(), path)          # a reference-format checkpoint (same keys and shapes)
+        ckpts.append(str(path))
+        with torch.no_grad():
+            preds.append(ref(tb["x"], tb["edge_index"], tb["edge_type"]))
+    want = math.sqrt(float(((torch.stack(preds, 1).mean(1) - tb["y"]) ** 2).mean()))
+    log = []
+    got = test_once(test, model, 50, logger=lambda info, m, o: log.append(info), ensemble=True, checkpoints=ckpts)
+    assert abs(got - want) <= 1e-4, (got, want)
+    assert log and log[0]["epoch"] == "ensemble"

@@ -104,3 +104,19 @@ def test_live_reference(h, mnph):
         assert tuple(data.x.shape) == d["x"].shape
         assert data.edge_index.shape[1] == d["edge_index"].shape[1]
         assert float(data.y) == d["y"][0]
+
+
+def test_flixster_real_data_golden():
+    """REAL flixster ratings (fixture built from the reference's raw_data by tests/golden/make_flixster_fixture.py):
+    the oracle reproduces what the reference's own extraction returned for 64 pairs (40 train incl. the target-edge
+    removal, 24 test), RNG-free because max_nodes_per_hop=10000 exceeds every degree."""
+    from tests.helpers import load_flixster_cases
+    ds, pairs, cases = load_flixster_cases()
+    assert ds["adj_train"].shape == (3000, 3000) and ds["adj_train"].nnz == 23556 and ds["num_relations"] == 10
+    assert len(ds["test"][0]) == 2617
+    g = extract_np.RatingCSR(ds["adj_train"])
+    for c, want in enumerate(cases):
+        sub = extract_np.extract_subgraph(g, pairs[0, c], pairs[1, c], 1, 1.0, 10000)
+        for k in ("u_nodes", "v_nodes", "u", "v", "r", "node_labels"):
+            assert np.array_equal(np.asarray(sub[k], np.int64), want[k]), (c, k)
+        assert float(ds["class_values"][pairs[2, c]]) == want["y"]
