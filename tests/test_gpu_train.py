@@ -154,3 +154,41 @@ def test_ensemble_eval_matches_oracle(tmp_path):
     got = test_once(test, model, 50, logger=lambda info, m, o: log.append(info), ensemble=True, checkpoints=ckpts)
     assert abs(got - want) <= 1e-4, (got, want)
     assert log and log[0]["epoch"] == "ensemble"
+
+
+def test_continue_from_checkpoint(tmp_path):
+    """train_multiple_epochs(..., continue_from=k, res_dir=...) (reference train_eval.py:56-64): model and optimizer
+    state are restored from the reference-format checkpoints, training resumes at epoch k+1 and runs epochs-k epochs"""
+    from igmc_b200.models import IGMC
+    from igmc_b200.train_eval import train_multiple_epochs
+    from igmc_b200.util_functions import MyDynamicDataset
+    ds = _tiny()
+    tu, tv, tl = ds["train"]
+    eu, ev, el = ds["test"]
+    train = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, 10, None, None, ds["class_values"])
+    test = MyDynamicDataset(None, ds["adj_train"], (eu[:100], ev[:100]), el[:100], 1, 1.0, 10, None, None,
+                            ds["class_values"])
+    steps_per_epoch = math.ceil(len(train) / 50)
+    state = {}
+
+    def logger(info, m, opt):
+        state.setdefault("log", []).append(dict(info))
+        state["steps"] = int(opt.step_count[0])
+        torch.save(m.state_dict(), tmp_path / "model_checkpoint{}.pth".format(info["epoch"]))
+        torch.save(opt.state_dict(), tmp_path / "optimizer_checkpoint{}.pth".format(info["epoch"]))
+
+    torch.manual_seed(1)
+    m1 = IGMC(train, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=0.2)
+    train_multiple_epochs(train, test, m1, epochs=2, batch_size=50, lr=1e-3, lr_decay_factor=0.1,
+                          lr_decay_step_size=50, weight_decay=0, ARR=0.001, logger=logger)
+    assert state["steps"] == 2 * steps_per_epoch
+    saved = {k: v.clone() for k, v in torch.load(tmp_path / "model_checkpoint2.pth").items()}
+    state["log"] = []
+    m2 = IGMC(train, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=0.2)
+    train_multiple_epochs(train, test, m2, epochs=3, batch_size=50, lr=1e-3, lr_decay_factor=0.1,
+                          lr_decay_step_size=50, weight_decay=0, ARR=0.001, logger=logger, continue_from=2,
+                          res_dir=str(tmp_path))
+    assert [l["epoch"] for l in state["log"]] == [3]
+    assert state["steps"] == 3 * steps_per_epoch                     # Adam's step count went on from the checkpoint
+    moved = max(float((m2.state_dict()[k].cpu() - saved[k].cpu()).abs().max()) for k in saved)
+    assert 0.0 < moved < 0.5                                          # started from the checkpoint, not from a fresh init
