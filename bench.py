@@ -314,15 +314,16 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     # ---- (1) value: inputs resident in HBM, per-step CUDA events, L2 flushed between steps ----
-    staged = torch.zeros(K, B + 3, dtype=torch.int64)
+    staged = torch.zeros(K, B + 4, dtype=torch.int64)
     from igmc_b200.train_eval import _u64_as_i64
     from igmc_b200.models import splitmix64
     value_first = cursor[0] + 1
     for k in range(K):
         staged[k, :B] = torch.as_tensor(steps_idx[value_first + k])   # indices of the batch extracted in step k
         staged[k, B] = _u64_as_i64(SAMPLE_SEED)
-        staged[k, B + 1] = _u64_as_i64(splitmix64(model.drop_seed + 100000 + k))
+        staged[k, B + 1] = _u64_as_i64(eng.drop_seed(100000 + k))
         staged[k, B + 2] = G
+        staged[k, B + 3] = _u64_as_i64(eng.drop_seed(100000 + k + 1))   # the next step's draws (list images)
     staged = staged.cuda()
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
@@ -369,7 +370,7 @@ def run_ours(args):
         barrier()
         t0 = time.perf_counter()
         for k in range(K):
-            eng.step_pipe(next_idx(), epoch=2, next_G=G)        # stages + copies (B+3) int64 from pinned memory
+            eng.step_pipe(next_idx(), epoch=2, next_G=G)        # stages + copies (B+4) int64 from pinned memory
             loss_host[k:k + 1].copy_(eng.last_loss, non_blocking=True)
         barrier()
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
@@ -396,9 +397,10 @@ def run_ours(args):
             flush.fill_(1)
             evs[0].record()
             b = ex.extract(idx=idx, reuse=True)
-            evs[1].record()
             model._step += 1
             drop = model.make_dropout(True)
+            model.stage_batch(b, True, drop)   # list images: part of the extraction branch of the step graph
+            evs[1].record()
             _, saved = model._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / G)
             evs[2].record()
             model._launch_backward(b, drop, saved, saved["ws"]["dpred"])
@@ -440,11 +442,12 @@ def run_ours(args):
                        "cuda_graph": not args.no_graph,
                        "pipeline": "extraction of batch k+1 overlaps the model step of batch k (two graph branches)"},
             "clocks": clk,
-            "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 3) * 8,
+            "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 4) * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K,
                     "runs_ms_per_step": [1000.0 * x / K for x in e2e_runs]},
-            # extract/assemble (2 | 1) + weight prep + forward + backward + grad_reduce + Adam (+ 3 readout launches)
-            "gpu_launches": ((6 if static else 7) + (3 if args.model == "dgcnn_rs" else 0)) * K,
+            # extract/assemble (2 | 1) + list images + weight prep + forward + backward + grad_reduce + Adam
+            # (+ 3 readout launches)
+            "gpu_launches": ((7 if static else 8) + (3 if args.model == "dgcnn_rs" else 0)) * K,
             "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
                         "note": "same steps back to back without the L2 flush (informative)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

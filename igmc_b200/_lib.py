@@ -11,6 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libigmc_b200.so")
 
 MAX_LAYERS = 8
+REDUCE_WS_FLOATS = MAX_LAYERS * 32 * 64 + MAX_LAYERS * 32 + 64   # IGMC_REDUCE_WS_FLOATS
 MAX_HOP = 3
 HIDDEN = 32
 LIN1_OUT = 128
@@ -79,6 +80,11 @@ class Saved(C.Structure):
                 ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp), ("wprep", vp), ("prof", vp)]
 
 
+class Stage(C.Structure):
+    _fields_ = [("tab", vp), ("ent", vp), ("inv_deg", vp), ("tab_ints", C.c_int32), ("lcap", C.c_int32),
+                ("chunk", C.c_int32), ("cluster", C.c_int32)]
+
+
 class SortPool(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("k", "width", "state_stride", "c1", "c2", "kw2", "t1", "t2", "dense_dim",
                                          "off_conv1_w", "off_conv1_b", "off_conv2_w", "off_conv2_b", "off_lin1_w",
@@ -97,10 +103,14 @@ _SIGS = {
     "igmc_batch_ptrs": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
     "igmc_batch_prepare": [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Adj), vp, vp],
     "igmc_forward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),
-                     C.c_int, C.POINTER(Saved), vp, C.c_float, vp, vp, C.c_int, vp, vp],
+                     C.c_int, C.POINTER(Saved), vp, C.c_float, vp, vp, C.c_int, C.POINTER(Stage), vp, vp],
     "igmc_backward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),
-                      C.POINTER(Saved), vp, vp, vp, C.c_int, vp, vp],
-    "igmc_grad_reduce": [C.POINTER(Model), vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+                      C.POINTER(Saved), vp, vp, vp, C.c_int, C.POINTER(Stage), vp, vp],
+    "igmc_raw_grad_count": [C.POINTER(Model)],
+    "igmc_stage_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.POINTER(Stage)],
+    "igmc_stage_lists": [C.POINTER(Model), vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout), C.c_int,
+                         C.POINTER(Stage), C.POINTER(Stage), vp, vp],
+    "igmc_grad_reduce": [C.POINTER(Model), vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                          C.c_float, vp, vp, vp, vp],
     "igmc_adam_step": [vp, vp, vp, vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                        C.c_float, vp, vp, C.c_float, vp],

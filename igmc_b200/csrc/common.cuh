@@ -20,6 +20,17 @@ __device__ __forceinline__ void igmc_set_err(int* err, int code) {
   if (err) atomicCAS(err, 0, code);
 }
 
+// ---- "raw" per-CTA gradient rows of the relation-space kernels (csrc/rgcn_rs.cu -> csrc/optim.cu) -------------
+// layer l: [ dW_r : R x inp x 32 | d root : inp x 32 | d bias : 32 ],  inp = in rounded up to 4 (in = in_dim0 for
+// layer 0, 32 after).  The (att, basis) chain rule is linear in dW_r, so it is applied ONCE to the sum over CTAs
+// (k_grad_reduce_raw) instead of in every CTA.
+__host__ __device__ __forceinline__ int igmc_raw_layer_floats(int R, int inp) { return (R + 1) * inp * 32 + 32; }
+__host__ __device__ __forceinline__ int igmc_raw_off(int R, int in0, int l) {
+  const int in0p = (in0 + 3) & ~3;
+  return l == 0 ? 0 : igmc_raw_layer_floats(R, in0p) + (l - 1) * igmc_raw_layer_floats(R, 32);
+}
+__host__ __device__ __forceinline__ int igmc_raw_count(int R, int in0, int L) { return igmc_raw_off(R, in0, L); }
+
 // ---- counter-based hashing (bit-exact twin: oracle/extract_np.py::splitmix64/hash_keys) ----
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
@@ -99,6 +110,39 @@ __device__ __forceinline__ int block_sum_i(int v, int* ws) {
   s = ws[32];
   __syncthreads();
   return s;
+}
+
+// ---- async-proxy bulk copies (TMA, 1-D) + mbarrier completion --------------------------------------
+// One thread arms the barrier with the byte count (mbar_expect_tx) and issues cp.async.bulk; every consumer
+// spins on mbar_wait(parity).  A barrier initialised with count 1 completes a phase when that one arrival AND all
+// announced bytes have landed.  Sizes / addresses must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// generic-proxy accesses of shared memory made before this fence are ordered before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
 
 #define IGMC_CUDA_CHECK_LAUNCH()                      \

@@ -152,6 +152,183 @@ k_grad_reduce(igmc_model_t M, const float* __restrict__ params, int B, int rows,
   }
 }
 
+// ---- raw rows of the cluster plans (csrc/rgcn_rs.cu): [rows][igmc_raw_count] with per layer dW_r | d root | d bias ----
+// Blocks [0, NA): block (l, k) owns row k of every dW_r of layer l (kj = k*32 + lane):
+//   dWs[r][j] = sum over the partial rows (8 warps = 8 interleaved row subsets, added in fixed order)
+//               + arr * d reg / d W_r[k][j]
+//   d basis[b][k][j] = sum_r att[r,b] dWs[r][j]                       (complete: written to grad)
+//   d att[r,b]      += sum_j dWs[r][j] basis[b][k][j]                 (partial over k: scratch, summed by the layer's
+//                                                                      last block in k order)
+//   reg             += sum_{r<R-1} sum_j (W_{r+1}[k][j] - W_r[k][j])^2   (same)
+// Blocks [NA, NA + PB): one thread per parameter for d root / d bias (row sums) and lin1 / lin2 (saved factors).
+// The last layer-finaliser writes the loss.  Every sum has a fixed order: bitwise deterministic.
+constexpr int RW_ATT = 0;                                   // [L][32][64] partial <dW_r, basis[b]> per (l, k)
+constexpr int RW_REGP = IGMC_MAX_LAYERS * 32 * 64;          // [L][32] partial regulariser values
+constexpr int RW_REGL = RW_REGP + IGMC_MAX_LAYERS * 32;     // [L] per-layer regulariser
+constexpr int RW_TICK = RW_REGL + IGMC_MAX_LAYERS;          // ints: [L] layer tickets, [1] global ticket
+
+__global__ void __launch_bounds__(256)
+k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int rows, int NA,
+                  const float* __restrict__ gpart, const float* __restrict__ dhid, const float* __restrict__ feat,
+                  const float* __restrict__ hid, const float* __restrict__ dpred, const float* __restrict__ sqerr,
+                  float loss_scale, float arr, float grad_scale, float* __restrict__ grad, float* __restrict__ loss_out,
+                  float* __restrict__ reg_ws) {
+  const int R = M.num_relations, NB = M.num_bases, L = M.num_layers, in0 = M.in_dim0;
+  const int RC = igmc_raw_count(R, in0, L), F = 2 * HID * L;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((int)blockIdx.x >= NA) {
+    const int p = ((int)blockIdx.x - NA) * 256 + tid;
+    if (p >= M.param_count) return;
+    float s = 0.f;
+    bool write = false;
+    if (p < M.conv_param_count) {
+      for (int l = 0; l < L; ++l) {
+        const int in = l == 0 ? in0 : HID, inp = (in + 3) & ~3;
+        const size_t ro = (size_t)igmc_raw_off(R, in0, l);
+        const int qr = p - M.off_root[l], qb = p - M.off_bias[l];
+        size_t src = 0;
+        if (qr >= 0 && qr < in * HID) { src = ro + (size_t)R * inp * HID + qr; write = true; }
+        else if (qb >= 0 && qb < HID) { src = ro + (size_t)(R + 1) * inp * HID + qb; write = true; }
+        if (write) {
+          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four interleaved chains, fixed combination order
+          int g = 0;
+          for (; g + 4 <= rows; g += 4) {
+            s0 += gpart[(size_t)g * RC + src];
+            s1 += gpart[(size_t)(g + 1) * RC + src];
+            s2 += gpart[(size_t)(g + 2) * RC + src];
+            s3 += gpart[(size_t)(g + 3) * RC + src];
+          }
+          for (; g < rows; ++g) s0 += gpart[(size_t)g * RC + src];
+          s = (s0 + s1) + (s2 + s3);
+          break;
+        }
+      }
+    } else if (M.readout != 0) {
+      // readout parameters belong to the external readout's gradient kernel
+    } else if (p >= M.off_lin1_w && p < M.off_lin1_w + L1O * F) {
+      const int q = p - M.off_lin1_w, o = q / F, i = q - o * F;      // lin1.weight[o][i]
+      for (int g = 0; g < B; ++g) s = fmaf(dhid[(size_t)g * L1O + o], feat[(size_t)g * F + i], s);
+      write = true;
+    } else if (p >= M.off_lin1_b && p < M.off_lin1_b + L1O) {
+      const int o = p - M.off_lin1_b;
+      for (int g = 0; g < B; ++g) s += dhid[(size_t)g * L1O + o];
+      write = true;
+    } else if (p >= M.off_lin2_w && p < M.off_lin2_w + L1O) {
+      const int o = p - M.off_lin2_w;
+      for (int g = 0; g < B; ++g) s = fmaf(dpred[g], hid[(size_t)g * L1O + o], s);
+      write = true;
+    } else if (p == M.off_lin2_b) {
+      for (int g = 0; g < B; ++g) s += dpred[g];
+      write = true;
+    }
+    if (write) grad[p] = s * grad_scale;
+    return;
+  }
+  // ---- block (l, k) ----
+  int l = 0, k = (int)blockIdx.x;
+  if (k >= in0) { l = 1 + (k - in0) / HID; k = (k - in0) % HID; }
+  const int in = l == 0 ? in0 : HID, inp = (in + 3) & ~3;
+  __shared__ float att[IGMC_MAX_BASES * 16];          // [R][NB], R <= 12
+  __shared__ float bs[IGMC_MAX_BASES][HID];           // basis[b][k][:]
+  __shared__ float ps[12][8][HID];                    // per-warp partial row sums
+  __shared__ float dWs[12][HID];
+  __shared__ float Wc[12][HID];
+  __shared__ float red[8];
+  __shared__ int s_last;
+  for (int i = tid; i < R * NB; i += 256) att[i] = params[M.off_att[l] + i];
+  for (int i = tid; i < NB * HID; i += 256) bs[i >> 5][i & 31] = params[M.off_basis[l] + ((i >> 5) * in + k) * HID + (i & 31)];
+  {
+    const float* gp = gpart + (size_t)igmc_raw_off(R, in0, l) + (size_t)k * HID + lane;
+    for (int r = 0; r < R; ++r) {
+      const float* gr = gp + (size_t)r * inp * HID;
+      float s0 = 0.f, s1 = 0.f;
+      int g = warp;
+      for (; g + 8 < rows; g += 16) {
+        s0 += gr[(size_t)g * RC];
+        s1 += gr[(size_t)(g + 8) * RC];
+      }
+      if (g < rows) s0 += gr[(size_t)g * RC];
+      ps[r][warp][lane] = s0 + s1;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < R * HID; t += 256) {
+    const int r = t >> 5, j = t & 31;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += ps[r][w][j];
+    dWs[r][j] = s;
+    float wv = 0.f;
+    for (int b = 0; b < NB; ++b) wv = fmaf(att[r * NB + b], bs[b][j], wv);
+    Wc[r][j] = wv;
+  }
+  __syncthreads();
+  float pair_sum = 0.f;
+  if (arr != 0.f) {
+    for (int t = tid; t < R * HID; t += 256) {
+      const int r = t >> 5, j = t & 31;
+      const float w0 = Wc[r][j];
+      float dw = 0.f;
+      if (r > 0) dw += 2.f * (w0 - Wc[r - 1][j]);
+      if (r < R - 1) {
+        const float dd = Wc[r + 1][j] - w0;
+        dw -= 2.f * dd;
+        pair_sum += dd * dd;
+      }
+      dWs[r][j] = fmaf(arr, dw, dWs[r][j]);
+    }
+  }
+  const float regp = block_sum_f256(pair_sum, red);   // barriers inside: dWs is complete afterwards
+  __syncthreads();
+  // d basis[b][k][:]
+  for (int t = tid; t < NB * HID; t += 256) {
+    const int b = t >> 5, j = t & 31;
+    float s = 0.f;
+    for (int r = 0; r < R; ++r) s = fmaf(att[r * NB + b], dWs[r][j], s);
+    grad[M.off_basis[l] + (b * in + k) * HID + j] = s * grad_scale;
+  }
+  // partial d att[r,b] over this k
+  float* wsa = reg_ws + RW_ATT + ((size_t)l * 32 + k) * 64;
+  for (int pr = warp; pr < R * NB; pr += 8) {
+    const int r = pr / NB, b = pr - r * NB;
+    const float s = warp_sum_f(dWs[r][lane] * bs[b][lane]);
+    if (lane == 0) wsa[pr] = s;
+  }
+  int* tick = reinterpret_cast<int*>(reg_ws + RW_TICK);
+  if (tid == 0) reg_ws[RW_REGP + l * 32 + k] = regp;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&tick[l], 1) == in - 1);
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last block of layer l: d att[l] and the layer's regulariser value, summed over k in order ----
+  __threadfence();
+  for (int pr = tid; pr < R * NB; pr += 256) {
+    float s = 0.f;
+    for (int kk = 0; kk < in; ++kk) s += __ldcg(reg_ws + RW_ATT + ((size_t)l * 32 + kk) * 64 + pr);
+    grad[M.off_att[l] + pr] = s * grad_scale;
+  }
+  if (tid == 0) {
+    float s = 0.f;
+    for (int kk = 0; kk < in; ++kk) s += __ldcg(reg_ws + RW_REGP + l * 32 + kk);
+    reg_ws[RW_REGL + l] = s;
+    tick[l] = 0;   // re-arm
+    __threadfence();
+    if (atomicAdd(&tick[IGMC_MAX_LAYERS], 1) == L - 1) {   // last layer to finish: the loss
+      __threadfence();
+      float reg = 0.f;
+      for (int q = 0; q < L; ++q) reg += __ldcg(reg_ws + RW_REGL + q);
+      float mse = 0.f;
+      if (sqerr)
+        for (int g = 0; g < B; ++g) mse += sqerr[g];
+      if (loss_out) loss_out[0] = mse * loss_scale + arr * reg;
+      tick[IGMC_MAX_LAYERS] = 0;
+    }
+  }
+}
+
 // torch.optim.Adam step; the last block to finish increments the device-side step counter.
 __global__ void k_adam(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int64_t* __restrict__ step_count, int* __restrict__ ticket, int n,
@@ -189,11 +366,20 @@ __global__ void k_adam(float* __restrict__ params, const float* __restrict__ gra
 }  // namespace
 
 extern "C" int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, int gpart_rows, const float* gpart,
-                                const float* dhid, const float* feat, const float* hid, const float* dpred,
-                                const float* sqerr, float loss_scale, float arr, float grad_scale, float* grad,
-                                float* loss_out, float* reg_ws, void* stream) {
+                                int raw_rows, const float* dhid, const float* feat, const float* hid,
+                                const float* dpred, const float* sqerr, float loss_scale, float arr, float grad_scale,
+                                float* grad, float* loss_out, float* reg_ws, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   const int PB = (M->param_count + 255) / 256;
+  if (raw_rows) {
+    if (!reg_ws) return -18;
+    if (M->num_relations > 12) return -16;
+    const int NA = M->in_dim0 + (M->num_layers - 1) * HID;
+    k_grad_reduce_raw<<<NA + PB, 256, 0, st>>>(*M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr,
+                                               loss_scale, arr, grad_scale, grad, loss_out, reg_ws);
+    IGMC_CUDA_CHECK_LAUNCH();
+    return 0;
+  }
   int blocks = PB;
   size_t smem = 0;
   if (arr != 0.f) {

@@ -591,11 +591,15 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
 int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
                const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, int cluster,
-               int* err, cudaStream_t st);
+               const igmc_stage_t* stage, int* err, cudaStream_t st);
 int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                 const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
-                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, int cluster, int* err,
-                cudaStream_t st);
+                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, int cluster,
+                const igmc_stage_t* stage, int* err, cudaStream_t st);
+int rs_stage_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, igmc_stage_t* img);
+int rs_stage_lists(const igmc_model_t* M, const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B,
+                   int n_cap, const igmc_dropout_t* D, int training, const igmc_stage_t* fwd, const igmc_stage_t* bwd,
+                   cudaStream_t st);
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st);
 
@@ -614,7 +618,7 @@ extern "C" int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, in
                               : fwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
     return b > 227 * 1024 ? -3 : (int)b;
   }
-  if (cluster != 1 && cluster != 2 && cluster != 4) return -15;
+  if (cluster < 1 || cluster > 4) return -15;
   if (!rs_supported(M)) return -16;
   int threads, lcap, chunk;
   size_t smem;
@@ -622,10 +626,36 @@ extern "C" int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, in
   return rc ? rc : (int)smem;
 }
 
+extern "C" int igmc_stage_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, igmc_stage_t* img) {
+  int rc = check_model(M);
+  if (rc) return rc;
+  if (cluster < 1 || cluster > 4) return -15;
+  if (!rs_supported(M)) return -16;
+  return rs_stage_plan(M, n_cap, cluster, backward, img);
+}
+
+extern "C" int igmc_stage_lists(const igmc_model_t* M, const int32_t* node_ptr, const int32_t* edge_ptr,
+                                const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
+                                const igmc_stage_t* fwd, const igmc_stage_t* bwd, int* err, void* stream) {
+  (void)err;
+  if (B <= 0) return 0;
+  int rc = check_model(M);
+  if (rc) return rc;
+  if (!rs_supported(M)) return -16;
+  return rs_stage_lists(M, node_ptr, edge_ptr, A, B, n_cap, D, training, fwd, bwd, (cudaStream_t)stream);
+}
+
+extern "C" int igmc_raw_grad_count(const igmc_model_t* M) {
+  int rc = check_model(M);
+  if (rc) return rc;
+  return igmc_raw_count(M->num_relations, M->in_dim0, M->num_layers);
+}
+
 extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                             const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                             const igmc_dropout_t* D, int training, const igmc_saved_t* S, const float* y,
-                            float loss_scale, float* dpred, float* sqerr, int cluster, int* err, void* stream) {
+                            float loss_scale, float* dpred, float* sqerr, int cluster, const igmc_stage_t* stage,
+                            int* err, void* stream) {
   if (B <= 0) return 0;
   int rc = check_model(M);
   if (rc) return rc;
@@ -634,7 +664,7 @@ extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const ui
     if (!rs_supported(M)) return -16;
     if (!S->wprep) return -17;
     return rs_forward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, training, S, y, loss_scale, dpred,
-                      sqerr, cluster, err, st);
+                      sqerr, cluster, stage, err, st);
   }
   const size_t smem = fwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
   if (smem > 227 * 1024) return -3;
@@ -654,7 +684,7 @@ extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const ui
 extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                              const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                              const igmc_dropout_t* D, const igmc_saved_t* S, const float* dpred, float* gpart,
-                             float* dhid, int cluster, int* err, void* stream) {
+                             float* dhid, int cluster, const igmc_stage_t* stage, int* err, void* stream) {
   if (B <= 0) return 0;
   int rc = check_model(M);
   if (rc) return rc;
@@ -664,8 +694,8 @@ extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const u
   if (cluster > 0) {
     if (!rs_supported(M)) return -16;
     if (!S->wprep) return -17;
-    return rs_backward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, dpred, gpart, dhid, cluster, err,
-                       st);
+    return rs_backward(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, dpred, gpart, dhid, cluster, stage,
+                       err, st);
   }
   const size_t smem = bwd_smem_bytes(n_cap, M->num_relations, M->num_bases, M->num_layers);
   if (smem > 227 * 1024) return -3;

@@ -97,9 +97,30 @@ struct Lists {
 };
 
 __host__ __device__ __forceinline__ int list_ints(int own_cap) { return 3 * (own_cap + 4) + 4 * (own_cap + XR * XCH); }
+// A list image = IMG_HDR header ints (entries, segments, staged flag, own nodes) directly followed by the tables
+// above.  Built either by the kernel itself (stage_lists) or once per batch by k_stage_lists (igmc_stage_lists), in
+// which case the model kernels pull it into shared memory with bulk (TMA) copies.
+constexpr int IMG_HDR = 4;
+__host__ __device__ __forceinline__ int img_ints(int own_cap) { return IMG_HDR + ((list_ints(own_cap) + 3) & ~3); }
 
-// Block-wide; ends with a barrier.  `ibuf` has list_ints(own_cap) ints.  invdeg_out/invdeg_glob (optional) get
-// 1/max(kept degree,1) of the own nodes.
+// pointers into a table block `ibuf` (the header sits at ibuf - IMG_HDR)
+__device__ __forceinline__ Lists lists_view(int* ibuf, int own_cap, const uint32_t* lbuf, const uint32_t* adj,
+                                            const int32_t* eid, bool mirror, int eb, int m_half) {
+  Lists Ls;
+  Ls.lptr = ibuf;
+  Ls.segbase = ibuf + (own_cap + 4);
+  Ls.ex = Ls.segbase + (own_cap + 4);
+  Ls.seg_p0 = Ls.ex + (own_cap + 4);
+  Ls.seg_p1 = Ls.seg_p0 + (own_cap + XR * XCH);
+  Ls.seg_row = Ls.seg_p1 + (own_cap + XR * XCH);
+  Ls.seg_ord = Ls.seg_row + (own_cap + XR * XCH);
+  Ls.adj = adj; Ls.eid = eid; Ls.mirror = mirror; Ls.eb = eb; Ls.m_half = m_half;
+  Ls.lst = ibuf[2 - IMG_HDR] ? lbuf : nullptr;
+  return Ls;
+}
+
+// Block-wide; ends with a barrier.  `ibuf` has list_ints(own_cap) ints and is preceded by the IMG_HDR header ints
+// (written here too).  invdeg_out/invdeg_glob (each optional) get 1/max(kept degree,1) of the own nodes.
 __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t* eid, const int32_t* ptr, int nb, int lo,
                                              int hi, const Keep& K, bool mirror, int eb, int m_half, uint32_t* lbuf,
                                              int lcap, int* ibuf, int own_cap, int chunk, int* ws, float* invdeg_out,
@@ -131,11 +152,11 @@ __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t*
   }
   if (tid == 0) lptr[0] = 0;
   __syncthreads();
-  if (invdeg_out)
+  if (invdeg_out || invdeg_glob)
     for (int i = tid; i < n_own; i += NT) {
       const float id = 1.f / (float)max(lptr[i + 1], 1);
-      invdeg_out[lo + i] = id;
-      invdeg_glob[nb + lo + i] = id;
+      if (invdeg_out) invdeg_out[lo + i] = id;
+      if (invdeg_glob) invdeg_glob[nb + lo + i] = id;
     }
   // ---- segments per node (uncapped) and their prefix sums: offsets | extras << 16 ----
   int run_off = 0, run_ex = 0;
@@ -189,7 +210,11 @@ __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t*
     run_seg += tot;
     __syncthreads();
   }
-  if (tid == 0) segbase[n_own] = run_seg;
+  if (tid == 0) {
+    segbase[n_own] = run_seg;
+    int* hdr = ibuf - IMG_HDR;
+    hdr[0] = total; hdr[1] = run_seg; hdr[2] = staged ? 1 : 0; hdr[3] = n_own;
+  }
   // ---- pass 2: compacted copy of the entries ----
   if (staged) {
     if (K.active) {
@@ -425,7 +450,7 @@ __global__ void __launch_bounds__(NTMAX, 1)
 k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
              int lcap, int chunk, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y,
-             float loss_scale, float* __restrict__ dpred, float* __restrict__ sqerr, int* err) {
+             float loss_scale, float* __restrict__ dpred, float* __restrict__ sqerr, igmc_stage_t IMG, int* err) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
@@ -443,10 +468,11 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   float* invdeg = bias_s + HID;                      // [n_cap]
   float* feat_s = invdeg + a4(n_cap);
   float* hid_s = feat_s + a4(F);
-  int* ibuf = reinterpret_cast<int*>(hid_s + L1O);              // list offsets + segment table
+  int* ibuf = reinterpret_cast<int*>(hid_s + L1O) + IMG_HDR;    // [header |] list offsets + segment table
   uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));   // [lcap]
   __shared__ int s_t[2];
   __shared__ int ws[34];
+  __shared__ __align__(8) uint64_t mbar[2];   // [0] list image, [1] weight slab of the current layer (TMA completion)
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
   const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
@@ -459,8 +485,36 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const int n_own = own.hi - own.lo;
   IGMC_STAMP(0);
 
-  if (tid == 0) { s_t[0] = 0x7fffffff; s_t[1] = 0x7fffffff; }
+  // weights of a layer: the [W_r ; root] slab prepared by igmc_prep_weights, one bulk (TMA) copy issued by a single
+  // thread; every thread waits on mbar[1] (phase = layer parity) right before the layer's tensor-core tiles, so the
+  // copy runs under the gather.  Callers guarantee (barrier) that nobody still reads Wn.
+  auto load_weights = [&](int l) {
+    const int inp = l == 0 ? in0p : HID;
+    const int KS = a8(R * inp) + a8(inp) + 4;
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&mbar[1], (uint32_t)(HID * KS * 4));
+      bulk_g2s(Wn, S.wprep + (size_t)l * 2 * wprep_slab(R), (uint32_t)(HID * KS * 4), &mbar[1]);
+    }
+    if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
+  };
+  if (tid == 0) {
+    s_t[0] = 0x7fffffff; s_t[1] = 0x7fffffff;
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_fence_init();
+  }
   __syncthreads();
+  const bool use_img = IMG.tab != nullptr;
+  if (use_img && tid == 0) {   // pre-staged lists: header + tables, then the entries, straight into shared memory
+    const int32_t* gt = IMG.tab + (size_t)blockIdx.x * IMG.tab_ints;
+    const int total = __ldg(gt), staged = __ldg(gt + 2);
+    const uint32_t tb = (uint32_t)IMG.tab_ints * 4u, eb4 = (staged && total > 0) ? (uint32_t)a4(total) * 4u : 0u;
+    mbar_expect_tx(&mbar[0], tb + eb4);
+    bulk_g2s(ibuf - IMG_HDR, gt, tb, &mbar[0]);
+    if (eb4) bulk_g2s(lbuf, IMG.ent + (size_t)blockIdx.x * IMG.lcap, eb4, &mbar[0]);
+  }
+  load_weights(0);
   float* H = Hbuf0;
   float* Hn = Hbuf1;
   for (int idx = tid; idx < n * HID; idx += NT) {
@@ -471,13 +525,26 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     if (c == 0 && lab == 1) atomicMin(&s_t[1], v);
   }
   // in-lists of the own nodes -> shared memory; kept in-degree (dropout_adj is applied once, models.py:193)
-  const Lists Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap,
-                               ibuf, own_cap, chunk, ws, invdeg, S.inv_deg);
+  Lists Ls;
+  if (use_img) {
+    for (int i = tid; i < n_own; i += NT) {
+      const float id = __ldg(IMG.inv_deg + nb + own.lo + i);
+      invdeg[own.lo + i] = id;
+      S.inv_deg[nb + own.lo + i] = id;
+    }
+    mbar_wait(&mbar[0], 0);
+    Ls = lists_view(ibuf, own_cap, lbuf, A.in_adj, A.in_eid, false, eb, m_half);
+    __syncthreads();
+  } else {
+    Ls = stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, lcap, ibuf, own_cap,
+                     chunk, ws, invdeg, S.inv_deg);
+  }
   if (tid == 0) ws[33] = 0;   // segment ticket of gather_segments (made visible by the barrier at the top of the layer loop)
   const bool ext = M.readout != 0;   // concat_states only: an external readout (csrc/sortpool.cu) takes over
   const int tu = s_t[0], ti = s_t[1];
   if (!ext && (tu >= n || ti >= n)) {
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
+    mbar_wait(&mbar[1], 0);   // do not exit under an in-flight bulk copy
     return;
   }
   if (S.prof && tid == 0) {   // debug: staging facts
@@ -487,14 +554,6 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
-  // weights of a layer: the [W_r ; root] slab prepared by igmc_prep_weights + bias
-  auto load_weights = [&](int l) {
-    const int inp = l == 0 ? in0p : HID;
-    const int KS = a8(R * inp) + a8(inp) + 4;
-    copy_f4(Wn, S.wprep + (size_t)l * 2 * wprep_slab(R), HID * KS);
-    if (tid < HID) bias_s[tid] = params[M.off_bias[l] + tid];
-  };
-  load_weights(0);
   for (int l = 0; l < L; ++l) {
     const int inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), SS = K1p + 4, KS = K1p + inpp + 4;
@@ -526,8 +585,8 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
           }
           t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
           st4[(size_t)r * SS4 + k4] = t;
-          if (S.zsave)
-            reinterpret_cast<float4*>(S.zsave + ((size_t)l * S.node_cap + nb + v) * (size_t)(R * HID))[k4] = t;
+          if (S.zsave && l == 0)   // layers >= 1: the backward takes its weight gradients from its own aggregate
+            reinterpret_cast<float4*>(S.zsave + (size_t)(nb + v) * (size_t)K1)[k4] = t;
         }
       }
       IGMC_STAMP_T(0, 42); IGMC_STAMP_T(992, 45);
@@ -535,6 +594,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       __syncthreads();
       IGMC_STAMP(4 + 6 * l);
       // ---- dense transform on tensor cores: out[16x8 tiles] = [AGG' | h] . [W_r ; root] ----
+      if (c0 == 0) mbar_wait(&mbar[1], (uint32_t)(l & 1));   // this layer's weight slab has landed
       const int mt = (crow + 15) >> 4;
       for (int tile = warp; tile < mt * 4; tile += nwarps) {
         const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
@@ -590,6 +650,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       __syncthreads();
     }
     IGMC_STAMP(6 + 6 * l);
+    if (n_own == 0) mbar_wait(&mbar[1], (uint32_t)(l & 1));   // keep the barrier phases in step (no tiles ran)
     // the next layer's weights do not depend on the peers: load them while the row pushes of the cluster land
     if (CL > 1) cluster_arrive();
     if (l + 1 < L) load_weights(l + 1);
@@ -671,20 +732,49 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
 // ------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------
-constexpr int DPS_ = 40;   // row stride of the own-rows dpre copy (B operand of the weight-gradient tiles)
+constexpr int DPS_ = 40;   // row stride of the own-rows dpre / h_{l-1} copies (== 8 mod 32: conflict-free k-major fragments)
 
+// 3xTF32 with the A operand split once (it is reused for several B tiles)
+__device__ __forceinline__ void split_tf32(const float (&f)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float_as_uint(f[i]) & 0xffffe000u;
+    lo[i] = __float_as_uint(f[i] - __uint_as_float(hi[i]));
+  }
+}
+__device__ __forceinline__ void mma_3xtf32_a(float (&d)[4], float (&dsm)[4], const uint32_t (&ah)[4],
+                                             const uint32_t (&al)[4], const float (&bf)[2]) {
+  uint32_t bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
+    bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i]));
+  }
+  mma_tf32(dsm, al, bh);
+  mma_tf32(dsm, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// Per layer l (top down), for the own nodes u of this CTA:
+//   (0) dpre = d h_l (1 - h_l^2); gather source DPS = dpre / deg of ALL nodes, DP = dpre of the own rows
+//   (1) Q[u,r,:] = sum_{(u->d) of type r, kept} DPS[d,:]                  (gather over the out-lists, as forward)
+//       d h_{l-1}[u] = [Q[u] | dpre[u]] . [W_r^T ; root^T]                (tensor cores) -> pushed to every CTA
+//   (2) dW_r = sum_u h_{l-1}[u]^T Q[u,r,:],  d root = sum_u h_{l-1}[u]^T dpre[u],  d bias = sum_u dpre[u]
+//       (tensor cores, K = own nodes; A = the h_{l-1} rows fetched by TMA under the gather)  -> raw partial row
+//   Layer 0 has no data gradient; its dW_r come from the saved aggregate of the one-hot input (S.zsave).
+// The (att, basis) chain rule is NOT applied here: it is linear and runs once on the sum (igmc_grad_reduce).
 template <int NTMAX>
 __global__ void __launch_bounds__(NTMAX, 1)
 k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
               const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
               int lcap, int chunk, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred,
-              float* __restrict__ gpart, float* __restrict__ dhid_out, int* err) {
+              float* __restrict__ gpart, float* __restrict__ dhid_out, igmc_stage_t IMG, int* err) {
   extern __shared__ __align__(16) float smem[];
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int g = blockIdx.x / CL;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5, NT = blockDim.x;
-  const int L = M.num_layers, R = M.num_relations, NB = M.num_bases, CW = HID * L, F = 2 * CW;
+  const int L = M.num_layers, R = M.num_relations, CW = HID * L, F = 2 * CW;
   const int in0 = M.in_dim0, in0p = a4(in0);
   const int SSmax = R * HID + 4, KSmax = (R + 1) * HID + 4;
   const int own_cap = own_cap_of(n_cap, CL), own_cap16 = a16(own_cap);
@@ -692,18 +782,16 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   float* DH1 = DH0 + (size_t)n_cap * HID;               //   parity: peers push d h_{l-1} into one while the other, turned
                                                         //   in place into dpre/deg (the gather source), is being read
   float* DP = DH1 + (size_t)n_cap * HID;                // [own_cap16][DPS_] dpre of the own rows (zero padded)
-  float* Wn = DP + (size_t)own_cap16 * DPS_;            // [32][KS]   prepared weights of the data-gradient tiles (1)
-  float* dW = Wn;                                       // [KRp][32]  weight gradients (2): Wn is dead by then and is
-                                                        //            reloaded at the top of the next layer
-  float* stage = Wn + (size_t)HID * KSmax;              // [chunk + XR][SSmax]  |  weight-gradient tile [rows][TS]
-  float* att_s = stage + (size_t)(chunk + XR) * SSmax;
-  float* invdeg = att_s + a4(R * NB);
+  float* Wn = DP + (size_t)own_cap16 * DPS_;            // [32][KS]   prepared weights of the data-gradient tiles
+  float* stage = Wn + (size_t)HID * KSmax;              // [chunk + XR][SSmax] Q rows  |  layer 0: aggregate tile [rows][TS]
+  float* Hs = stage + (size_t)(chunk + XR) * SSmax;     // [chunk][DPS_] h_{l-1} of the chunk's rows (TMA)
+  float* invdeg = Hs + (size_t)chunk * DPS_;
   float* dfeat = invdeg + a4(n_cap);
   float* dhid_s = dfeat + a4(F);
-  float* dB = dhid_s + L1O;                              // [32]
-  int* ibuf = reinterpret_cast<int*>(dB + HID);          // list offsets + segment table
+  int* ibuf = reinterpret_cast<int*>(dhid_s + L1O) + IMG_HDR;   // [header |] list offsets + segment table
   uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));   // [lcap]
   __shared__ int ws[34];
+  __shared__ __align__(8) uint64_t mbar[3];   // TMA completion: [0] list image, [1] weight slab, [2] h_{l-1} rows
 
   const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
   const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
@@ -717,13 +805,48 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int n_own = own.hi - own.lo;
   const bool ext = M.readout != 0;   // d concat_states comes from an external readout (S.dstate)
   const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
-  float* gp = gpart + ((size_t)g * CL + rank) * M.conv_param_count;
+  float* gp = gpart + ((size_t)g * CL + rank) * (size_t)igmc_raw_count(R, in0, L);
   IGMC_STAMP(0);
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    mbar_init(&mbar[2], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  uint32_t wuse = 0, huse = 0;   // completed-phase counters of mbar[1] / mbar[2] (uniform over the block)
+  // per-layer operand that does not depend on the peers: the [W_r^T ; root^T] slab of the data gradient (one bulk
+  // copy by one thread; waited for right before the tiles).  Callers guarantee that nobody still reads Wn.
+  auto load_weights = [&](int l) {
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)(HID * ((R + 1) * HID + 4) * 4);
+      fence_proxy_async();
+      mbar_expect_tx(&mbar[1], bytes);
+      bulk_g2s(Wn, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), bytes, &mbar[1]);
+    }
+  };
+  const bool use_img = IMG.tab != nullptr;
+  if (use_img && tid == 0) {
+    const int32_t* gt = IMG.tab + (size_t)blockIdx.x * IMG.tab_ints;
+    const int total = __ldg(gt), staged = __ldg(gt + 2);
+    const uint32_t tb = (uint32_t)IMG.tab_ints * 4u, eb4 = (staged && total > 0) ? (uint32_t)a4(total) * 4u : 0u;
+    mbar_expect_tx(&mbar[0], tb + eb4);
+    bulk_g2s(ibuf - IMG_HDR, gt, tb, &mbar[0]);
+    if (eb4) bulk_g2s(lbuf, IMG.ent + (size_t)blockIdx.x * IMG.lcap, eb4, &mbar[0]);
+  }
+  if (L > 1) load_weights(L - 1);
+  // stale staging rows are read as (discarded or zero-weighted) tile padding: keep them finite
+  {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4* st4 = reinterpret_cast<float4*>(stage);
+    const int tot4 = (int)((((size_t)(chunk + XR) * SSmax) + (size_t)chunk * DPS_) >> 2);   // stage + Hs are adjacent
+    for (int i = tid; i < tot4; i += NT) st4[i] = z4;
+  }
   // out-lists of the own nodes (symmetric batches: the in-lists with mirrored edge ids)
-  const Lists Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb,
-                               own.lo, own.hi, K, sym, eb, m_half, lbuf, lcap, ibuf, own_cap, chunk, ws, nullptr,
-                               nullptr);
-  if (tid == 0) ws[33] = 0;   // segment ticket of gather_segments
+  Lists Ls;
+  if (!use_img)
+    Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb, own.lo,
+                     own.hi, K, sym, eb, m_half, lbuf, lcap, ibuf, own_cap, chunk, ws, nullptr, nullptr);
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
   if (!ext) {
@@ -767,22 +890,22 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       DHtop[hix(v, c)] = dh;
     }
   }
+  if (use_img) {
+    mbar_wait(&mbar[0], 0);
+    Ls = lists_view(ibuf, own_cap, lbuf, sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym, eb, m_half);
+  }
+  if (tid == 0) ws[33] = 0;   // segment ticket of gather_segments
   __syncthreads();
 
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
-  // per-layer operands that do not depend on the peers: att and the [W_r^T ; root^T] slab of the data gradient
-  auto load_weights = [&](int l) {
-    for (int idx = tid; idx < R * NB; idx += NT) att_s[idx] = params[M.off_att[l] + idx];
-    if (l > 0) copy_f4(Wn, S.wprep + ((size_t)l * 2 + 1) * wprep_slab(R), HID * ((R + 1) * HID + 4));
-  };
-  load_weights(L - 1);
   for (int l = L - 1; l >= 0; --l) {
     const int in = l == 0 ? in0 : HID, inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), KRp = K1p + inpp;
     const int sb = 2 + 8 * (L - 1 - l);
     float* DPS = (l & 1) ? DH1 : DH0;                    // d h_l on entry, dpre/deg after step (0)
     float* DHn = (l & 1) ? DH0 : DH1;                    // d h_{l-1} (written here and by the peers)
+    float* gpl = gp + igmc_raw_off(R, in0, l);           // this layer's block of the raw partial row
     // (0) d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows (padded with zeros)
     for (int idx = tid; idx < n * 8; idx += NT) {
       const int v = idx >> 3, c4 = (idx & 7) * 4;
@@ -800,13 +923,30 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     }
     __syncthreads();
     IGMC_STAMP(sb);
+    // d bias = column sums of d pre over the own rows (last warp, lane = channel; the loads are independent)
+    if (warp == nwarps - 1) {
+      float accb = 0.f;
+      for (int r_ = 0; r_ < n_own; ++r_) accb += DP[(size_t)r_ * DPS_ + lane];
+      gpl[(R + 1) * inp * HID + lane] = accb;
+    }
 
-    // (1) data gradient of the own nodes:  d h_{l-1}[u] = [Q[u] | dpre[u]] . [W_r^T ; root^T],
-    //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)         -> pushed to every CTA's DH
     if (l > 0) {
       const int SS = K1p + 4, KS = KRp + 4;
+      const int NTN = (R + 1) * 4;                        // 8-column tiles of [dW_r ... | d root]
+      bool arrived = false;
       for (int c0 = 0; c0 < n_own; c0 += chunk) {
         const int crow = min(chunk, n_own - c0);
+        // h_{l-1} of the chunk's rows -> Hs, one 128 B bulk copy per row issued by warp 0 (lands under the gather)
+        if (warp == 0) {
+          fence_proxy_async();
+          if (lane == 0) mbar_expect_tx(&mbar[2], (uint32_t)crow * 128u);
+          __syncwarp();
+          for (int r_ = lane; r_ < crow; r_ += 32)
+            bulk_g2s(Hs + (size_t)r_ * DPS_, S.states + (size_t)(nb + own.lo + c0 + r_) * CW + (l - 1) * HID, 128u,
+                     &mbar[2]);
+        }
+        // (1) data gradient of the own nodes:  d h_{l-1}[u] = [Q[u] | dpre[u]] . [W_r^T ; root^T],
+        //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)         -> pushed to every CTA's DH
         gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, DPS, stage, SS, HID, &ws[33]);
         __syncthreads();
         if (tid == 0) ws[33] = 0;
@@ -826,9 +966,16 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
             }
           }
         }
+        if (crow < chunk) {   // short (last) chunk: the K-padding rows of Hs must be zero (TMA fills rows < crow only)
+          const int zr = a8(crow) - crow;
+          for (int idx = tid; idx < zr * 8; idx += NT)
+            *reinterpret_cast<float4*>(Hs + (size_t)(crow + (idx >> 3)) * DPS_ + ((idx & 7) << 2)) =
+                make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         IGMC_STAMP(sb + 5);
         __syncthreads();
         IGMC_STAMP(sb + 6);
+        if (c0 == 0) { mbar_wait(&mbar[1], wuse & 1u); ++wuse; }   // [W_r^T ; root^T] has landed
         const int mt = (crow + 15) >> 4;
         for (int tile = warp; tile < mt * 4; tile += nwarps) {
           const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
@@ -883,86 +1030,112 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
             }
           }
         }
-        __syncthreads();
+        IGMC_STAMP(sb + 1);
+        // the last chunk's pushes of d h_{l-1} are issued: arrive now, wait at the end of the layer - the
+        // weight-gradient tiles below touch neither peer memory nor the buffer the peers are writing (DHn)
+        if (CL > 1 && c0 + chunk >= n_own) { cluster_arrive(); arrived = true; }
+        // (2) weight gradients over the chunk's rows:  D[k][(r,j) | j'] += sum_u h_{l-1}[u][k] [Q[u] | dpre[u]]
+        //     M = 32 (k, two 16-row tiles), N = (R+1)*32, K = crow nodes; warp = (m tile, every (nwarps/2)-th n tile)
+        mbar_wait(&mbar[2], huse & 1u); ++huse;            // the chunk's h_{l-1} rows have landed
+        {
+          constexpr int MAXI = 4;
+          const int m0 = (warp & 1) << 4, jn0 = warp >> 1, jstep = nwarps >> 1;
+          float acc[MAXI][4], acs[MAXI][4];
+#pragma unroll
+          for (int i = 0; i < MAXI; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) { acc[i][c] = 0.f; acs[i][c] = 0.f; }
+          const int krows = a8(crow);                       // rows beyond crow: Hs is zero there, stage/DP are finite
+          for (int k0 = 0; k0 < krows; k0 += 8) {
+            // A^T fragment: row = k (m0+g), col = node (k0+t)
+            const float* a = Hs + (size_t)(k0 + tq) * DPS_ + m0 + gq;
+            const float af[4] = {a[0], a[8], a[4 * DPS_], a[4 * DPS_ + 8]};
+            uint32_t ah[4], al[4];
+            split_tf32(af, ah, al);
+#pragma unroll
+            for (int i = 0; i < MAXI; ++i) {
+              const int jn = jn0 + i * jstep;
+              if (jn < NTN) {
+                const int n0 = jn << 3;
+                // B fragment: k = node, n = column of [Q | dpre]
+                const float* bp = n0 < K1 ? stage + (size_t)(k0 + tq) * SS + n0 + gq
+                                          : DP + (size_t)(c0 + k0 + tq) * DPS_ + (n0 - K1) + gq;
+                const int bs4 = n0 < K1 ? 4 * SS : 4 * DPS_;
+                const float bf[2] = {bp[0], bp[bs4]};
+                mma_3xtf32_a(acc[i], acs[i], ah, al, bf);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < MAXI; ++i) {
+            const int jn = jn0 + i * jstep;
+            if (jn < NTN) {
+              const int c = (jn << 3) + 2 * tq;             // column of [dW_0 .. dW_{R-1} | d root]
+              const int k = m0 + gq;
+              // raw layout: dW_r[k][j] at (r*32 + k)*32 + j, d root[k][j] at R*32*32 + k*32 + j
+              float* o0 = gpl + (size_t)(((c >> 5) * HID + k) * HID + (c & 31));
+              float* o1 = o0 + 8 * HID;
+              float2 v0 = make_float2(acc[i][0] + acs[i][0], acc[i][1] + acs[i][1]);
+              float2 v1 = make_float2(acc[i][2] + acs[i][2], acc[i][3] + acs[i][3]);
+              if (c0 > 0) {   // later chunks accumulate into the row this thread wrote before (same thread, no race)
+                const float2 p0 = *reinterpret_cast<const float2*>(o0), p1 = *reinterpret_cast<const float2*>(o1);
+                v0.x += p0.x; v0.y += p0.y; v1.x += p1.x; v1.y += p1.y;
+              }
+              *reinterpret_cast<float2*>(o0) = v0;
+              *reinterpret_cast<float2*>(o1) = v1;
+            }
+          }
+        }
+        IGMC_STAMP(sb + 7);
+        __syncthreads();   // stage / Hs are free for the next chunk
       }
-    }
-    IGMC_STAMP(sb + 1);
-    // the pushes of d h_{l-1} are done: arrive now, wait at the end of the layer - the weight-gradient phase below
-    // touches neither peer memory nor the buffer the peers are writing (DHn), so it hides the barrier latency
-    if (CL > 1 && l > 0) cluster_arrive();
-
-    // (2) weight gradients over the own nodes on tensor cores:  dW[kk][j] = sum_v A[v][kk] dpre[v][j]
-    //     A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | h_{l-1}[v,k] ]  ->  M = KRp rows, N = 32, K = own nodes
-    {
+      if (n_own == 0) {   // nothing ran: keep the barrier phases in step and write the zero gradient block
+        mbar_wait(&mbar[1], wuse & 1u); ++wuse;
+        for (int i = tid; i < (R + 1) * HID * HID; i += NT) gpl[i] = 0.f;
+      }
+      if (CL > 1 && !arrived) cluster_arrive();
+    } else {
+      // layer 0: dW[kk][j] = sum_v A[v][kk] dpre[v][j],  A[v] = [ AGG'[v,r,k] (saved, 1/deg-scaled) | x[v,k] one-hot ]
+      //          M = KRp rows, N = 32, K = own nodes
       const int TS = KRp + 8;                              // tile row stride (== 8 mod 32: conflict-free A^T frags)
       int trows = (int)(((size_t)(chunk + XR) * SSmax) / TS) & ~7;   // node rows of one tile pass
       if (trows > a8(n_own)) trows = a8(n_own);
-      const int mtiles = KRp >> 4;                          // KRp is a multiple of 8; odd multiples handled below
       const int mt = (KRp + 15) >> 4;
-      (void)mtiles;
-      // accumulators live across node passes: tile list per warp is fixed (<= 2 tiles per warp for R <= 7 at 32 warps)
       constexpr int MAXT = 4;
       float acc[MAXT][4], acs[MAXT][4];
 #pragma unroll
       for (int i = 0; i < MAXT; ++i)
 #pragma unroll
         for (int c = 0; c < 4; ++c) { acc[i][c] = 0.f; acs[i][c] = 0.f; }
-      float accb = 0.f;
       for (int t0 = 0; t0 < a8(n_own) && trows > 0; t0 += trows) {
         const int rows = min(trows, a8(n_own) - t0);        // multiple of 8, rows beyond n_own are zero
-        {   // tile[r][0..K1) = saved aggregate, [K1..K1p) = 0, [K1p..KRp) = h_{l-1}; rows beyond n_own are zero
+        {   // tile[r][0..K1) = saved aggregate, [K1..K1p) = 0, [K1p..KRp) = one-hot input; rows beyond n_own are zero
           const int kq = K1 >> 2, TS4 = TS >> 2;
           float4* t4 = reinterpret_cast<float4*>(stage);
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-          // L2-latency bound: four independent loads in flight per thread, then the four stores
-          const float* zbase = S.zsave + ((size_t)l * S.node_cap + nb + own.lo + t0) * (size_t)(R * HID);
-          for (int base = tid; base < rows * kq; base += 4 * NT) {
-            float4 val[4];
-            int dst[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int idx = base + u * NT;
-              val[u] = z4;
-              dst[u] = -1;
-              if (idx < rows * kq) {
-                const int r_ = idx / kq, k4 = idx - r_ * kq;
-                dst[u] = r_ * TS4 + k4;
-                if (t0 + r_ < n_own) val[u] = __ldg(reinterpret_cast<const float4*>(zbase + (size_t)r_ * (R * HID)) + k4);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < 4; ++u)
-              if (dst[u] >= 0) t4[dst[u]] = val[u];
+          const float* zbase = S.zsave + (size_t)(nb + own.lo + t0) * (size_t)K1;
+          for (int idx = tid; idx < rows * kq; idx += NT) {
+            const int r_ = idx / kq, k4 = idx - r_ * kq;
+            float4 val = z4;
+            if (t0 + r_ < n_own) val = __ldg(reinterpret_cast<const float4*>(zbase + (size_t)r_ * K1) + k4);
+            t4[r_ * TS4 + k4] = val;
           }
-          if (l > 0) {   // h_{l-1} columns: one float4 of the states row per item (K1 == K1p for 32-wide inputs)
-            for (int idx = tid; idx < rows * 8; idx += NT) {
-              const int r_ = idx >> 3, c4 = (idx & 7) << 2;
-              float4 hv = z4;
-              if (t0 + r_ < n_own)
-                hv = __ldcg(reinterpret_cast<const float4*>(S.states + (size_t)(nb + own.lo + t0 + r_) * CW + (l - 1) * HID + c4));
-              *reinterpret_cast<float4*>(stage + (size_t)r_ * TS + K1p + c4) = hv;
-            }
-          } else {
-            const int tail = KRp - K1;   // zero padding of the aggregate + the one-hot input columns
-            for (int idx = tid; idx < rows * tail; idx += NT) {
-              const int r_ = idx / tail, q = idx - r_ * tail, kk = K1 + q;
-              float hv = 0.f;
-              const int k = kk - K1p;
-              if (k >= 0 && k < in && t0 + r_ < n_own) hv = (k == (int)node_label[nb + own.lo + t0 + r_]) ? 1.f : 0.f;
-              stage[(size_t)r_ * TS + kk] = hv;
-            }
+          const int tail = KRp - K1;   // zero padding of the aggregate + the one-hot input columns
+          for (int idx = tid; idx < rows * tail; idx += NT) {
+            const int r_ = idx / tail, q = idx - r_ * tail, kk = K1 + q;
+            float hv = 0.f;
+            const int k = kk - K1p;
+            if (k >= 0 && k < in && t0 + r_ < n_own) hv = (k == (int)node_label[nb + own.lo + t0 + r_]) ? 1.f : 0.f;
+            stage[(size_t)r_ * TS + kk] = hv;
           }
         }
         __syncthreads();
-        IGMC_STAMP(sb + 7);
-        // node (k) loop outside, the warp's tiles inside: independent accumulator chains interleave
         for (int k0 = 0; k0 < rows; k0 += 8) {
 #pragma unroll
           for (int i = 0; i < MAXT; ++i) {
             const int tile = warp + i * nwarps;
             if (tile < mt * 4) {
               const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
-              // A^T fragment: row = kk (m0+g), col = node (k0+t);  B: k = node, n = channel
               const bool hi_ok = (m0 + 8) < KRp;               // KRp may be an odd multiple of 8
               const float* a = stage + (size_t)(k0 + tq) * TS + m0 + gq;
               const float* bp = DP + (size_t)(t0 + k0 + tq) * DPS_ + n0 + gq;
@@ -972,69 +1145,86 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
             }
           }
         }
-        if (warp == nwarps - 1) {   // d bias: column sums of dpre over the pass (lane = channel)
-          for (int r_ = 0; r_ < rows; ++r_) accb += DP[(size_t)(t0 + r_) * DPS_ + lane];
-        }
         __syncthreads();
       }
+      // tile row kk -> raw row: kk < K1: dW (r*inp + k = kk); K1p <= kk < K1p + in: d root row kk - K1p
 #pragma unroll
       for (int i = 0; i < MAXT; ++i) {
         const int tile = warp + i * nwarps;
         if (tile < mt * 4) {
           const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3, cc = n0 + 2 * tq;
-          *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq) * HID + cc) =
-              make_float2(acc[i][0] + acs[i][0], acc[i][1] + acs[i][1]);
-          if (m0 + 8 < KRp)
-            *reinterpret_cast<float2*>(dW + (size_t)(m0 + gq + 8) * HID + cc) =
-                make_float2(acc[i][2] + acs[i][2], acc[i][3] + acs[i][3]);
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int kk = m0 + gq + 8 * half;
+            const float2 v = make_float2(acc[i][2 * half] + acs[i][2 * half], acc[i][2 * half + 1] + acs[i][2 * half + 1]);
+            if (kk < K1) *reinterpret_cast<float2*>(gpl + (size_t)kk * HID + cc) = v;
+            else if (kk >= K1p && kk < K1p + in) *reinterpret_cast<float2*>(gpl + (size_t)(K1 + kk - K1p) * HID + cc) = v;
+          }
         }
       }
-      if (warp == nwarps - 1) dB[lane] = accb;
-      __syncthreads();
       IGMC_STAMP(sb + 2);
-      copy_f4(stage, params + M.off_basis[l], NB * in * HID);   // basis of this layer -> shared (tile is done)
-      __syncthreads();
-      const float* bs = stage;
-      // d basis[b][k][j] = sum_r att[r,b] dW_r[k][j]
-      for (int row = warp; row < NB * in; row += nwarps) {
-        const int b = row / in, k = row - b * in;
-        float s = 0.f;
-        for (int r = 0; r < R; ++r) s = fmaf(att_s[r * NB + b], dW[(r * inp + k) * HID + lane], s);
-        gp[M.off_basis[l] + row * HID + lane] = s;
-      }
-      // d root[k][j], d bias[j]
-      for (int idx = tid; idx < in * HID; idx += NT) gp[M.off_root[l] + idx] = dW[K1p * HID + idx];
-      if (tid < HID) gp[M.off_bias[l] + tid] = dB[tid];
-      // d att[r,b] = < dW_r , basis[b] >   (warp per (r,b), fixed-order tree)
-      for (int rb = warp; rb < R * NB; rb += nwarps) {
-        const int r = rb / NB, b = rb - r * NB;
-        float s = 0.f;
-        for (int k = 0; k < in; ++k) s = fmaf(dW[(r * inp + k) * HID + lane], bs[(b * in + k) * HID + lane], s);
-        s = warp_sum_f(s);
-        if (lane == 0) gp[M.off_att[l] + rb] = s;
-      }
     }
     __syncthreads();
     IGMC_STAMP(sb + 3);
-    // (3) every CTA's DH holds d h_{l-1} of all nodes once the pushes have landed; the next layer's operands are
-    //     loaded while they do (dW, which aliases Wn, has been consumed by the chain rule above)
-    if (l > 0) load_weights(l - 1);
+    // (3) every CTA's DH holds d h_{l-1} of all nodes once the pushes have landed; the next layer's weight slab is
+    //     requested while they do (every read of Wn is behind the barrier above)
+    if (l > 1) load_weights(l - 1);
     if (CL > 1 && l > 0) cluster_wait();   // nothing is exchanged after layer 0
     IGMC_STAMP(sb + 4);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// list images: what stage_lists builds, once per batch and off the model kernels' critical path
+// grid = (B * CL, 2): blockIdx.y = 0 forward (in-lists, kept in-degree), 1 backward (out-lists / mirrored in-lists)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+k_stage_lists(const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
+              int CL, igmc_dropout_t D, int training, igmc_stage_t F, igmc_stage_t Bw) {
+  extern __shared__ __align__(16) int smem_i[];
+  __shared__ int ws[34];
+  const int dir = blockIdx.y;
+  const igmc_stage_t I = dir ? Bw : F;
+  const int blk = blockIdx.x, g = blk / CL, rank = blk % CL;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const int own_cap = own_cap_of(n_cap, CL);
+  int* ibuf = smem_i + IMG_HDR;
+  uint32_t* lbuf = reinterpret_cast<uint32_t*>(ibuf + a4(list_ints(own_cap)));
+  const int nb = node_ptr[g], n = node_ptr[g + 1] - nb;
+  const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
+  int32_t* gt = I.tab + (size_t)blk * I.tab_ints;
+  if (n > n_cap) {   // the model kernels flag IGMC_ERR_SMEM_NODES and never look at the image
+    if (tid < IMG_HDR) gt[tid] = 0;
+    return;
+  }
+  const Keep K = make_keep(D, training);
+  const bool sym = A.symmetric != 0;
+  const Split own = own_range(n, rank, CL);
+  if (dir == 0)
+    stage_lists(A.in_adj, A.in_eid, A.in_ptr, nb, own.lo, own.hi, K, false, eb, m_half, lbuf, I.lcap, ibuf, own_cap,
+                I.chunk, ws, nullptr, I.inv_deg);
+  else
+    stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb, own.lo, own.hi,
+                K, sym, eb, m_half, lbuf, I.lcap, ibuf, own_cap, I.chunk, ws, nullptr, nullptr);
+  const int total = smem_i[0], staged = smem_i[2];
+  for (int i = tid; i < I.tab_ints; i += NT) gt[i] = smem_i[i];
+  if (staged) {
+    uint32_t* ge = I.ent + (size_t)blk * I.lcap;
+    for (int i = tid; i < a4(total); i += NT) ge[i] = i < total ? lbuf[i] : 0u;
   }
 }
 
 size_t fwd_base_fl(int n_cap, int R, int L, int CL) {   // everything except the stage rows and the list buffer
   const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL);
-  return 2 * (size_t)n_cap * HID + HID * KSmax + HID + a4(n_cap) + a4((int)F) + L1O + a4(list_ints((int)own_cap)) +
+  return 2 * (size_t)n_cap * HID + HID * KSmax + HID + a4(n_cap) + a4((int)F) + L1O + img_ints((int)own_cap) +
          (size_t)XR * ((size_t)R * HID + 4);
 }
-size_t bwd_base_fl(int n_cap, int R, int NB, int L, int CL) {
-  const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;   // dW [(R+1)*32][32] aliases Wn [32][KSmax]
+size_t bwd_base_fl(int n_cap, int R, int L, int CL) {   // everything except the (stage + Hs) rows and the list buffer
+  const size_t KSmax = (size_t)(R + 1) * HID + 4, F = 2 * HID * L;
   const size_t own_cap = (size_t)own_cap_of(n_cap, CL), own_cap16 = (size_t)a16((int)own_cap);
-  return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + a4(R * NB) + a4(n_cap) +
-         a4((int)F) + L1O + HID + a4(list_ints((int)own_cap)) + (size_t)XR * ((size_t)R * HID + 4);
+  return 2 * (size_t)n_cap * HID + own_cap16 * DPS_ + HID * KSmax + a4(n_cap) + a4((int)F) + L1O +
+         img_ints((int)own_cap) + (size_t)XR * ((size_t)R * HID + 4);
 }
 
 }  // namespace rs
@@ -1044,23 +1234,24 @@ int rs_supported(const igmc_model_t* M) { return M->num_relations <= rs::RS_MAX_
 
 // threads per CTA, dynamic shared memory, stage chunk rows and edge-list staging capacity for a plan
 int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* threads, size_t* smem, int* lcap, int* chunk) {
-  const size_t limit = 227 * 1024 - 1024;   // static shared memory of the kernels (scan scratch) counts too
+  const size_t limit = 227 * 1024 - 1024;   // static shared memory of the kernels (scan scratch, mbarriers) counts too
   const int R = M->num_relations;
   const size_t SSmax = (size_t)R * rs::HID + 4;
-  const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, R, M->num_bases, M->num_layers, cluster)
+  const size_t rowfl = SSmax + (backward ? rs::DPS_ : 0);   // a chunk row: staging row (+ its h_{l-1} row, backward)
+  const size_t base = 4 * (backward ? rs::bwd_base_fl(n_cap, R, M->num_layers, cluster)
                                     : rs::fwd_base_fl(n_cap, R, M->num_layers, cluster));
   const int own16 = rs::a16(rs::own_cap_of(n_cap, cluster));
-  // weight-gradient accumulators: ceil(4 * KRp/16 / nwarps) tiles per warp must be <= 4
+  // weight-gradient accumulators: ceil(8 (R+1) tiles / nwarps) per warp must be <= 4
   const int tiles = 4 * ((R + 1) * rs::HID / 16);
   if (backward && (tiles + 31) / 32 > 4) return -3;
   // stage rows: as many as fit (multiple of 16, at least 16), leaving >= 4 KB for the edge lists
-  if (base + 4096 + 16 * SSmax * 4 > limit) return -3;
-  size_t rows = (limit - base - 4096) / (SSmax * 4);
+  if (base + 4096 + 16 * rowfl * 4 > limit) return -3;
+  size_t rows = (limit - base - 4096) / (rowfl * 4);
   rows &= ~(size_t)15;
   if (rows > (size_t)own16) rows = own16;
-  // prefer a larger list buffer over more stage rows once half of the own rows fit
-  size_t left = limit - base - rows * SSmax * 4;
-  size_t lc = left / 4;
+  // the layer-0 aggregate tile of the backward reuses the staging rows: it must hold at least 8 node rows
+  size_t left = limit - base - rows * rowfl * 4;
+  size_t lc = (left / 4) & ~(size_t)3;
   if (lc > 16384) lc = 16384;
   {
     // 1024 threads (64 registers) or 512 threads (128 registers: no address rematerialisation, fewer instructions)
@@ -1077,7 +1268,7 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
   }
   *chunk = (int)rows;
   *lcap = (int)lc;
-  *smem = base + rows * SSmax * 4 + lc * 4;
+  *smem = base + rows * rowfl * 4 + lc * 4;
   return 0;
 }
 
@@ -1101,34 +1292,95 @@ static int launch_cluster(Kern kern, int grid, int threads, size_t smem, int clu
   return 0;
 }
 
+// the image a kernel is handed must have been built for exactly its plan
+static int check_image(const igmc_stage_t* I, int n_cap, int cluster, int lcap, int chunk, igmc_stage_t* out) {
+  igmc_stage_t none = {};
+  *out = none;
+  if (!I || !I->tab) return 0;
+  if (I->cluster != cluster || I->chunk != chunk || I->lcap != lcap ||
+      I->tab_ints != rs::img_ints(rs::own_cap_of(n_cap, cluster)) || !I->ent)
+    return -19;
+  *out = *I;
+  return 0;
+}
+
+int rs_stage_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, igmc_stage_t* img) {
+  int threads, lcap, chunk;
+  size_t smem;
+  int rc = rs_plan(M, n_cap, cluster, backward, &threads, &smem, &lcap, &chunk);
+  if (rc) return rc;
+  img->tab_ints = rs::img_ints(rs::own_cap_of(n_cap, cluster));
+  img->lcap = lcap;
+  img->chunk = chunk;
+  img->cluster = cluster;
+  return 0;
+}
+
+int rs_stage_lists(const igmc_model_t* M, const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B,
+                   int n_cap, const igmc_dropout_t* D, int training, const igmc_stage_t* fwd, const igmc_stage_t* bwd,
+                   cudaStream_t st) {
+  if (!fwd || !fwd->tab || !fwd->ent || !fwd->inv_deg) return -19;
+  const int cluster = fwd->cluster;
+  igmc_stage_t want;
+  int rc = rs_stage_plan(M, n_cap, cluster, 0, &want);
+  if (rc) return rc;
+  if (want.tab_ints != fwd->tab_ints || want.lcap != fwd->lcap || want.chunk != fwd->chunk) return -19;
+  const bool both = training && bwd && bwd->tab;
+  igmc_stage_t bw = {};
+  int lcmax = fwd->lcap;
+  if (both) {
+    rc = rs_stage_plan(M, n_cap, cluster, 1, &want);
+    if (rc) return rc;
+    if (want.tab_ints != bwd->tab_ints || want.lcap != bwd->lcap || want.chunk != bwd->chunk || bwd->cluster != cluster ||
+        !bwd->ent)
+      return -19;
+    bw = *bwd;
+    if (bw.lcap > lcmax) lcmax = bw.lcap;
+  }
+  const size_t smem = ((size_t)fwd->tab_ints + (size_t)lcmax) * 4;
+  cudaFuncSetAttribute(rs::k_stage_lists, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  rs::k_stage_lists<<<dim3(B * cluster, both ? 2 : 1), 512, smem, st>>>(node_ptr, edge_ptr, *A, n_cap, cluster, *D,
+                                                                        training, *fwd, bw);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e + 1000;
+}
+
 int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D, int training,
                const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, int cluster,
-               int* err, cudaStream_t st) {
+               const igmc_stage_t* stage, int* err, cudaStream_t st) {
   int threads, lcap, chunk;
   size_t smem;
   int rc = rs_plan(M, n_cap, cluster, 0, &threads, &smem, &lcap, &chunk);
   if (rc) return rc;
+  igmc_stage_t img;
+  rc = check_image(stage, n_cap, cluster, lcap, chunk, &img);
+  if (rc) return rc;
+  if (img.tab && !img.inv_deg) return -19;
   if (threads == 512)
     return launch_cluster(rs::k_forward_rs<512>, B * cluster, threads, smem, cluster, st, *M, params, node_label,
-                          node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, err);
+                          node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, img,
+                          err);
   return launch_cluster(rs::k_forward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
-                        edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, err);
+                        edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, img, err);
 }
 
 int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
                 const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
-                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, int cluster, int* err,
-                cudaStream_t st) {
+                const igmc_saved_t* S, const float* dpred, float* gpart, float* dhid, int cluster,
+                const igmc_stage_t* stage, int* err, cudaStream_t st) {
   int threads, lcap, chunk;
   size_t smem;
   int rc = rs_plan(M, n_cap, cluster, 1, &threads, &smem, &lcap, &chunk);
   if (rc) return rc;
+  igmc_stage_t img;
+  rc = check_image(stage, n_cap, cluster, lcap, chunk, &img);
+  if (rc) return rc;
   if (threads == 512)
     return launch_cluster(rs::k_backward_rs<512>, B * cluster, threads, smem, cluster, st, *M, params, node_label,
-                          node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, err);
+                          node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, img, err);
   return launch_cluster(rs::k_backward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
-                        edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, err);
+                        edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, img, err);
 }
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st) {

@@ -242,17 +242,71 @@ class IGMC(nn.Module):
                       hid_gscale=torch.empty(B, 128, **f32), pred=torch.empty(B, **f32),
                       target=torch.empty(B, 2, dtype=torch.int32, device=dev),
                       dpred=torch.zeros(B, **f32), sqerr=torch.zeros(B, **f32), loss=torch.zeros(1, **f32),
-                      reg_ws=torch.zeros(_lib.MAX_LAYERS * 256 + 4, **f32), cluster=cl)
+                      reg_ws=torch.zeros(_lib.REDUCE_WS_FLOATS, **f32), cluster=cl)
             if train:
-                zdim = max(NB, self.num_relations if cl > 0 else 0) * HID
-                ws.update(zsave=torch.empty(L, ncap, zdim, **f32),
-                          dstate=torch.empty(L, ncap, HID, **f32),
-                          gpart=torch.zeros(B * max(cl, 1), self._cmodel.conv_param_count, **f32),
+                if cl > 0:   # cluster plans: layer-0 aggregate only; raw partial rows (chain rule in igmc_grad_reduce)
+                    zs = torch.empty(ncap, self.num_relations * _align4(self.num_features), **f32)
+                    width = _lib.load().igmc_raw_grad_count(C.byref(self._cmodel))
+                else:
+                    zs = torch.empty(L, ncap, NB * HID, **f32)
+                    width = self._cmodel.conv_param_count
+                ws.update(zsave=zs, dstate=torch.empty(L, ncap, HID, **f32),
+                          gpart=torch.zeros(B * max(cl, 1), width, **f32),
                           dhid=torch.empty(B, 128, **f32))
-            if len(self._ws) > 8:
-                self._ws.clear()
+            # never evicted: captured CUDA graphs hold raw pointers into these buffers (a handful of
+            # (capacity, batch size, mode) keys per run; a few MB each)
             self._ws[key] = ws
         return ws
+
+    # ---- pre-staged edge lists (igmc_stage_lists): built once per batch, off the model kernels' critical path ----
+    def stage_batch(self, batch, training=True, drop=None, slot=0):
+        """Build the list images of ``batch`` for the forward (and, when training, backward) kernel of its plan and
+        attach them to the batch.  ``drop`` must be the dropout descriptor the step will use (same seed source).
+        No-op for the generic plan."""
+        cl = self._plan(batch)
+        if cl <= 0:
+            batch._stage = None
+            return None
+        lib = _lib.load()
+        p = batch._priv
+        key = (p["node_cap"], batch.num_graphs, bool(training), cl, int(slot))
+        cache = self.__dict__.setdefault("_stage_ws", {})
+        st = cache.get(key)
+        if st is None:
+            dev = self.flat_params.device
+            st = {}
+            for name, bw in (("fwd", 0), ("bwd", 1)):
+                if bw and not training:
+                    continue
+                img = _lib.Stage()
+                _lib.check(lib.igmc_stage_plan(C.byref(self._cmodel), p["n_cap"], cl, bw, C.byref(img)),
+                           "igmc_stage_plan")
+                rows = batch.num_graphs * cl
+                t = dict(tab=torch.zeros(rows, img.tab_ints, dtype=torch.int32, device=dev),
+                         ent=torch.zeros(rows, img.lcap, dtype=torch.int32, device=dev))
+                img.tab, img.ent = t["tab"].data_ptr(), t["ent"].data_ptr()
+                if not bw:
+                    t["inv_deg"] = torch.ones(p["node_cap"], dtype=torch.float32, device=dev)
+                    img.inv_deg = t["inv_deg"].data_ptr()
+                st[name] = (img, t)
+            cache[key] = st
+        if drop is None:
+            drop = self.make_dropout(training)
+        d, keep = drop
+        adj_c, _ = batch.adjacency()
+        _lib.check(lib.igmc_stage_lists(C.byref(self._cmodel), p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(),
+                                        C.byref(adj_c), batch.num_graphs, p["n_cap"], C.byref(d), int(training),
+                                        C.byref(st["fwd"][0]), C.byref(st["bwd"][0]) if training else None,
+                                        batch._err.data_ptr(), _stream_ptr()), "igmc_stage_lists")
+        batch._stage = st
+        return st
+
+    @staticmethod
+    def _stage_arg(batch, name):
+        st = getattr(batch, "_stage", None)
+        if not st or name not in st:
+            return None
+        return C.byref(st[name][0])
 
     def _saved_struct(self, ws, ncap):
         return _lib.Saved(ws["states"].data_ptr(), _lib.ptr(ws.get("zsave")), ws["inv_deg"].data_ptr(),
@@ -304,7 +358,8 @@ class IGMC(nn.Module):
                                     batch.num_graphs, p["n_cap"], C.byref(d), int(training), C.byref(S),
                                     _lib.ptr(y), float(loss_scale), ws["dpred"].data_ptr() if y is not None else None,
                                     ws["sqerr"].data_ptr() if y is not None else None, ws["cluster"],
-                                    batch._err.data_ptr(), _stream_ptr()), "igmc_forward")
+                                    self._stage_arg(batch, "fwd"), batch._err.data_ptr(), _stream_ptr()),
+                   "igmc_forward")
         return ws["pred"], dict(ws=ws, S=S, train=bool(training))
 
     def _launch_backward(self, batch, drop, saved, dpred):
@@ -318,14 +373,16 @@ class IGMC(nn.Module):
                                      p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
                                      batch.num_graphs, p["n_cap"], C.byref(d), C.byref(saved["S"]),
                                      dpred.data_ptr(), ws["gpart"].data_ptr(), ws["dhid"].data_ptr(), ws["cluster"],
-                                     batch._err.data_ptr(), _stream_ptr()), "igmc_backward")
+                                     self._stage_arg(batch, "bwd"), batch._err.data_ptr(), _stream_ptr()),
+                   "igmc_backward")
 
     def _launch_grad_reduce(self, batch, saved, loss_scale, arr, with_loss=True):
         lib = _lib.load()
         ws = saved["ws"]
         _lib.check(lib.igmc_grad_reduce(C.byref(self._cmodel), self.flat_params.data_ptr(), batch.num_graphs,
                                         batch.num_graphs * max(ws["cluster"], 1),
-                                        ws["gpart"].data_ptr(), ws["dhid"].data_ptr(), ws["feat"].data_ptr(),
+                                        ws["gpart"].data_ptr(), 1 if ws["cluster"] > 0 else 0,
+                                        ws["dhid"].data_ptr(), ws["feat"].data_ptr(),
                                         ws["hid"].data_ptr(), saved["dpred_used"].data_ptr(),
                                         ws["sqerr"].data_ptr() if with_loss else None, float(loss_scale),
                                         float(arr), 1.0, self.flat_grad.data_ptr(),

@@ -76,9 +76,10 @@ class TrainEngine(object):
         self.sample_seed = int(sample_seed)
         self.graphs = {}
         self.eager_done = set()
-        # [idx(B) | sample_seed | drop_seed | global batch size]  per step, pinned ring + one device copy
-        self.stepbuf_dev = torch.zeros(self.B + 3, dtype=torch.int64, device=self.dev)
-        self.ring = [torch.zeros(self.B + 3, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+        # [idx(B) | sample_seed | drop_seed | global batch size | drop_seed of the NEXT step]  per step, pinned ring +
+        # one device copy (the next step's seed is what the list images of the batch being extracted are built with)
+        self.stepbuf_dev = torch.zeros(self.B + 4, dtype=torch.int64, device=self.dev)
+        self.ring = [torch.zeros(self.B + 4, dtype=torch.int64).pin_memory() for _ in range(self.RING)]
         self.ring_ev = [None] * self.RING
         self.ring_pos = 0
         self.lr_dev = torch.zeros(1, dtype=torch.float32, device=self.dev)
@@ -90,13 +91,23 @@ class TrainEngine(object):
     def sync_lr(self):
         self.lr_dev.fill_(float(self.opt.param_groups[0]["lr"]))
 
+    def drop_seed(self, step):
+        """dropout stream of optimisation step ``step`` on this rank (ranks draw independent masks)."""
+        return splitmix64(self.model.drop_seed + step * self.world + self.rank)
+
+    @property
+    def arr_local(self):
+        """the regulariser is added once per global batch: rank 0 carries it (every global batch gives rank 0 at
+        least one graph), so that the all-reduced gradient and the summed loss equal the single-process ones."""
+        return self.ARR if self.rank == 0 else 0.0
+
     # ---- the launches of one step, reading everything from stepbuf_dev ----------------------------
     def _launch(self, nb, G):
         B = self.B
         buf = self.stepbuf_dev
         if nb > 0:
             batch = self.dataset.extractor.extract(idx=buf[:nb], seed_dev=buf[B:B + 1], reuse=True)
-            loss = self.model.fused_step(batch, ARR=self.ARR / self.world, global_num_graphs=G,
+            loss = self.model.fused_step(batch, ARR=self.arr_local, global_num_graphs=G,
                                          seed_dev=buf[B + 1:B + 2])
         else:  # this rank got no graph of a short tail batch: contribute zeros
             self.model.flat_grad.zero_()
@@ -108,7 +119,7 @@ class TrainEngine(object):
 
     def _launch_static(self, idx, G):
         batch = self.dataset.extract_batch(idx)
-        loss = self.model.fused_step(batch, ARR=self.ARR / self.world, global_num_graphs=G)
+        loss = self.model.fused_step(batch, ARR=self.arr_local, global_num_graphs=G)
         if self.world > 1:
             dist.all_reduce(self.model.flat_grad)
         self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
@@ -124,8 +135,9 @@ class TrainEngine(object):
         nb = len(idx)
         host[:nb] = torch.as_tensor(idx, dtype=torch.int64)
         host[self.B] = _u64_as_i64(splitmix64(self.sample_seed + epoch))
-        host[self.B + 1] = _u64_as_i64(splitmix64(self.model.drop_seed + self.steps))
+        host[self.B + 1] = _u64_as_i64(self.drop_seed(self.steps))
         host[self.B + 2] = G
+        host[self.B + 3] = _u64_as_i64(self.drop_seed(self.steps + 1))
         self.stepbuf_dev.copy_(host, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record()
@@ -165,8 +177,11 @@ class TrainEngine(object):
             with torch.cuda.stream(self.side):
                 self.batches[slot ^ 1] = self.dataset.extractor.extract(idx=buf[:nb_next], seed_dev=buf[B:B + 1],
                                                                         reuse=True, slot=slot ^ 1)
+                # the next step's edge lists (after its dropout draws), staged for the model kernels' bulk loads
+                self.model.stage_batch(self.batches[slot ^ 1], True,
+                                       self.model.make_dropout(True, seed_dev=buf[B + 3:B + 4]), slot=slot ^ 1)
         if nb > 0:
-            loss = self.model.fused_step(self.batches[slot], ARR=self.ARR / self.world, global_num_graphs=G,
+            loss = self.model.fused_step(self.batches[slot], ARR=self.arr_local, global_num_graphs=G,
                                          seed_dev=buf[B + 1:B + 2])
         else:
             self.model.flat_grad.zero_()
@@ -190,6 +205,9 @@ class TrainEngine(object):
             self.batches[0] = self.dataset.extractor.extract(idx=self.stepbuf_dev[:nb],
                                                              seed_dev=self.stepbuf_dev[self.B:self.B + 1], reuse=True,
                                                              slot=0)
+            self.model.stage_batch(self.batches[0], True,
+                                   self.model.make_dropout(True, seed_dev=self.stepbuf_dev[self.B + 3:self.B + 4]),
+                                   slot=0)
         self.cur = (nb, G)
 
     def step_pipe(self, next_idx=None, epoch=0, next_G=None, staged=False):

@@ -175,7 +175,10 @@ typedef struct {
 /* Activations kept between forward and backward. */
 typedef struct {
   float* states;    /* [node_cap * 32*L]  concat_states (models.py:203) */
-  float* zsave;     /* [L * node_cap * zdim] saved aggregates (zdim = max(NB,R)*32), training only, NULL in eval */
+  float* zsave;     /* training only, NULL in eval.  cluster plans: [node_cap * R*in0p] 1/deg-scaled relation-space
+                     * aggregate of the one-hot input (layer 0 only, in0p = in_dim0 rounded up to 4; layers >= 1 take
+                     * their weight gradients from the backward's own aggregate and need nothing saved);
+                     * generic plan (cluster 0): [L * node_cap * NB*32] basis-space aggregates of every layer */
   float* inv_deg;   /* [node_cap] 1/max(kept in-degree,1) */
   float* feat;      /* [B * 2*32*L] target-user | target-item rows */
   float* hid;       /* [B * 128] relu(lin1) after dropout scaling */
@@ -188,6 +191,30 @@ typedef struct {
   const float* wprep; /* [L * 2 * 32*((R+1)*32+4)] per-step prepared weights (igmc_prep_weights), cluster plans only */
   long long* prof;    /* optional debug: [grid][32] clock64() stamps of the kernel phases (cluster plans), or NULL */
 } igmc_saved_t;
+
+/* Pre-staged edge lists of one batch for the cluster plans (igmc_stage_lists): per (graph, cluster rank) the
+ * compacted, kept (after this step's dropout_adj draws, models.py:193-198), pre-swizzled list entries of the rank's
+ * own nodes plus the segment tables the gather hands out work from - everything the model kernels otherwise rebuild
+ * in their prologues.  The kernels pull an image into shared memory with two bulk (TMA) copies.
+ * One image per direction: forward = in-lists, backward = out-lists. */
+typedef struct {
+  int32_t* tab;       /* [B*cluster][tab_ints] header (entries, segments, staged, own nodes) + segment tables */
+  uint32_t* ent;      /* [B*cluster][lcap] staged entries */
+  float* inv_deg;     /* [node_cap] 1/max(kept in-degree,1); forward image only (NULL in the backward image) */
+  int32_t tab_ints, lcap, chunk, cluster;   /* the consuming kernel's plan, see igmc_stage_plan */
+} igmc_stage_t;
+
+/* Shape of the image the forward (backward = 0) / backward (1) kernel of plan `cluster` expects for subgraphs of up
+ * to n_cap nodes: fills tab_ints, lcap, chunk, cluster of *img (pointers untouched).  Negative if the plan does not
+ * exist. */
+int igmc_stage_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, igmc_stage_t* img);
+
+/* Build the images of a prepared batch: `fwd` always, `bwd` when training != 0 (may be NULL otherwise).  The dropout
+ * descriptor must be the one the forward / backward of this step will be given (same seed).  Replaces, once per
+ * batch and off the critical path, the list staging of igmc_forward / igmc_backward. */
+int igmc_stage_lists(const igmc_model_t* M, const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A,
+                     int B, int n_cap, const igmc_dropout_t* D, int training, const igmc_stage_t* fwd,
+                     const igmc_stage_t* bwd, int* err, void* stream);
 
 /* W_r = sum_b att[r,b] basis[b] (and its transpose) for every layer, once per step, so that the
  * per-subgraph CTAs only copy them into shared memory.  Required before igmc_forward / igmc_backward with
@@ -209,23 +236,33 @@ int igmc_model_plan(const igmc_model_t* M, int n_cap, int cluster, int backward)
 int igmc_forward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                  const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                  const igmc_dropout_t* D, int training, const igmc_saved_t* S, const float* y,
-                 float loss_scale, float* dpred, float* sqerr, int cluster, int* err, void* stream);
+                 float loss_scale, float* dpred, float* sqerr, int cluster, const igmc_stage_t* stage, int* err,
+                 void* stream);
 
 /* Backward of igmc_forward given dpred [B] (gradient wrt the lin2 output).  Writes partial gradients of
- * the conv parameters, one row per CTA: gpart[B*max(cluster,1)][conv_param_count], and the readout
- * factors dhid [B*128]; igmc_grad_reduce turns them into the flat gradient.  Must use the same `cluster`
- * as the forward that produced S.  (autograd of models.py:190-217) */
+ * the conv parameters, one row per CTA, and the readout factors dhid [B*128]; igmc_grad_reduce turns them into the
+ * flat gradient.  Row layout: cluster 0 -> gpart[B][conv_param_count] in parameter layout; cluster > 0 ->
+ * gpart[B*cluster][igmc_raw_grad_count()] "raw" rows (per layer dW_r [R][in0p|32][32] | d root | d bias): the
+ * (att, basis) chain rule is linear and is applied once to the sum by igmc_grad_reduce.  Must use the same `cluster`
+ * as the forward that produced S.  `stage` (optional) = the backward image of igmc_stage_lists.
+ * (autograd of models.py:190-217) */
 int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
                   const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
                   const igmc_dropout_t* D, const igmc_saved_t* S, const float* dpred,
-                  float* gpart, float* dhid, int cluster, int* err, void* stream);
+                  float* gpart, float* dhid, int cluster, const igmc_stage_t* stage, int* err, void* stream);
 
-/* grad[p] = sum over gpart rows (conv) ; lin1/lin2 gradients from (dhid, feat, hid, dpred) ;
- * + ARR * d/dW sum_l sum_r ||W_{r+1}-W_r||^2 (train_eval.py:167-174).  Also writes
+/* floats per raw gradient row of the cluster plans (see igmc_backward) */
+int igmc_raw_grad_count(const igmc_model_t* M);
+
+/* grad[p] = sum over gpart rows (conv; `raw_rows` != 0: raw rows of the cluster plans, chain rule
+ * d basis[b] = sum_r att[r,b] dW_r, d att[r,b] = <dW_r, basis[b]> applied to the sum) ; lin1/lin2 gradients from
+ * (dhid, feat, hid, dpred) ; + ARR * d/dW sum_l sum_r ||W_{r+1}-W_r||^2 (train_eval.py:167-174).  Also writes
  * loss_out[0] = sum_g sqerr[g]*loss_scale + ARR*reg  when loss_out != NULL.  `reg_ws` is a zero-initialised
- * scratch of IGMC_MAX_LAYERS*256 + 1 floats (per-(layer,relation) regulariser values + an int ticket). */
+ * scratch of IGMC_REDUCE_WS_FLOATS floats (partial dot products / regulariser values + int tickets, re-armed by the
+ * kernel). */
+#define IGMC_REDUCE_WS_FLOATS (IGMC_MAX_LAYERS * 32 * 64 + IGMC_MAX_LAYERS * 32 + 64)
 int igmc_grad_reduce(const igmc_model_t* M, const float* params, int B, int gpart_rows, const float* gpart,
-                     const float* dhid, const float* feat, const float* hid, const float* dpred,
+                     int raw_rows, const float* dhid, const float* feat, const float* hid, const float* dpred,
                      const float* sqerr, float loss_scale, float arr, float grad_scale,
                      float* grad, float* loss_out, float* reg_ws, void* stream);
 

@@ -1,0 +1,18 @@
+#!/bin/bash
+# quick GPU iteration: full GPU suite, smoke, short headline bench, in-kernel phase timeline
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+T=${1:-r02}
+timeout 1200 python -m pytest tests -q -m gpu --tb=short --timeout=300 --timeout-method=thread -p no:cacheprovider -x 2>&1 | tail -25 | tee gpurun_out/${T}_pytest.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3
+timeout 400 python bench.py --steps 100 --warmup 10 --skip-cpu-baseline > gpurun_out/${T}_bench_1gpu.json 2> gpurun_out/${T}_bench_1gpu.err; echo "bench rc=$?"
+tail -3 gpurun_out/${T}_bench_1gpu.err
+timeout 200 python scripts/phase_profile.py > gpurun_out/${T}_phase_timeline.txt 2>&1; echo "phase rc=$?"
+python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${T}_bench_1gpu.json"))
+    print("value", round(d["value"], 1), "ms/step", round(d["ms_per_step"], 4), "e2e", round(d["e2e"]["value"], 1), d["roofline"]["kernel_ms"])
+except Exception as e:
+    print("bench ERR", e)
+PY

@@ -23,6 +23,8 @@ for plan in (2, 1):
         b = d.extract_batch(rng.choice(len(tu), B, replace=False))
         m._step += 1
         drop = m.make_dropout(True)
+        if os.environ.get("IGMC_NO_STAGE") != "1":
+            m.stage_batch(b, True, drop)     # list images, as the pipelined engine does on its side stream
         m._prof_buf.zero_()
         _, saved = m._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / B)
         torch.cuda.synchronize()
@@ -57,9 +59,9 @@ for plan in (2, 1):
             col = (a[:, i] - a[:, 0])[ok]
             print("  %-34s t=%7.1f us  +%6.1f   max=%7.1f" % (lab, col.mean() / 1965.0, (col.mean() - prev) / 1965.0, col.max() / 1965.0))
             prev = col.mean()
-    fl = {0: "start", 1: "init+stage lists"}
+    fl = {0: "start", 1: "init+lists"}
     for l in range(4):
-        fl.update({2 + 6 * l: "L%d weights copied" % l, 3 + 6 * l: "L%d gather done (warp0)" % l, 4 + 6 * l: "L%d gather synced" % l,
+        fl.update({2 + 6 * l: "L%d layer start" % l, 3 + 6 * l: "L%d gather done (warp0)" % l, 4 + 6 * l: "L%d gather synced" % l,
                    5 + 6 * l: "L%d mma done (warp0)" % l, 6 + 6 * l: "L%d mma synced" % l, 7 + 6 * l: "L%d cluster synced" % l})
     fl.update({39: "L1 w0 gather start", 49: "L1 w31 gather start", 40: "L1 w0 gather_segments done", 43: "L1 w31 gather_segments done", 46: "L1 w15 gather_segments done",
                41: "L1 w0 after sync", 44: "L1 w31 after sync", 42: "L1 w0 fold done", 45: "L1 w31 fold done"})
@@ -67,10 +69,10 @@ for plan in (2, 1):
     show2("forward", f, fl)
     print("  staging facts (fwd): staged=%s entries=%s segs=%s lcap=%s chunk=%s n_own=%s" % tuple(
         sorted(set(f[:, c].tolist()))[:6] for c in (60, 61, 62, 63, 59, 58)))
-    bl = {0: "start", 1: "stage+readout bwd"}
+    bl = {0: "start", 1: "lists+readout bwd"}
     for i, l in enumerate((3, 2, 1, 0)):
         sb = 2 + 8 * i
-        bl.update({sb: "L%d dpre+W ready" % l, sb + 5: "L%d dgrad gather done (warp0)" % l, sb + 6: "L%d dgrad gather synced" % l,
-                   sb + 1: "L%d dgrad mma done" % l, sb + 7: "L%d wgrad tile loaded" % l, sb + 2: "L%d wgrad done" % l,
-                   sb + 3: "L%d chain rule done" % l, sb + 4: "L%d cluster synced" % l})
+        bl.update({sb: "L%d dpre ready" % l, sb + 5: "L%d dgrad gather+fold done (warp0)" % l, sb + 6: "L%d dgrad gather synced" % l,
+                   sb + 1: "L%d dgrad mma done" % l, sb + 7: "L%d wgrad done (warp0)" % l, sb + 2: "L%d layer-0 wgrad done" % l,
+                   sb + 3: "L%d layer synced" % l, sb + 4: "L%d cluster synced" % l})
     show2("backward", bw, bl)

@@ -31,11 +31,16 @@ def test_build_info_and_plans():
     from igmc_b200.models import IGMC
     m = IGMC(4, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True)
     c = ctypes.byref(m._cmodel)
-    for n_cap, cl in ((202, 1), (202, 2), (202, 4), (402, 2), (402, 0), (202, 0)):
+    for n_cap, cl in ((202, 1), (202, 2), (202, 3), (202, 4), (402, 2), (402, 0), (202, 0)):
         f, b = lib.igmc_model_plan(c, n_cap, cl, 0), lib.igmc_model_plan(c, n_cap, cl, 1)
         assert 0 < f <= 227 * 1024 and 0 < b <= 227 * 1024, (n_cap, cl, f, b)
     assert lib.igmc_model_plan(c, 5000, 1, 0) < 0          # does not fit: refused, never silently clipped
-    assert lib.igmc_model_plan(c, 202, 3, 0) < 0           # unsupported cluster size
+    assert lib.igmc_model_plan(c, 202, 5, 0) < 0           # unsupported cluster size
+    # the list image of a plan: shape only (no device memory touched)
+    img = _lib.Stage()
+    assert lib.igmc_stage_plan(c, 202, 2, 1, ctypes.byref(img)) == 0
+    assert img.cluster == 2 and img.chunk % 16 == 0 and img.lcap % 4 == 0 and img.tab_ints % 4 == 0
+    assert lib.igmc_raw_grad_count(c) == 800 + 3 * 6176    # per layer (R+1)*inp*32 + 32 floats
     m30 = IGMC(4, latent_dim=[32] * 4, num_relations=30, num_bases=4, regression=True)
     assert lib.igmc_model_plan(ctypes.byref(m30._cmodel), 100, 2, 0) < 0   # relation-space plan needs R <= 12
     assert lib.igmc_model_plan(ctypes.byref(m30._cmodel), 100, 0, 0) > 0   # generic plan takes it
@@ -49,5 +54,6 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.ExtractWS) == 8 * P
     assert ctypes.sizeof(_lib.Adj) == 7 * P + 8
     assert ctypes.sizeof(_lib.Model) == 4 * (4 + 4 * 8 + 4 + 2 + 1 + 1)
+    assert ctypes.sizeof(_lib.Stage) == 3 * P + 16
     assert ctypes.sizeof(_lib.SortPool) == 4 * 19
     assert ctypes.sizeof(_lib.SortPoolSaved) == 10 * P

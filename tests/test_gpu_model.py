@@ -41,7 +41,7 @@ def _rmse(a, b):
     return float(torch.sqrt(torch.mean((a.double().cpu() - b.double().cpu()) ** 2)))
 
 
-@pytest.mark.parametrize("R,NB,mult,plan", [(5, 4, 1, 0), (5, 4, 1, 1), (5, 4, 1, 2), (5, 4, 1, 4), (10, 2, 1, 0),
+@pytest.mark.parametrize("R,NB,mult,plan", [(5, 4, 1, 0), (5, 4, 1, 1), (5, 4, 1, 2), (5, 4, 1, 3), (5, 4, 1, 4), (10, 2, 1, 0),
                                             (10, 2, 1, 2), (5, 4, 2, "auto"), (30, 4, 1, "auto")])
 def test_forward_eval_parity(R, NB, mult, plan):
     A, links, cv, ob = _oracle_batch(R=R)
@@ -70,7 +70,7 @@ def test_forward_on_extracted_batch_matches_foreign_batch():
     assert torch.equal(p1, p2)
 
 
-@pytest.mark.parametrize("R,NB,symmetric,plan", [(5, 4, True, 0), (5, 4, True, 1), (5, 4, True, 2), (5, 4, True, 4),
+@pytest.mark.parametrize("R,NB,symmetric,plan", [(5, 4, True, 0), (5, 4, True, 1), (5, 4, True, 2), (5, 4, True, 3), (5, 4, True, 4),
                                                  (10, 2, True, 0), (10, 2, True, 2), (5, 4, False, 0),
                                                  (5, 4, False, 2), (30, 4, True, "auto")])
 def test_train_forward_backward_parity(R, NB, symmetric, plan):
@@ -241,3 +241,38 @@ def test_full_size_train_step_parity(name, mnph, plan):
         gref = sd_ref[names[id(p)]].grad.reshape(-1)
         err = float((m.flat_grad[o:o + n].double().cpu() - gref).abs().max()) / (float(gref.abs().max()) + 1e-12)
         assert err <= 2e-4, (names[id(p)], err)
+
+
+@pytest.mark.parametrize("plan,adj_dropout,symmetric", [(1, 0.0, True), (2, 0.0, True), (2, 0.2, True), (3, 0.2, True),
+                                                        (4, 0.2, True), (2, 0.2, False), (1, 0.3, False)])
+def test_staged_list_images_equal_self_staged(plan, adj_dropout, symmetric):
+    """igmc_stage_lists + the kernels' bulk (TMA) loads of the list images give BIT-identical predictions, loss and
+    gradients to the kernels staging their own lists (same hash dropout draws), for extracted (symmetric) batches
+    and for foreign batches with separate out-lists."""
+    from igmc_b200.util_functions import MyDynamicDataset
+    A, (u, v, lab), cv, ob = _oracle_batch(B=12)
+    ref, m = _models(adj_dropout=adj_dropout, plan=plan)
+    m.train()
+    if symmetric:
+        ds = MyDynamicDataset(None, A, (u, v), lab, 1, 1.0, 30, None, None, cv, seed=5)
+        b = ds.extract_batch(np.arange(12))
+    else:
+        keep = np.random.default_rng(1).random(ob["edge_index"].shape[1]) > 0.3
+        b = _gpu_batch(dict(ob, edge_index=ob["edge_index"][:, keep], edge_type=ob["edge_type"][keep]))
+    hk = torch.rand(12, 128, generator=torch.Generator().manual_seed(2)) > 0.5
+    m._step = 20
+    loss0 = float(m.fused_step(b, ARR=0.001, hidden_keep=hk))
+    b.check()
+    ws = next(iter(v for k, v in m._ws.items() if k[2]))
+    g0, p0 = m.flat_grad.clone(), ws["pred"].clone()
+    m._step = 21                                   # fused_step draws with the seed of step 21
+    st = m.stage_batch(b, True, m.make_dropout(True))
+    assert st is not None and int(st["fwd"][1]["tab"][:, 3].sum()) == int(b._priv["node_ptr"][-1])   # own nodes add up
+    m._step = 20
+    m.flat_grad.zero_()
+    loss1 = float(m.fused_step(b, ARR=0.001, hidden_keep=hk))
+    b.check()
+    assert torch.equal(ws["pred"], p0) and loss1 == loss0
+    assert torch.equal(m.flat_grad, g0)
+    assert float(g0.abs().max()) > 0
+    b._stage = None

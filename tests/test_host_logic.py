@@ -95,11 +95,12 @@ def _dp_worker(rank, world, port, out):
     mine, Gs = shard_batches(perm, B, rank, world)[0]
     torch.manual_seed(0)
     model = pyg_restated.IGMCRef(4, (32, 32, 32, 32), 5, 4, 0.0).double().eval()
-    # this rank's contribution: sum over its graphs of (out-y)^2 / G + ARR/world * reg  (what fused_step computes)
+    # this rank's contribution: sum over its graphs of (out-y)^2 / G, + ARR * reg on rank 0 only (TrainEngine.arr_local:
+    # the regulariser enters once per global batch, also when a short tail batch leaves other ranks empty)
     ob = extract_np.extract_batch(g, u[mine], v[mine], lab[mine], cv, 1, 1.0, 20, pair_ids=mine)
     tb = pyg_restated.to_torch_batch(ob, torch.float64)
     pred = model(tb["x"], tb["edge_index"], tb["edge_type"])
-    loss = ((pred - tb["y"]) ** 2).sum() / Gs + 0.001 / world * pyg_restated.arr_regulariser(model)
+    loss = ((pred - tb["y"]) ** 2).sum() / Gs + (0.001 if rank == 0 else 0.0) * pyg_restated.arr_regulariser(model)
     loss.backward()
     flat = torch.cat([p.grad.reshape(-1) for p in model.parameters()])
     dist.all_reduce(flat)                                    # the one collective of a step
@@ -116,7 +117,7 @@ def _dp_worker(rank, world, port, out):
 
 def test_data_parallel_gradient_identity_gloo():
     """world_size 2 on CPU (gloo): all-reduce(SUM) of per-rank gradients with the loss scaled by the GLOBAL
-    batch and ARR/world equals the single-process gradient of the concatenated batch."""
+    batch and ARR on rank 0 equals the single-process gradient of the concatenated batch."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
