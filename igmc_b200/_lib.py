@@ -85,6 +85,14 @@ class Stage(C.Structure):
                 ("chunk", C.c_int32), ("cluster", C.c_int32)]
 
 
+MAX_RANKS = 8
+
+
+class Comm(C.Structure):
+    _fields_ = [("grad", vp * MAX_RANKS), ("flag", vp * MAX_RANKS), ("state", vp), ("world", C.c_int32),
+                ("rank", C.c_int32), ("stride", C.c_int32), ("pad_", C.c_int32)]
+
+
 class SortPool(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("k", "width", "state_stride", "c1", "c2", "kw2", "t1", "t2", "dense_dim",
                                          "off_conv1_w", "off_conv1_b", "off_conv2_w", "off_conv2_b", "off_lin1_w",
@@ -114,6 +122,13 @@ _SIGS = {
                          C.c_float, vp, vp, vp, vp],
     "igmc_adam_step": [vp, vp, vp, vp, vp, C.c_int, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_float,
                        C.c_float, vp, vp, C.c_float, vp],
+    "igmc_reduce_update": [C.POINTER(Model), vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp, C.c_float, C.c_float,
+                           C.POINTER(Comm), vp, vp, vp, C.c_float, vp, C.c_float, C.c_float, C.c_float, C.c_float,
+                           C.c_float, vp, vp, C.c_float, vp, vp, vp],
+    "igmc_comm_alloc": [C.c_int64, C.POINTER(C.c_void_p), C.c_char_p],
+    "igmc_comm_open": [C.c_char_p, C.POINTER(C.c_void_p)],
+    "igmc_comm_close": [vp],
+    "igmc_comm_free": [vp],
     "igmc_prep_weights": [C.POINTER(Model), vp, vp, vp],
     "igmc_build_info": [],
     "igmc_model_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int],

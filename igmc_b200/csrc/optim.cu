@@ -3,6 +3,9 @@
 // Replaces autograd's accumulation + `loss += ARR * sum((w[1:]-w[:-1])**2)` (train_eval.py:167-174)
 // + `torch.optim.Adam.step` (train_eval.py:54,177) with TWO launches on the flat parameter bucket, which is
 // also what the one NCCL all-reduce per step operates on.
+#include <cmath>
+#include <cstring>
+
 #include "common.cuh"
 #include "../../include/igmc_b200.h"
 
@@ -167,54 +170,71 @@ constexpr int RW_REGP = IGMC_MAX_LAYERS * 32 * 64;          // [L][32] partial r
 constexpr int RW_REGL = RW_REGP + IGMC_MAX_LAYERS * 32;     // [L] per-layer regulariser
 constexpr int RW_TICK = RW_REGL + IGMC_MAX_LAYERS;          // ints: [L] layer tickets, [1] global ticket
 
-__global__ void __launch_bounds__(256)
-k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int rows, int NA,
-                  const float* __restrict__ gpart, const float* __restrict__ dhid, const float* __restrict__ feat,
-                  const float* __restrict__ hid, const float* __restrict__ dpred, const float* __restrict__ sqerr,
-                  float loss_scale, float arr, float grad_scale, float* __restrict__ grad, float* __restrict__ loss_out,
-                  float* __restrict__ reg_ws) {
+// per-warp partial sums of NC columns of the raw rows g == warp (mod 8) -> ps[c][warp][lane]; fixed order
+template <int NCT, int UR>
+__device__ __forceinline__ void sum_rows(const float* __restrict__ gp, int rows, int RC, int R, int inp, int k, int NC,
+                                         int warp, int lane, float (*ps)[8][HID]) {
+  int off[NCT];
+  float acc[NCT];
+#pragma unroll
+  for (int c = 0; c < NCT; ++c) {
+    off[c] = c < NC ? (c <= R ? (c * inp + k) * HID : (R + 1) * inp * HID) : 0;
+    acc[c] = 0.f;
+  }
+  int g0 = warp;
+  for (; g0 + 8 * (UR - 1) < rows; g0 += 8 * UR) {   // full batches: no guards, every load independent
+    float v[UR][NCT];
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const float* gr = gp + (size_t)(g0 + 8 * u) * RC;
+#pragma unroll
+      for (int c = 0; c < NCT; ++c) v[u][c] = __ldcg(gr + off[c]);
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u)
+#pragma unroll
+      for (int c = 0; c < NCT; ++c) acc[c] += v[u][c];
+  }
+  for (; g0 < rows; g0 += 8) {                        // tail rows
+    float v[NCT];
+    const float* gr = gp + (size_t)g0 * RC;
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) v[c] = __ldcg(gr + off[c]);
+#pragma unroll
+    for (int c = 0; c < NCT; ++c) acc[c] += v[c];
+  }
+#pragma unroll
+  for (int c = 0; c < NCT; ++c)
+    if (c < NC) ps[c][warp][lane] = acc[c];
+}
+
+__device__ __forceinline__ void reduce_raw_block(const igmc_model_t& M, const float* __restrict__ params, int B, int rows,
+                                                 int NA, const float* __restrict__ gpart, const float* __restrict__ dhid,
+                                                 const float* __restrict__ feat, const float* __restrict__ hid,
+                                                 const float* __restrict__ dpred, const float* __restrict__ sqerr,
+                                                 float loss_scale, float arr, float grad_scale, float* __restrict__ grad,
+                                                 float* __restrict__ loss_out, float* __restrict__ reg_ws) {
   const int R = M.num_relations, NB = M.num_bases, L = M.num_layers, in0 = M.in_dim0;
   const int RC = igmc_raw_count(R, in0, L), F = 2 * HID * L;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if ((int)blockIdx.x >= NA) {
-    const int p = ((int)blockIdx.x - NA) * 256 + tid;
+  if ((int)blockIdx.x >= NA) {   // readout parameters (lin1 / lin2) from the saved factors
+    const int p = M.conv_param_count + ((int)blockIdx.x - NA) * 256 + tid;
     if (p >= M.param_count) return;
     float s = 0.f;
     bool write = false;
-    if (p < M.conv_param_count) {
-      for (int l = 0; l < L; ++l) {
-        const int in = l == 0 ? in0 : HID, inp = (in + 3) & ~3;
-        const size_t ro = (size_t)igmc_raw_off(R, in0, l);
-        const int qr = p - M.off_root[l], qb = p - M.off_bias[l];
-        size_t src = 0;
-        if (qr >= 0 && qr < in * HID) { src = ro + (size_t)R * inp * HID + qr; write = true; }
-        else if (qb >= 0 && qb < HID) { src = ro + (size_t)(R + 1) * inp * HID + qb; write = true; }
-        if (write) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // four interleaved chains, fixed combination order
-          int g = 0;
-          for (; g + 4 <= rows; g += 4) {
-            s0 += gpart[(size_t)g * RC + src];
-            s1 += gpart[(size_t)(g + 1) * RC + src];
-            s2 += gpart[(size_t)(g + 2) * RC + src];
-            s3 += gpart[(size_t)(g + 3) * RC + src];
-          }
-          for (; g < rows; ++g) s0 += gpart[(size_t)g * RC + src];
-          s = (s0 + s1) + (s2 + s3);
-          break;
-        }
-      }
-    } else if (M.readout != 0) {
-      // readout parameters belong to the external readout's gradient kernel
-    } else if (p >= M.off_lin1_w && p < M.off_lin1_w + L1O * F) {
+    if (p >= M.off_lin1_w && p < M.off_lin1_w + L1O * F) {
       const int q = p - M.off_lin1_w, o = q / F, i = q - o * F;      // lin1.weight[o][i]
+#pragma unroll 10
       for (int g = 0; g < B; ++g) s = fmaf(dhid[(size_t)g * L1O + o], feat[(size_t)g * F + i], s);
       write = true;
     } else if (p >= M.off_lin1_b && p < M.off_lin1_b + L1O) {
       const int o = p - M.off_lin1_b;
+#pragma unroll 10
       for (int g = 0; g < B; ++g) s += dhid[(size_t)g * L1O + o];
       write = true;
     } else if (p >= M.off_lin2_w && p < M.off_lin2_w + L1O) {
       const int o = p - M.off_lin2_w;
+#pragma unroll 10
       for (int g = 0; g < B; ++g) s = fmaf(dpred[g], hid[(size_t)g * L1O + o], s);
       write = true;
     } else if (p == M.off_lin2_b) {
@@ -224,43 +244,45 @@ k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int r
     if (write) grad[p] = s * grad_scale;
     return;
   }
-  // ---- block (l, k) ----
+  // ---- block (l, k): row k of dW_0..dW_{R-1} and of d root; block (l, 0) also d bias ----
   int l = 0, k = (int)blockIdx.x;
   if (k >= in0) { l = 1 + (k - in0) / HID; k = (k - in0) % HID; }
   const int in = l == 0 ? in0 : HID, inp = (in + 3) & ~3;
-  __shared__ float att[IGMC_MAX_BASES * 16];          // [R][NB], R <= 12
+  constexpr int MAXC = 14;                            // R <= 12 relation rows + root + bias
+  __shared__ float att[IGMC_MAX_BASES * 16];          // [R][NB]
   __shared__ float bs[IGMC_MAX_BASES][HID];           // basis[b][k][:]
-  __shared__ float ps[12][8][HID];                    // per-warp partial row sums
+  __shared__ float ps[MAXC][8][HID];                  // per-warp partial row sums
   __shared__ float dWs[12][HID];
   __shared__ float Wc[12][HID];
   __shared__ float red[8];
   __shared__ int s_last;
   for (int i = tid; i < R * NB; i += 256) att[i] = params[M.off_att[l] + i];
   for (int i = tid; i < NB * HID; i += 256) bs[i >> 5][i & 31] = params[M.off_basis[l] + ((i >> 5) * in + k) * HID + (i & 31)];
+  const int NC = R + 1 + (k == 0 ? 1 : 0);
   {
-    const float* gp = gpart + (size_t)igmc_raw_off(R, in0, l) + (size_t)k * HID + lane;
-    for (int r = 0; r < R; ++r) {
-      const float* gr = gp + (size_t)r * inp * HID;
-      float s0 = 0.f, s1 = 0.f;
-      int g = warp;
-      for (; g + 8 < rows; g += 16) {
-        s0 += gr[(size_t)g * RC];
-        s1 += gr[(size_t)(g + 8) * RC];
-      }
-      if (g < rows) s0 += gr[(size_t)g * RC];
-      ps[r][warp][lane] = s0 + s1;
-    }
+    // column c of this block inside a raw row: c <= R: row k of dW_c / d root; c == R + 1: d bias.
+    // warp w sums the partial rows g == w (mod 8); loads are issued in batches (UR rows x NCT columns in flight per
+    // thread) BEFORE any of them is consumed - the row sums are L2-latency bound
+    const float* gp = gpart + (size_t)igmc_raw_off(R, in0, l) + lane;
+    if (NC <= 7) sum_rows<7, 4>(gp, rows, RC, R, inp, k, NC, warp, lane, ps);
+    else sum_rows<14, 2>(gp, rows, RC, R, inp, k, NC, warp, lane, ps);
   }
   __syncthreads();
-  for (int t = tid; t < R * HID; t += 256) {
-    const int r = t >> 5, j = t & 31;
+  for (int t = tid; t < NC * HID; t += 256) {
+    const int c = t >> 5, j = t & 31;
     float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += ps[r][w][j];
-    dWs[r][j] = s;
-    float wv = 0.f;
-    for (int b = 0; b < NB; ++b) wv = fmaf(att[r * NB + b], bs[b][j], wv);
-    Wc[r][j] = wv;
+    for (int w = 0; w < 8; ++w) s += ps[c][w][j];
+    if (c < R) {
+      dWs[c][j] = s;
+      float wv = 0.f;
+      for (int b = 0; b < NB; ++b) wv = fmaf(att[c * NB + b], bs[b][j], wv);
+      Wc[c][j] = wv;
+    } else if (c == R) {
+      grad[M.off_root[l] + k * HID + j] = s * grad_scale;
+    } else {
+      grad[M.off_bias[l] + j] = s * grad_scale;
+    }
   }
   __syncthreads();
   float pair_sum = 0.f;
@@ -303,28 +325,138 @@ k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int r
   }
   __syncthreads();
   if (!s_last) return;
-  // ---- last block of layer l: d att[l] and the layer's regulariser value, summed over k in order ----
+  // ---- last block of layer l: d att[l] and the layer's regulariser value (warp per value, lane = k; the shuffle tree
+  //      fixes the order) ----
   __threadfence();
-  for (int pr = tid; pr < R * NB; pr += 256) {
-    float s = 0.f;
-    for (int kk = 0; kk < in; ++kk) s += __ldcg(reg_ws + RW_ATT + ((size_t)l * 32 + kk) * 64 + pr);
-    grad[M.off_att[l] + pr] = s * grad_scale;
+  for (int pr = warp; pr < R * NB + 1; pr += 8) {
+    const float* src = pr < R * NB ? reg_ws + RW_ATT + (size_t)l * 32 * 64 + pr : reg_ws + RW_REGP + l * 32;
+    const int strd = pr < R * NB ? 64 : 1;
+    const float s = warp_sum_f(lane < in ? __ldcg(src + (size_t)lane * strd) : 0.f);
+    if (lane == 0) {
+      if (pr < R * NB) grad[M.off_att[l] + pr] = s * grad_scale;
+      else reg_ws[RW_REGL + l] = s;
+    }
   }
+  __syncthreads();
   if (tid == 0) {
-    float s = 0.f;
-    for (int kk = 0; kk < in; ++kk) s += __ldcg(reg_ws + RW_REGP + l * 32 + kk);
-    reg_ws[RW_REGL + l] = s;
     tick[l] = 0;   // re-arm
     __threadfence();
-    if (atomicAdd(&tick[IGMC_MAX_LAYERS], 1) == L - 1) {   // last layer to finish: the loss
-      __threadfence();
-      float reg = 0.f;
-      for (int q = 0; q < L; ++q) reg += __ldcg(reg_ws + RW_REGL + q);
-      float mse = 0.f;
-      if (sqerr)
-        for (int g = 0; g < B; ++g) mse += sqerr[g];
-      if (loss_out) loss_out[0] = mse * loss_scale + arr * reg;
-      tick[IGMC_MAX_LAYERS] = 0;
+    s_last = (atomicAdd(&tick[IGMC_MAX_LAYERS], 1) == L - 1);
+  }
+  __syncthreads();
+  if (!s_last || warp != 0) return;
+  // last layer to finish: the loss (one warp; lane-strided partial sums + shuffle tree)
+  __threadfence();
+  float reg = lane < L ? __ldcg(reg_ws + RW_REGL + lane) : 0.f;
+  reg = warp_sum_f(reg);
+  float mse = 0.f;
+  if (sqerr)
+    for (int g = lane; g < B; g += 32) mse += sqerr[g];
+  mse = warp_sum_f(mse);
+  if (lane == 0) {
+    if (loss_out) loss_out[0] = mse * loss_scale + arr * reg;
+    tick[IGMC_MAX_LAYERS] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int rows, int NA,
+                  const float* __restrict__ gpart, const float* __restrict__ dhid, const float* __restrict__ feat,
+                  const float* __restrict__ hid, const float* __restrict__ dpred, const float* __restrict__ sqerr,
+                  float loss_scale, float arr, float grad_scale, float* __restrict__ grad, float* __restrict__ loss_out,
+                  float* __restrict__ reg_ws) {
+  reduce_raw_block(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, grad_scale, grad,
+                   loss_out, reg_ws);
+}
+
+// ---- system-scope flags for the peer exchange ----------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// ONE launch for  gradient assembly (+ARR)  ->  data-parallel all-reduce  ->  Adam:
+//   phase 1  every block assembles its part of this rank's gradient into the rank's exchange buffer (parity t & 1)
+//   phase 2  grid barrier; the last block publishes "step t ready" to every peer's flag array (st.release.sys over
+//            NVLink); every block then waits until all ranks (itself included) have published step t
+//   phase 3  one-shot all-reduce: each thread sums its elements over the ranks' buffers in rank order (peer loads
+//            through NVLink / NVSwitch; identical order on every rank -> bit-identical parameters everywhere) and
+//            applies the torch-Adam update
+// Two parities are enough: a rank overwrites parity p in step t + 2 only after it has seen every peer's flag t + 1,
+// which a peer raises after its step-t kernel (and thus its reads of parity p) has finished.
+// The grid (<= 300 blocks of 256 threads) is always co-resident, so spinning inside the grid is safe.
+__global__ void __launch_bounds__(256)
+k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int rows, int NA,
+                        const float* __restrict__ gpart, const float* __restrict__ dhid, const float* __restrict__ feat,
+                        const float* __restrict__ hid, const float* __restrict__ dpred, const float* __restrict__ sqerr,
+                        float loss_scale, float arr, igmc_comm_t C, float* __restrict__ exp_avg,
+                        float* __restrict__ exp_avg_sq, int64_t* __restrict__ step_count, float lr_val,
+                        const float* __restrict__ lr_dev, float b1, float b2, double log_b1, double log_b2, float eps,
+                        float wd, float grad_mul, float* __restrict__ loss_out, float* __restrict__ loss_acc,
+                        float loss_weight, float* __restrict__ reg_ws, float* __restrict__ grad_copy) {
+  const int tid = threadIdx.x;
+  const int64_t t64 = C.state[0] + 1;               // the exchange step this launch executes
+  const int t = (int)t64;
+  const int64_t step_i = step_count[0] + 1;
+  __shared__ float s_bc[2];
+  if (tid >= 254) {   // bias corrections 1 - beta^step (double, off the critical path: before the gradient assembly)
+    const double step = (double)step_i;
+    s_bc[tid - 254] = (float)(1.0 - exp(step * (tid == 255 ? log_b2 : log_b1)));
+  }
+  float* gl = C.grad[C.rank] + (size_t)(t & 1) * C.stride;
+  reduce_raw_block(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, 1.0f, gl, loss_out,
+                   reg_ws);
+  int* tick = reinterpret_cast<int*>(C.state + 1);  // [0] phase-1 ticket, [1] phase-3 ticket
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence_system();
+    if (atomicAdd(&tick[0], 1) == (int)gridDim.x - 1) {
+      tick[0] = 0;
+      __threadfence_system();
+      for (int r = 0; r < C.world; ++r) st_release_sys(C.flag[r] + C.rank, t);   // includes the own flag
+    }
+    for (int r = 0; r < C.world; ++r)
+      while (ld_acquire_sys(C.flag[C.rank] + r) - t < 0) {}
+  }
+  __syncthreads();
+  const float lr = lr_dev ? *lr_dev : lr_val;
+  const float bc1 = s_bc[0], bc2 = s_bc[1];
+  const size_t poff = (size_t)(t & 1) * C.stride;
+  for (int i = blockIdx.x * 256 + tid; i < M.param_count; i += gridDim.x * 256) {
+    float gv[IGMC_MAX_RANKS];
+#pragma unroll
+    for (int r = 0; r < IGMC_MAX_RANKS; ++r) gv[r] = r < C.world ? ld_relaxed_sys(C.grad[r] + poff + i) : 0.f;
+    float g = 0.f;
+#pragma unroll
+    for (int r = 0; r < IGMC_MAX_RANKS; ++r) g += gv[r];   // rank order; absent ranks add +0
+    if (grad_copy) grad_copy[i] = g;
+    g *= grad_mul;
+    const float p = params[i];
+    if (wd != 0.f) g = fmaf(wd, p, g);
+    const float mi = b1 * exp_avg[i] + (1.f - b1) * g;
+    const float vi = b2 * exp_avg_sq[i] + (1.f - b2) * g * g;
+    exp_avg[i] = mi;
+    exp_avg_sq[i] = vi;
+    const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
+    params[i] = p - (lr / bc1) * (mi / denom);
+  }
+  if (blockIdx.x == 0 && tid == 0 && loss_acc && loss_out) loss_acc[0] += __ldcg(loss_out) * loss_weight;
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&tick[1], 1) == (int)gridDim.x - 1) {
+      tick[1] = 0;
+      step_count[0] = step_i;
+      C.state[0] = t64;
     }
   }
 }
@@ -332,17 +464,21 @@ k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int r
 // torch.optim.Adam step; the last block to finish increments the device-side step counter.
 __global__ void k_adam(float* __restrict__ params, const float* __restrict__ grad, float* __restrict__ m,
                        float* __restrict__ v, int64_t* __restrict__ step_count, int* __restrict__ ticket, int n,
-                       float lr_val, const float* __restrict__ lr_dev, float b1, float b2, float eps, float wd,
-                       float grad_mul, const float* __restrict__ loss_in, float* __restrict__ loss_acc,
-                       float loss_weight) {
+                       float lr_val, const float* __restrict__ lr_dev, float b1, float b2, double log_b1, double log_b2,
+                       float eps, float wd, float grad_mul, const float* __restrict__ loss_in,
+                       float* __restrict__ loss_acc, float loss_weight) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0 && loss_acc) loss_acc[0] += loss_in[0] * loss_weight;   // epoch loss bookkeeping (train_eval.py:176)
   const int64_t step_i = step_count[0] + 1;
+  __shared__ float s_bc[2];
+  if (threadIdx.x < 2) {   // bias corrections 1 - beta^step in double, once per block (log beta comes from the host)
+    const double step = (double)step_i;
+    s_bc[threadIdx.x] = (float)(1.0 - exp(step * (threadIdx.x ? log_b2 : log_b1)));
+  }
+  __syncthreads();
   if (i < n) {
     const float lr = lr_dev ? *lr_dev : lr_val;
-    const double step = (double)step_i;
-    const float bc1 = (float)(1.0 - pow((double)b1, step));
-    const float bc2 = (float)(1.0 - pow((double)b2, step));
+    const float bc1 = s_bc[0], bc2 = s_bc[1];
     float g = grad[i] * grad_mul;
     const float p = params[i];
     if (wd != 0.f) g = fmaf(wd, p, g);
@@ -375,7 +511,8 @@ extern "C" int igmc_grad_reduce(const igmc_model_t* M, const float* params, int 
     if (!reg_ws) return -18;
     if (M->num_relations > 12) return -16;
     const int NA = M->in_dim0 + (M->num_layers - 1) * HID;
-    k_grad_reduce_raw<<<NA + PB, 256, 0, st>>>(*M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr,
+    const int PBr = M->readout != 0 ? 0 : (M->param_count - M->conv_param_count + 255) / 256;
+    k_grad_reduce_raw<<<NA + PBr, 256, 0, st>>>(*M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr,
                                                loss_scale, arr, grad_scale, grad, loss_out, reg_ws);
     IGMC_CUDA_CHECK_LAUNCH();
     return 0;
@@ -401,9 +538,70 @@ extern "C" int igmc_adam_step(float* params, const float* grad, float* exp_avg, 
   // step_count points at [int64 step | int32 ticket]: the word after the counter is the kernel's completion ticket
   int* ticket = reinterpret_cast<int*>(step_count + 1);
   k_adam<<<(n + 255) / 256, 256, 0, st>>>(params, grad, exp_avg, exp_avg_sq, step_count, ticket, n, lr, lr_dev, beta1,
-                                          beta2, eps, weight_decay, grad_mul, loss_in, loss_acc, loss_weight);
+                                          beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,
+                                          loss_in, loss_acc, loss_weight);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, int gpart_rows, const float* gpart,
+                                  const float* dhid, const float* feat, const float* hid, const float* dpred,
+                                  const float* sqerr, float loss_scale, float arr, const igmc_comm_t* comm,
+                                  float* exp_avg, float* exp_avg_sq, int64_t* step_count, float lr, const float* lr_dev,
+                                  float beta1, float beta2, float eps, float weight_decay, float grad_mul,
+                                  float* loss_out, float* loss_acc, float loss_weight, float* reg_ws, float* grad_copy,
+                                  void* stream) {
+  if (!comm || !reg_ws || comm->world < 1 || comm->world > IGMC_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
+    return -20;
+  if (comm->stride < M->param_count || !comm->state) return -20;
+  for (int r = 0; r < comm->world; ++r)
+    if (!comm->grad[r] || !comm->flag[r]) return -20;
+  if (M->num_relations > 12) return -16;
+  if (M->readout != 0) return -16;   // external readouts write their own gradient slice: use the separate kernels
+  const int NA = M->in_dim0 + (M->num_layers - 1) * HID;
+  const int PBr = (M->param_count - M->conv_param_count + 255) / 256;
+  k_reduce_allreduce_adam<<<NA + PBr, 256, 0, (cudaStream_t)stream>>>(
+      *M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, *comm, exp_avg, exp_avg_sq,
+      step_count, lr, lr_dev, beta1, beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,
+      loss_out, loss_acc, loss_weight, reg_ws, grad_copy);
+  IGMC_CUDA_CHECK_LAUNCH();
+  return 0;
+}
+
+// ---- exchange buffers: device memory every rank of the node maps (CUDA IPC); NCCL / gloo only carry the 64-byte
+// handles once at start-up ----
+extern "C" int igmc_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64) {
+  if (bytes <= 0 || !dev_ptr || !handle64) return -20;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, (size_t)bytes);
+  if (e != cudaSuccess) return (int)e + 1000;
+  e = cudaMemset(p, 0, (size_t)bytes);
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  cudaIpcMemHandle_t h;
+  if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return (int)e + 1000; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  memcpy(handle64, &h, 64);
+  *dev_ptr = p;
+  return 0;
+}
+extern "C" int igmc_comm_open(const unsigned char* handle64, void** dev_ptr) {
+  if (!handle64 || !dev_ptr) return -20;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, 64);
+  void* p = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return (int)e + 1000;
+  *dev_ptr = p;
+  return 0;
+}
+extern "C" int igmc_comm_close(void* peer_ptr) {
+  cudaError_t e = cudaIpcCloseMemHandle(peer_ptr);
+  return e == cudaSuccess ? 0 : (int)e + 1000;
+}
+extern "C" int igmc_comm_free(void* dev_ptr) {
+  cudaError_t e = cudaFree(dev_ptr);
+  return e == cudaSuccess ? 0 : (int)e + 1000;
 }
 
 extern "C" int igmc_build_info(void) {

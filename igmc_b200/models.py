@@ -204,7 +204,8 @@ class IGMC(nn.Module):
         self.lin2.reset_parameters()
 
     # ---- kernel launches ---------------------------------------------------------------------------------
-    kernel_plan = "auto"   # "auto" | 0 (generic kernels) | 1 | 2 | 4 (relation-space kernels, CTAs per subgraph)
+    kernel_plan = "auto"   # "auto" | 0 (generic kernels) | 1 | 2 | 3 | 4 (relation-space kernels, CTAs per subgraph)
+    hidden_dropout_p = 0.5   # F.dropout(x, p=0.5) before lin2 (models.py:212)
     NUM_SMS = 148
 
     def _plan(self, batch):
@@ -325,7 +326,7 @@ class IGMC(nn.Module):
         """dropout descriptor of one step (+ the tensors it references, to keep them alive)."""
         d = _lib.Dropout()
         d.adj_dropout = float(self.adj_dropout) if training else 0.0
-        d.hidden_dropout = 0.5 if training else 0.0
+        d.hidden_dropout = float(self.hidden_dropout_p) if training else 0.0
         if seed is None:
             seed = splitmix64(self.drop_seed + self._step)
         d.seed = int(seed) & ((1 << 64) - 1)
@@ -408,6 +409,21 @@ class IGMC(nn.Module):
             return _IGMCFunction.apply(self, batch, self.training, drop, *params)
         out, _ = self._launch_forward(batch, False if not self.training else True, drop)
         return out.clone()
+
+    def forward_backward(self, batch, global_num_graphs=None, edge_keep=None, hidden_keep=None, seed_dev=None):
+        """prep + forward + loss + backward of one training step WITHOUT the gradient assembly: leaves the raw partial
+        rows / readout factors in the workspace for ``FusedAdam.reduce_update`` (or ``_launch_grad_reduce``)."""
+        self._step += 1
+        drop = self.make_dropout(True, edge_keep, hidden_keep, seed_dev=seed_dev)
+        G = batch.num_graphs if global_num_graphs is None else int(global_num_graphs)
+        out, saved = self._launch_forward(batch, True, drop, y=batch.y, loss_scale=1.0 / G)
+        self._launch_backward(batch, drop, saved, saved["ws"]["dpred"])
+        return saved
+
+    def fused_update_ok(self, batch):
+        """the one-kernel reduce -> all-reduce -> Adam path needs raw partial rows (cluster plans) and the IGMC
+        readout (an external readout writes its own gradient slice)."""
+        return self._cmodel.readout == 0 and self._plan(batch) > 0
 
     def fused_step(self, batch, ARR=0.0, global_num_graphs=None, edge_keep=None, hidden_keep=None,
                    seed_dev=None):
@@ -629,6 +645,27 @@ class FusedAdam(torch.optim.Optimizer):
                                       float(g["betas"][1]), float(g["eps"]), float(g["weight_decay"]),
                                       float(grad_mul), _lib.ptr(loss_in), _lib.ptr(loss_acc) if loss_in is not None else None,
                                       float(loss_weight), _stream_ptr()), "igmc_adam_step")
+
+    @torch.no_grad()
+    def reduce_update(self, exchange, ws, B, rows, loss_scale, arr, lr_dev=None, loss_acc=None, loss_weight=0.0,
+                      grad_copy=None):
+        """gradient assembly (+ARR) -> one-shot all-reduce over the ranks of ``exchange`` -> Adam, ONE kernel
+        (igmc_reduce_update).  ``ws`` is the model workspace ``forward_backward`` filled (``B`` graphs, ``rows`` raw
+        partial rows; both 0 for a rank that holds no graph of a short tail batch)."""
+        lib = _lib.load()
+        g = self.param_groups[0]
+        m = self.model
+        _lib.check(lib.igmc_reduce_update(C.byref(m._cmodel), m.flat_params.data_ptr(), int(B), int(rows),
+                                          ws["gpart"].data_ptr(), ws["dhid"].data_ptr(), ws["feat"].data_ptr(),
+                                          ws["hid"].data_ptr(), ws["dpred"].data_ptr(), ws["sqerr"].data_ptr(),
+                                          float(loss_scale), float(arr), C.byref(exchange.c),
+                                          self.exp_avg.data_ptr(), self.exp_avg_sq.data_ptr(),
+                                          self.step_count.data_ptr(), float(g["lr"]), _lib.ptr(lr_dev),
+                                          float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
+                                          float(g["weight_decay"]), 1.0, ws["loss"].data_ptr(), _lib.ptr(loss_acc),
+                                          float(loss_weight), ws["reg_ws"].data_ptr(), _lib.ptr(grad_copy),
+                                          _stream_ptr()), "igmc_reduce_update")
+        return ws["loss"]
 
     def zero_grad(self, set_to_none=False):
         pass  # flat_grad is fully overwritten by every fused_step

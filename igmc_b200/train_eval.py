@@ -86,6 +86,8 @@ class TrainEngine(object):
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.dev)   # sum_steps loss*G (this rank)
         self.last_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.steps = 0
+        self.exchange = None      # peer-mapped gradient buffers of the fused update kernel (created on first use)
+        self.fused_update = os.environ.get("IGMC_FUSED_UPDATE", "1") != "0"
         self.sync_lr()
 
     def sync_lr(self):
@@ -102,20 +104,41 @@ class TrainEngine(object):
         return self.ARR if self.rank == 0 else 0.0
 
     # ---- the launches of one step, reading everything from stepbuf_dev ----------------------------
+    def _model_step(self, batch, nb, G, seed_dev):
+        """model half of a step on an extracted batch: [prep, forward+loss, backward] then either ONE fused kernel
+        (gradient assembly + ARR -> all-reduce over NVLink peer memory -> Adam) or, for plans without raw partial
+        rows / external readouts, gradient assembly -> NCCL all-reduce -> Adam."""
+        m = self.model
+        if self.fused_update and (m.fused_update_ok(batch) if nb > 0 else self.exchange is not None):
+            if self.exchange is None:
+                from .exchange import Exchange
+                self.exchange = Exchange(m.flat_params.numel(), self.dev, self.rank, self.world)
+            if nb > 0:
+                ws = m.forward_backward(batch, global_num_graphs=G, seed_dev=seed_dev)["ws"]
+                self._last_ws = ws
+                rows = nb * ws["cluster"]
+            else:   # no graph of a short tail batch on this rank: it still takes part in the exchange (zero rows)
+                ws, rows = self._last_ws, 0
+            loss = self.opt.reduce_update(self.exchange, ws, nb, rows, 1.0 / max(G, 1), self.arr_local,
+                                          lr_dev=self.lr_dev, loss_acc=self.loss_acc, loss_weight=float(G))
+        else:
+            if nb > 0:
+                loss = m.fused_step(batch, ARR=self.arr_local, global_num_graphs=G, seed_dev=seed_dev)
+            else:
+                m.flat_grad.zero_()
+                loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            if self.world > 1:
+                dist.all_reduce(m.flat_grad)
+            self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
+        self.last_loss = loss
+
     def _launch(self, nb, G):
         B = self.B
         buf = self.stepbuf_dev
+        batch = None
         if nb > 0:
             batch = self.dataset.extractor.extract(idx=buf[:nb], seed_dev=buf[B:B + 1], reuse=True)
-            loss = self.model.fused_step(batch, ARR=self.arr_local, global_num_graphs=G,
-                                         seed_dev=buf[B + 1:B + 2])
-        else:  # this rank got no graph of a short tail batch: contribute zeros
-            self.model.flat_grad.zero_()
-            loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        if self.world > 1:
-            dist.all_reduce(self.model.flat_grad)
-        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
-        self.last_loss = loss
+        self._model_step(batch, nb, G, buf[B + 1:B + 2])
 
     def _launch_static(self, idx, G):
         batch = self.dataset.extract_batch(idx)
@@ -180,16 +203,7 @@ class TrainEngine(object):
                 # the next step's edge lists (after its dropout draws), staged for the model kernels' bulk loads
                 self.model.stage_batch(self.batches[slot ^ 1], True,
                                        self.model.make_dropout(True, seed_dev=buf[B + 3:B + 4]), slot=slot ^ 1)
-        if nb > 0:
-            loss = self.model.fused_step(self.batches[slot], ARR=self.arr_local, global_num_graphs=G,
-                                         seed_dev=buf[B + 1:B + 2])
-        else:
-            self.model.flat_grad.zero_()
-            loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
-        if self.world > 1:
-            dist.all_reduce(self.model.flat_grad)
-        self.opt.step(grad_mul=1.0, lr_dev=self.lr_dev, loss_in=loss, loss_acc=self.loss_acc, loss_weight=float(G))
-        self.last_loss = loss
+        self._model_step(self.batches[slot] if nb > 0 else None, nb, G, buf[B + 1:B + 2])
         if nb_next > 0:
             main.wait_stream(self.side)
 

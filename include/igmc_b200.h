@@ -278,6 +278,38 @@ int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_
                    float eps, float weight_decay, float grad_mul, const float* loss_in, float* loss_acc,
                    float loss_weight, void* stream);
 
+/* ---- data-parallel exchange + fused update (the reference has no DP; world 1 reproduces its step) ----
+ * Every rank owns one exchange allocation that all ranks of the node map (CUDA IPC): a double-buffered copy of its
+ * gradient plus an array of arrival flags its peers write.  The collective library (NCCL / gloo) only carries the
+ * 64-byte handles once at start-up. */
+#define IGMC_MAX_RANKS 8
+typedef struct {
+  float* grad[IGMC_MAX_RANKS];    /* grad[r]: rank r's [2][stride] gradient buffers (r = rank: local memory) */
+  int32_t* flag[IGMC_MAX_RANKS];  /* flag[r]: rank r's [IGMC_MAX_RANKS] arrival flags, flag[r][src] = last step src published */
+  int64_t* state;                 /* local [2]: exchange step counter, two int32 tickets (zero-initialised) */
+  int32_t world, rank, stride, pad_;
+} igmc_comm_t;
+
+/* cudaMalloc + zero + IPC handle (64 bytes) of an exchange allocation / map a peer's / unmap / free. */
+int igmc_comm_alloc(int64_t bytes, void** dev_ptr, unsigned char* handle64);
+int igmc_comm_open(const unsigned char* handle64, void** dev_ptr);
+int igmc_comm_close(void* peer_ptr);
+int igmc_comm_free(void* dev_ptr);
+
+/* igmc_grad_reduce (raw rows) -> all-reduce(SUM) of the flat gradient over the ranks of `comm` -> igmc_adam_step,
+ * as ONE kernel: the gradient is assembled into this rank's exchange buffer, the ranks publish / await each other's
+ * arrival flags, and every thread sums its elements straight out of the peers' memory (NVLink, fixed rank order ->
+ * bit-identical parameters on all ranks) before applying Adam.  Replaces `loss.backward()`'s accumulation +
+ * `optimizer.step()` (train_eval.py:175-177) and the ncclAllReduce a DDP port would put between them.
+ * `grad_copy` (optional) receives the reduced gradient.  IGMC readout only (readout = 0), cluster plans only. */
+int igmc_reduce_update(const igmc_model_t* M, float* params, int B, int gpart_rows, const float* gpart,
+                       const float* dhid, const float* feat, const float* hid, const float* dpred,
+                       const float* sqerr, float loss_scale, float arr, const igmc_comm_t* comm,
+                       float* exp_avg, float* exp_avg_sq, int64_t* step_count, float lr, const float* lr_dev,
+                       float beta1, float beta2, float eps, float weight_decay, float grad_mul,
+                       float* loss_out, float* loss_acc, float loss_weight, float* reg_ws, float* grad_copy,
+                       void* stream);
+
 /* ---- SortPooling + 1-D convolution readout of DGCNN_RS (models.py:123-167 over DGCNN.__init__ models.py:65-85) ----
  * Consumes the concat_states a readout=1 igmc_forward produced.  latent_dim = [32,...,32,1] is run by the conv
  * kernels as 32-wide layers whose unused output columns have zero weights, so a states row has `state_stride` =

@@ -16,3 +16,4 @@ try:
 except Exception as e:
     print("bench ERR", e)
 PY
+timeout 300 python scripts/step_breakdown.py > gpurun_out/${T}_step_breakdown.txt 2>&1; echo "breakdown rc=$?"; cat gpurun_out/${T}_step_breakdown.txt | tail -8

@@ -1,5 +1,6 @@
 """GPU end-to-end checks of the reference-facing API: train_multiple_epochs, eval, static dataset."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -192,3 +193,91 @@ def test_continue_from_checkpoint(tmp_path):
     assert state["steps"] == 3 * steps_per_epoch                     # Adam's step count went on from the checkpoint
     moved = max(float((m2.state_dict()[k].cpu() - saved[k].cpu()).abs().max()) for k in saved)
     assert 0.0 < moved < 0.5                                          # started from the checkpoint, not from a fresh init
+
+
+def _engine(ds, B, fused, seed=0, adj_dropout=0.2, hidden_p=0.5):
+    from igmc_b200.models import IGMC, FusedAdam
+    from igmc_b200.train_eval import TrainEngine
+    from igmc_b200.util_functions import MyDynamicDataset
+    tu, tv, tl = ds["train"]
+    d = MyDynamicDataset(None, ds["adj_train"], (tu, tv), tl, 1, 1.0, 10, None, None, ds["class_values"])
+    torch.manual_seed(seed)
+    m = IGMC(d, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=adj_dropout).cuda()
+    m.hidden_dropout_p = hidden_p
+    opt = FusedAdam(m, lr=1e-3)
+    eng = TrainEngine(d, m, opt, B, ARR=0.001)
+    eng.fused_update = fused
+    return eng, m, opt
+
+
+def test_fused_update_kernel_equals_separate_kernels():
+    """igmc_reduce_update (gradient assembly + ARR -> exchange -> Adam in ONE launch, world 1) leaves bit-identical
+    parameters, Adam moments, step count and epoch-loss accumulator to igmc_grad_reduce + igmc_adam_step"""
+    ds = _tiny()
+    res = []
+    for fused in (False, True):
+        eng, m, opt = _engine(ds, 8, fused)
+        eng.prime(np.arange(0, 8), epoch=1)
+        for s in range(7):
+            eng.step_pipe(np.arange((s + 1) * 8, (s + 1) * 8 + 8) if s < 6 else None, epoch=1)
+        eng.check()
+        torch.cuda.synchronize()
+        assert (eng.exchange is not None) == fused
+        res.append((m.flat_params.clone(), opt.exp_avg.clone(), opt.exp_avg_sq.clone(), int(opt.step_count[0]),
+                    float(eng.loss_acc), float(eng.last_loss)))
+        if eng.exchange is not None:
+            eng.exchange.close()
+    a, b = res
+    assert a[3] == b[3] == 7
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert a[4] == b[4] and a[5] == b[5] and math.isfinite(a[4])
+
+
+def _dp_rank(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)   # carries the IPC handles only
+    ds = _tiny()
+    B = 8
+    eng, m, opt = _engine(ds, B, True, adj_dropout=0.0, hidden_p=0.0)
+    G = B * world
+    sl = lambda s: np.arange(s * G + rank * B, s * G + rank * B + B)   # noqa: E731
+    eng.prime(sl(0), epoch=1, G=G)
+    for s in range(5):
+        eng.step_pipe(sl(s + 1) if s < 4 else None, epoch=1, next_G=G)
+    eng.check()
+    torch.cuda.synchronize()
+    q.put((rank, m.flat_params.cpu(), float(eng.loss_acc)))
+    dist.barrier()
+    eng.exchange.close()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_dp2_peer_exchange_equals_single_gpu_global_batch():
+    """2 ranks x batch 8 through the NVLink peer exchange inside igmc_reduce_update == 1 GPU x batch 16 on the same
+    pairs (dropout off so that both see the same function): parameters within 1e-6, both ranks bit-identical, and the
+    summed epoch-loss accumulators agree."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_rank, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted([q.get(timeout=240) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert torch.equal(got[0][1], got[1][1])                 # ranks stay bit-identical
+    ds = _tiny()
+    eng, m, opt = _engine(ds, 16, True, adj_dropout=0.0, hidden_p=0.0)
+    eng.prime(np.arange(0, 16), epoch=1)
+    for s in range(5):
+        eng.step_pipe(np.arange((s + 1) * 16, (s + 1) * 16 + 16) if s < 4 else None, epoch=1)
+    eng.check()
+    torch.cuda.synchronize()
+    assert float((m.flat_params.cpu() - got[0][1]).abs().max()) <= 1e-6
+    assert abs(float(eng.loss_acc) - (got[0][2] + got[1][2])) <= 1e-3 * abs(float(eng.loss_acc))
+    eng.exchange.close()
