@@ -40,7 +40,7 @@ class Pairs(C.Structure):
 
 class ExtractWS(C.Structure):
     _fields_ = [("nodes_u", vp), ("nodes_v", vp), ("n_u", vp), ("n_v", vp), ("row_cnt", vp), ("m_cnt", vp),
-                ("col_cnt", vp), ("hop_off", vp)]
+                ("col_cnt", vp), ("hop_off", vp), ("sync", vp)]
 
 
 class BatchOut(C.Structure):
@@ -106,7 +106,7 @@ class SortPoolSaved(C.Structure):
 
 _SIGS = {
     "igmc_extract_batch": [C.POINTER(CSR), C.POINTER(Pairs), C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, vp, C.c_int,
-                           vp, vp, vp, vp, C.POINTER(ExtractWS), vp, C.POINTER(BatchOut), vp, vp],
+                           vp, vp, vp, vp, C.POINTER(ExtractWS), vp, C.c_int, C.c_int, C.POINTER(BatchOut), vp, vp],
     "igmc_assemble_batch": [C.POINTER(Store), vp, C.c_int, C.POINTER(BatchOut), vp, vp],
     "igmc_batch_ptrs": [vp, vp, C.c_int, C.c_int, C.c_int, vp, vp, vp, vp],
     "igmc_batch_prepare": [vp, C.c_int64, vp, vp, vp, C.c_int, C.c_int, C.POINTER(Adj), vp, vp],

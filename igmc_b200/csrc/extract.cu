@@ -17,6 +17,8 @@
 //       second row scan with warp-ballot ordered compaction, writes x / labels / batch / y /
 //       edge_index (int64, PyG order [u|v ; v|u]) / edge_type / node_ptr / edge_ptr.
 // HBM-bound integer work: no tensor cores; int32 index + uint8 rating per nonzero.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "../../include/igmc_b200.h"
 
@@ -477,6 +479,375 @@ k_extract_fill(igmc_csr_t G, igmc_pairs_t P, int B, int cap,
 }
 
 
+// ------------------------------------------------------------------------------------------------------------------
+// h = 1 fast path: ONE launch, one 512-thread CTA per pair (two CTAs per SM, so that a batch sits next to the model
+// kernels' one-per-SM CTAs), every row entry read once.
+//   A  node lists (select_side, as above)
+//   B  the concatenated user rows are cut into 128-entry tiles handed round-robin to the warps (balanced whatever
+//      the row lengths; four independent index loads in flight per lane).  A matching entry (item in the subgraph,
+//      looked up in the shared-memory item table) is packed as  u_local << 20 | v_local << 8 | rating  and appended
+//      to the graph's scratch slot at a cursor position reserved per tile; edges to the target item (which sort first
+//      in their row) are kept per row instead.  Per-row counts by shared atomics; a bitmap over the user rows per
+//      (item, rating) replaces every per-item counter.
+//   C  canonical rank of an entry = exclusive prefix of the tile counts + index in its tile (+ the row's target-item
+//      edges before it): block scans, then the cross-graph node / edge offsets by look-back on the counts the
+//      lower-numbered CTAs publish (no second launch, no host sync).
+//   D  the entries go to their canonical positions in a shared-memory copy and in the API arrays (edge_index,
+//      edge_type; both directions); message-passing lists sorted by (rating, neighbour): a user's list is its
+//      contiguous run of the canonical order, stably split by rating with warp ballots; an entry's position in its
+//      item's list is a population count over the (item, rating) bitmaps.  No sort, no O(k^2) ranking.
+// Same outputs, bit for bit, as the generic two-kernel path (tests/test_gpu_extract.py runs both).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FX_THREADS = 512;
+constexpr int FX_TILE = 128;
+constexpr int FX_TCAP = 2048;        // tiles per pair: the user rows of one subgraph hold <= 262144 entries
+constexpr int FX_CANO = 12288;       // canonical edges kept in shared memory (more: second half of the scratch slot)
+constexpr int FX_MAXCAP = 4095;      // local ids travel in 12 bits
+constexpr int FX_MAXR = 32;          // rating classes (lane = class in the ballot split)
+
+__device__ __forceinline__ void st_release_gpu(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+struct FastSmem {   // carve-up of the dynamic shared memory (ints unless noted); `words` = bitmap words per (item, rating)
+  int *rp, *rowstart, *rowcnt, *rowoff, *jbefore, *hj, *colcnt, *coloff, *cur, *tilebase, *stage_off;
+  uint32_t *bm, *cano;
+  uint16_t* tab;
+};
+__host__ __device__ __forceinline__ size_t fast_smem_ints(int cap, int R, int words) {
+  return (size_t)cap * 4 + (size_t)(cap + 1) * 4 + (size_t)cap * R + (size_t)cap * R * words + (FX_TCAP + 1) + FX_TCAP +
+         FX_CANO;
+}
+
+__global__ void __launch_bounds__(FX_THREADS, 2)
+k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint64_t seed_val,
+               const uint64_t* __restrict__ seed_dev, int cap, const int32_t* __restrict__ inj_nodes_u,
+               const int32_t* __restrict__ inj_nodes_v, const int32_t* __restrict__ inj_n_u,
+               const int32_t* __restrict__ inj_n_v, igmc_extract_ws_t W, int R, int words, int slot_e,
+               const float* __restrict__ class_values, igmc_batch_out_t O, int* err) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  FastSmem S;
+  {
+    int* p = reinterpret_cast<int*>(smem_raw);
+    S.rp = p; p += cap;
+    S.rowcnt = p; p += cap;
+    S.hj = p; p += cap;
+    S.colcnt = p; p += cap;
+    S.rowstart = p; p += cap + 1;
+    S.rowoff = p; p += cap + 1;
+    S.jbefore = p; p += cap + 1;
+    S.coloff = p; p += cap + 1;
+    S.cur = p; p += cap * R;
+    S.bm = reinterpret_cast<uint32_t*>(p); p += (size_t)cap * R * words;
+    S.tilebase = p; p += FX_TCAP + 1;
+    S.stage_off = p; p += FX_TCAP;
+    S.cano = reinterpret_cast<uint32_t*>(p); p += FX_CANO;
+    S.tab = reinterpret_cast<uint16_t*>(p);
+  }
+  __shared__ int hist[256];
+  __shared__ int ws[34];
+  __shared__ int sh[4];
+  __shared__ int s_nu, s_nv, s_cursor;
+  const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const uint64_t seed = seed_dev ? *seed_dev : seed_val;
+  int* flags = W.sync;   // [B] "counts published" flags + [1] completion ticket (all zero between launches)
+  int i, j, lab;
+  int64_t pid;
+  resolve_pair(P, g, &i, &j, &lab, &pid);
+  int32_t* gu = W.nodes_u + (size_t)g * cap;
+  int32_t* gv = W.nodes_v + (size_t)g * cap;
+
+  // ---- A: node lists ----
+  if (inj_nodes_u) {
+    const int nu0 = inj_n_u[g], nv0 = inj_n_v[g];
+    if (nu0 > cap || nv0 > cap) {
+      if (tid == 0) { igmc_set_err(err, IGMC_ERR_NODE_CAP); s_nu = 1; s_nv = 1; gu[0] = i; gv[0] = j; }
+    } else {
+      for (int t = tid; t < nu0; t += nt) gu[t] = inj_nodes_u[(size_t)g * cap + t];
+      for (int t = tid; t < nv0; t += nt) gv[t] = inj_nodes_v[(size_t)g * cap + t];
+      if (tid == 0) { s_nu = nu0; s_nv = nv0; }
+    }
+    __syncthreads();
+  } else {
+    select_side(G.row_idx + G.col_ptr[j], G.col_ptr[j + 1] - G.col_ptr[j], i, true, mnph, ratio,
+                sample_state(seed, pid, 0, 1), gu, cap, &s_nu, hist, ws, sh, err);
+    select_side(G.col_idx + G.row_ptr[i], G.row_ptr[i + 1] - G.row_ptr[i], j, true, mnph, ratio,
+                sample_state(seed, pid, 1, 1), gv, cap, &s_nv, hist, ws, sh, err);
+  }
+  __syncthreads();
+  const int nu = s_nu, nv = s_nv, n = nu + nv;
+
+  // ---- B: one balanced scan of the user rows ----
+  for (int t = tid; t < G.num_items; t += nt) S.tab[t] = NONE16;
+  for (int t = tid; t < nv * R * words; t += nt) S.bm[t] = 0u;
+  for (int a = tid; a < nu; a += nt) { S.rowcnt[a] = 0; S.hj[a] = 0; }
+  if (tid == 0) s_cursor = 0;
+  {   // row pointers and the flat prefix of the row lengths
+    int running = 0;
+    for (int base = 0; base < nu; base += nt) {
+      const int a = base + tid;
+      int d = 0;
+      if (a < nu) {
+        const int u = gu[a];
+        const int s0 = G.row_ptr[u];
+        S.rp[a] = s0;
+        d = G.row_ptr[u + 1] - s0;
+      }
+      int tot;
+      const int ex = block_excl_scan_i(d, ws, &tot);
+      if (a < nu) S.rowstart[a] = running + ex;
+      running += tot;
+    }
+    if (tid == 0) S.rowstart[nu] = running;
+  }
+  __syncthreads();
+  for (int b = tid; b < nv; b += nt) S.tab[gv[b]] = (uint16_t)b;
+  __syncthreads();
+  const int D = S.rowstart[nu];
+  const int T = (D + FX_TILE - 1) / FX_TILE;
+  uint32_t* stage = reinterpret_cast<uint32_t*>(O.adj_tmp + (size_t)g * slot_e);   // [2 * slot_e] u32 of scratch
+  if (T > FX_TCAP) {   // the host sizes the plan so that this cannot happen; never run past the tables
+    if (tid == 0) igmc_set_err(err, IGMC_ERR_EDGE_CAP);
+  } else {
+    for (int tile = warp; tile < T; tile += nwarps) {
+      const int q0 = tile * FX_TILE;
+      int lo = 0, hi = nu - 1;   // row of entry q0 (uniform over the warp)
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (S.rowstart[mid] <= q0) lo = mid; else hi = mid - 1;
+      }
+      int ar[4], pr[4], col[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int q = q0 + 32 * u + lane;
+        int a = lo;
+        col[u] = -1;
+        pr[u] = 0;
+        if (q < D) {
+          while (q >= S.rowstart[a + 1]) ++a;
+          pr[u] = S.rp[a] + (q - S.rowstart[a]);
+          col[u] = __ldg(G.col_idx + pr[u]);
+        }
+        ar[u] = a;
+      }
+      uint32_t word[4];
+      unsigned bal[4];
+      int cnt = 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        uint16_t b = NONE16;
+        if (col[u] >= 0) b = S.tab[col[u]];
+        const bool match = (b != NONE16) && !(ar[u] == 0 && b == 0);   // (target user, target item): removed (ref :238)
+        uint32_t r = 0;
+        if (match) {
+          r = G.rating[pr[u]];
+          if ((int)r >= R) { igmc_set_err(err, IGMC_ERR_BAD_BATCH); r = 0; }   // label outside class_values
+          atomicAdd(&S.rowcnt[ar[u]], 1);
+          atomicOr(&S.bm[((size_t)b * R + r) * words + (ar[u] >> 5)], 1u << (ar[u] & 31));
+          if (b == 0) S.hj[ar[u]] = 1 | (int)(r << 8);
+        }
+        const bool nonj = match && b != 0;
+        word[u] = nonj ? (((uint32_t)ar[u] << 20) | ((uint32_t)b << 8) | r) : 0xFFFFFFFFu;
+        bal[u] = __ballot_sync(IGMC_FULL, nonj);
+        cnt += __popc(bal[u]);
+      }
+      int off = 0;
+      if (lane == 0) {
+        if (cnt) off = atomicAdd(&s_cursor, cnt);
+        S.stage_off[tile] = off;
+        S.tilebase[tile] = cnt;
+      }
+      off = __shfl_sync(IGMC_FULL, off, 0);
+      if (off + cnt <= 2 * slot_e) {   // never write past the scratch slot (the overflow is reported below)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (word[u] != 0xFFFFFFFFu) stage[off + __popc(bal[u] & lt_mask)] = word[u];
+          off += __popc(bal[u]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- C: prefixes ----
+  {   // rows: edge offsets and the number of target-item edges in earlier rows, one packed scan (counts < 2^20)
+    int running = 0;
+    for (int base = 0; base < nu; base += nt) {
+      const int a = base + tid;
+      const int v = a < nu ? (S.rowcnt[a] | ((S.hj[a] & 1) << 20)) : 0;
+      int tot;
+      const int ex = block_excl_scan_i(v, ws, &tot);
+      if (a < nu) {
+        S.rowoff[a] = (running + ex) & 0xFFFFF;
+        S.jbefore[a] = (running + ex) >> 20;
+      }
+      running += tot;
+    }
+    if (tid == 0) { S.rowoff[nu] = running & 0xFFFFF; S.jbefore[nu] = running >> 20; }
+  }
+  {   // tiles: counts -> exclusive prefix, in place
+    int running = 0;
+    const int TT = T > FX_TCAP ? 0 : T;
+    for (int base = 0; base < TT; base += nt) {
+      const int t = base + tid;
+      const int v = t < TT ? S.tilebase[t] : 0;
+      int tot;
+      const int ex = block_excl_scan_i(v, ws, &tot);
+      if (t < TT) S.tilebase[t] = running + ex;
+      running += tot;
+    }
+    if (tid == 0) S.tilebase[TT] = running;
+  }
+  // items: per-rating sub-list offsets and list lengths from the bitmaps
+  for (int b = tid; b < nv; b += nt) {
+    int run = 0;
+    for (int r = 0; r < R; ++r) {
+      S.cur[b * R + r] = run;
+      const uint32_t* w = S.bm + ((size_t)b * R + r) * words;
+      for (int x = 0; x < words; ++x) run += __popc(w[x]);
+    }
+    S.colcnt[b] = run;
+  }
+  __syncthreads();
+  {
+    int running = 0;
+    for (int base = 0; base < nv; base += nt) {
+      const int b = base + tid;
+      const int v = b < nv ? S.colcnt[b] : 0;
+      int tot;
+      const int ex = block_excl_scan_i(v, ws, &tot);
+      if (b < nv) S.coloff[b] = running + ex;
+      running += tot;
+    }
+  }
+  const int m = S.rowoff[nu];
+  // publish this graph's counts, then sum the predecessors' (they run at the same time; lower block ids are
+  // dispatched first, so waiting on them cannot deadlock)
+  if (tid == 0) {
+    W.n_u[g] = nu; W.n_v[g] = nv; W.m_cnt[g] = m;
+    __threadfence();
+    st_release_gpu(&flags[g], 1);
+  }
+  int nsum = 0, msum = 0;
+  for (int q = tid; q < g; q += nt) {
+    while (ld_acquire_gpu(&flags[q]) == 0) {}
+    nsum += __ldcg(W.n_u + q) + __ldcg(W.n_v + q);
+    msum += __ldcg(W.m_cnt + q);
+  }
+  const int Nbase = block_sum_i(nsum, ws);
+  const int Mbase = block_sum_i(msum, ws);
+  const bool overflow = (Nbase + n > O.node_cap) || (2 * (Mbase + m) > O.edge_cap) || T > FX_TCAP || m > slot_e;
+  if (g == B - 1 && tid == 0) {
+    O.counts[0] = Nbase + n;
+    O.counts[1] = 2 * (Mbase + m);
+    O.node_ptr[B] = Nbase + n;
+    O.edge_ptr[B] = 2 * (Mbase + m);
+    if (Nbase + n <= O.node_cap) O.adj_in_ptr[Nbase + n] = 2 * (Mbase + m);
+  }
+  if (tid == 0) { O.node_ptr[g] = Nbase; O.edge_ptr[g] = 2 * Mbase; }
+  if (overflow) {
+    if (tid == 0 && T <= FX_TCAP)
+      igmc_set_err(err, (Nbase + n > O.node_cap) ? IGMC_ERR_NODE_TOTAL : IGMC_ERR_EDGE_CAP);
+  } else {
+    // ---- D: outputs ----
+    if (tid == 0) { O.y[g] = class_values[lab]; O.graph_nu[g] = nu; }
+    for (int t = tid; t < n; t += nt) {
+      const int label = t < nu ? (t == 0 ? 0 : 2) : (t == nu ? 1 : 3);   // ref :245 with h = 1
+      const size_t row = (size_t)Nbase + t;
+      O.node_label[row] = (uint8_t)label;
+      O.batch[row] = g;
+      O.node_gid[row] = t < nu ? gu[t] : gv[t - nu];
+      if (O.x)
+        for (int f = 0; f < O.feat_dim; ++f) O.x[row * O.feat_dim + f] = (f == label) ? 1.0f : 0.0f;
+      O.adj_in_ptr[row] = t < nu ? 2 * Mbase + S.rowoff[t] : 2 * Mbase + m + S.coloff[t - nu];
+    }
+    // canonical (row-major, target item first) order: in shared memory, or (large subgraphs) in the upper half of
+    // the scratch slot, read back past L1
+    const bool cs = m <= FX_CANO;
+    uint32_t* cano = cs ? S.cano : stage + slot_e;
+    auto cld = [&](int q) -> uint32_t { return cs ? S.cano[q] : __ldcg(stage + slot_e + q); };
+    int64_t* ei0 = O.edge_index;
+    int64_t* ei1 = O.edge_index + O.edge_cap;
+    auto emit = [&](uint32_t w, int pos) {
+      cano[pos] = w;
+      const int a = (int)(w >> 20), b = (int)((w >> 8) & 0xFFFu);
+      const int64_t r = (int64_t)(w & 0xFFu);
+      const size_t e1 = (size_t)2 * Mbase + pos, e2 = e1 + m;
+      const int64_t un = Nbase + a, vn = Nbase + nu + b;
+      ei0[e1] = un; ei1[e1] = vn; O.edge_type[e1] = r;
+      ei0[e2] = vn; ei1[e2] = un; O.edge_type[e2] = r;
+    };
+    for (int tile = warp; tile < T; tile += nwarps) {
+      const int base = S.tilebase[tile], cnt = S.tilebase[tile + 1] - base, so = S.stage_off[tile];
+      for (int k = lane; k < cnt; k += 32) {
+        const uint32_t w = __ldcg(stage + so + k);
+        const int a = (int)(w >> 20);
+        emit(w, base + k + S.jbefore[a] + (S.hj[a] & 1));
+      }
+    }
+    for (int a = tid; a < nu; a += nt)
+      if (S.hj[a] & 1) emit(((uint32_t)a << 20) | (uint32_t)(S.hj[a] >> 8), S.rowoff[a]);
+    __syncthreads();
+    // user lists: the row's run of the canonical order, stably split by rating (lane r keeps rating r's counter)
+    for (int a = warp; a < nu; a += nwarps) {
+      const int ro = S.rowoff[a], cnt = S.rowoff[a + 1] - ro;
+      int tc = 0;
+      for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const int k = c0 + lane;
+        const int r = k < cnt ? (int)(cld(ro + k) & 0xFFu) : -1;
+        for (int t = 0; t < R; ++t) {
+          const unsigned mk = __ballot_sync(IGMC_FULL, r == t);
+          if (lane == t) tc += __popc(mk);
+        }
+      }
+      int run = warp_incl_scan_i(tc, lane) - tc;   // first slot of rating `lane`
+      const size_t beg = (size_t)2 * Mbase + ro;
+      for (int c0 = 0; c0 < cnt; c0 += 32) {
+        const int k = c0 + lane;
+        const uint32_t w = k < cnt ? cld(ro + k) : 0u;
+        const int r = k < cnt ? (int)(w & 0xFFu) : -1;
+        int slot = 0;
+        for (int t = 0; t < R; ++t) {
+          const unsigned mk = __ballot_sync(IGMC_FULL, r == t);
+          const int rt = __shfl_sync(IGMC_FULL, run, t);
+          if (r == t) slot = rt + __popc(mk & lt_mask);
+          if (lane == t) run += __popc(mk);
+        }
+        if (k < cnt) {
+          O.adj_in[beg + slot] = (uint32_t)(nu + (int)((w >> 8) & 0xFFFu)) | ((uint32_t)r << 16);
+          O.adj_eid[beg + slot] = 2 * Mbase + m + ro + k;          // the mirrored (item -> user) directed edge
+        }
+      }
+    }
+    // item lists: position = rating sub-list offset + number of earlier user rows holding the same (item, rating)
+    for (int k = tid; k < m; k += nt) {
+      const uint32_t w = cld(k);
+      const int a = (int)(w >> 20), b = (int)((w >> 8) & 0xFFFu), r = (int)(w & 0xFFu);
+      const uint32_t* bw = S.bm + ((size_t)b * R + r) * words;
+      int rank = __popc(bw[a >> 5] & ((1u << (a & 31)) - 1u));
+      for (int x = 0; x < (a >> 5); ++x) rank += __popc(bw[x]);
+      const size_t o = (size_t)2 * Mbase + m + S.coloff[b] + S.cur[b * R + r] + rank;
+      O.adj_in[o] = (uint32_t)a | ((uint32_t)r << 16);
+      O.adj_eid[o] = 2 * Mbase + k;
+    }
+  }
+  // the last CTA to finish re-arms the flags for the next launch
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    if (atomicAdd(&flags[B], 1) == B - 1) {
+      for (int q = 0; q <= B; ++q) flags[q] = 0;
+    }
+  }
+}
+
 // Batch assembly from the static store (one CTA per output graph).
 __global__ void __launch_bounds__(256)
 k_assemble(igmc_store_t S, const int64_t* __restrict__ idx, int B, igmc_batch_out_t O, int* err) {
@@ -537,13 +908,44 @@ extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, in
                                   double sample_ratio, uint64_t seed, const uint64_t* seed_dev, int cap,
                                   const int32_t* inj_nodes_u, const int32_t* inj_nodes_v,
                                   const int32_t* inj_n_u, const int32_t* inj_n_v,
-                                  const igmc_extract_ws_t* W, const float* class_values,
-                                  const igmc_batch_out_t* O, int* err, void* stream) {
+                                  const igmc_extract_ws_t* W, const float* class_values, int num_classes,
+                                  int max_row_deg, const igmc_batch_out_t* O, int* err, void* stream) {
   if (B <= 0) return 0;
   if (cap < 1 || cap > 65534) return -2;
   if (h < 1 || h > IGMC_MAX_HOP) return -4;
   if (h > 1 && (inj_nodes_u || !W->hop_off)) return -4;   // injected node lists carry no hop boundaries
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // h = 1 fast path (one launch) whenever its tables fit: ids in 12 bits, <= 32 rating classes, the user rows of
+    // one subgraph within the tile table, two CTAs per SM worth of shared memory, scratch slot >= the edge bound
+    static int fast_env = -1;
+    if (fast_env < 0) {
+      const char* e = getenv("IGMC_EXTRACT_FAST");
+      fast_env = e ? atoi(e) : 1;
+    }
+    const int R = num_classes;
+    const int words = (cap + 31) / 32;
+    const int slot_e = O->edge_cap / B;
+    const size_t smemF = fast_smem_ints(cap, R > 0 ? R : 1, words) * 4 + (((size_t)G->num_items * 2 + 15) & ~(size_t)15);
+    const long long rows_max = (long long)cap * (long long)(max_row_deg > 0 ? max_row_deg : G->num_items);
+    if (fast_env && h == 1 && W->sync && O->adj_in_ptr && R >= 1 && R <= FX_MAXR && cap <= FX_MAXCAP &&
+        rows_max <= (long long)FX_TILE * FX_TCAP && smemF <= 110 * 1024 && slot_e >= 2) {
+      cudaFuncSetAttribute(k_extract_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemF);
+      k_extract_fast<<<B, FX_THREADS, smemF, st>>>(*G, *P, B, max_nodes_per_hop, sample_ratio, seed, seed_dev, cap,
+                                                   inj_nodes_u, inj_nodes_v, inj_n_u, inj_n_v, *W, R, words, slot_e,
+                                                   class_values, *O, err);
+      IGMC_CUDA_CHECK_LAUNCH();
+      return 0;
+    }
+  }
+  // generic two-kernel path (any hop count / capacity): 1024-thread CTAs.  Measured on the headline workload
+  // (profiles/README.md): 131 us per batch-50 at 1024 threads, 170 us at 512, 240 us at 256 - latency-bound.
+  static int ex_threads = 0;
+  if (!ex_threads) {
+    const char* e = getenv("IGMC_EX_THREADS");
+    ex_threads = e ? atoi(e) : 1024;
+    if (ex_threads != 256 && ex_threads != 512 && ex_threads != 1024) ex_threads = 1024;
+  }
   size_t smemA = (size_t)cap * sizeof(int) + (size_t)G->num_items * sizeof(uint16_t);
   if (h > 1) {   // visited / candidate bitmaps + the fringe list of the larger side
     const size_t wu = (G->num_users + 31) / 32, wv = (G->num_items + 31) / 32;
@@ -555,12 +957,12 @@ extern "C" int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, in
   if (smemB > 220 * 1024) return -3;  // item table does not fit in shared memory
   cudaFuncSetAttribute(k_extract_select_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemA);
   cudaFuncSetAttribute(k_extract_fill, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemB);
-  k_extract_select_count<<<B, EX_THREADS, smemA, st>>>(*G, *P, B, max_nodes_per_hop, sample_ratio, seed, seed_dev, cap,
+  k_extract_select_count<<<B, ex_threads, smemA, st>>>(*G, *P, B, max_nodes_per_hop, sample_ratio, seed, seed_dev, cap,
                                                        inj_nodes_u, inj_nodes_v, inj_n_u, inj_n_v,
                                                        W->nodes_u, W->nodes_v, W->n_u, W->n_v, W->row_cnt, W->m_cnt,
                                                        W->col_cnt, h, W->hop_off, err);
   IGMC_CUDA_CHECK_LAUNCH();
-  k_extract_fill<<<B, EX_THREADS, smemB, st>>>(*G, *P, B, cap, W->nodes_u, W->nodes_v, W->n_u, W->n_v,
+  k_extract_fill<<<B, ex_threads, smemB, st>>>(*G, *P, B, cap, W->nodes_u, W->nodes_v, W->n_u, W->n_v,
                                                W->row_cnt, W->m_cnt, W->col_cnt, h, W->hop_off, class_values, *O, err);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;

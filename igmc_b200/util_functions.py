@@ -252,11 +252,12 @@ class SubgraphExtractor(object):
     """
 
     def __init__(self, graph, links_u, links_v, labels, class_values, h=1, sample_ratio=1.0,
-                 max_nodes_per_hop=None, max_batch=64, seed=0, emit_x=True):
+                 max_nodes_per_hop=None, max_batch=64, seed=0, emit_x=True, fast=True):
         if not 1 <= int(h) <= _lib.MAX_HOP:
             raise NotImplementedError("igmc_b200 extraction implements hop = 1..%d (Main.py:88 default 1)" % _lib.MAX_HOP)
         self.lib = _lib.load()
         self.graph = graph
+        self.fast = bool(fast)    # h = 1: one-launch extraction (False forces the generic two-launch kernels)
         self.device = graph.device if graph.device is not None else _require_cuda()
         if graph.device is None:
             graph.to(self.device)
@@ -291,9 +292,13 @@ class SubgraphExtractor(object):
                        n_u=torch.zeros(B, **i32), n_v=torch.zeros(B, **i32),
                        row_cnt=torch.empty(B * cap, **i32), m_cnt=torch.zeros(B, **i32),
                        col_cnt=torch.empty(B * cap, **i32),
-                       hop_off=torch.zeros(B * 2 * (_lib.MAX_HOP + 1), **i32))
-        self._ws_c = _lib.ExtractWS(*[self.ws[k].data_ptr() for k in ("nodes_u", "nodes_v", "n_u", "n_v",
-                                                                          "row_cnt", "m_cnt", "col_cnt", "hop_off")])
+                       hop_off=torch.zeros(B * 2 * (_lib.MAX_HOP + 1), **i32),
+                       sync=torch.zeros(B + 1, **i32))
+        ptrs = [self.ws[k].data_ptr() for k in ("nodes_u", "nodes_v", "n_u", "n_v", "row_cnt", "m_cnt", "col_cnt",
+                                                "hop_off", "sync")]
+        if not self.fast:
+            ptrs[-1] = None      # no flags -> the generic two-launch path
+        self._ws_c = _lib.ExtractWS(*ptrs)
 
     def _alloc_out(self, B, reuse=False, slot=0):
         if reuse and (B, slot) in self._out_cache:
@@ -368,7 +373,8 @@ class SubgraphExtractor(object):
                                                self.sample_ratio, self.seed if seed is None else int(seed),
                                                _lib.ptr(seed_dev), self.cap, inj[0], inj[1], inj[2], inj[3],
                                                C.byref(self._ws_c),
-                                               self.class_values.data_ptr(), C.byref(O), o["err"].data_ptr(),
+                                               self.class_values.data_ptr(), int(self.class_values.numel()),
+                                               int(self.graph.max_row_deg), C.byref(O), o["err"].data_ptr(),
                                                _stream_ptr()), "igmc_extract_batch")
         b = Batch(B, dev, y=o["y"])
         b._lazy = o

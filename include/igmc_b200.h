@@ -56,6 +56,8 @@ typedef struct {
   int32_t* m_cnt;    /* [B] undirected edges per graph */
   int32_t* col_cnt;  /* [B*cap] matches per item column */
   int32_t* hop_off;  /* [B*2*(IGMC_MAX_HOP+1)] nodes within distance d per side (users then items); needed for h > 1 */
+  int32_t* sync;     /* [B+1] zero-initialised flags of the one-launch h = 1 path (re-armed by the kernel); NULL
+                      * selects the generic two-launch path */
 } igmc_extract_ws_t;
 
 /* The collated batch in the reference's layout (what construct_pyg_graph + Batch.from_data_list
@@ -87,12 +89,14 @@ typedef struct {
  * (util_functions.py:138-145, 208-297) and PyG's Batch.from_data_list.  `max_nodes_per_hop` < 0
  * means None; `cap` bounds one side's node list over all hops.  `inj_*` (all or none NULL) inject per-graph
  * node lists [B*cap] (test hook: the reference's own random.sample draw; h = 1 only).  `seed_dev` (optional, device) overrides `seed` so that a
- * captured CUDA graph can be replayed with a fresh sampling stream every step. */
+ * captured CUDA graph can be replayed with a fresh sampling stream every step.
+ * `num_classes` = len(class_values), `max_row_deg` = the longest user row of G (0 = unknown): with W->sync set they
+ * let h = 1 batches take the one-launch path (single balanced row scan, look-back offsets; same outputs bit for bit). */
 int igmc_extract_batch(const igmc_csr_t* G, const igmc_pairs_t* P, int B, int h, int max_nodes_per_hop,
                        double sample_ratio, uint64_t seed, const uint64_t* seed_dev, int cap,
                        const int32_t* inj_nodes_u, const int32_t* inj_nodes_v,
                        const int32_t* inj_n_u, const int32_t* inj_n_v,
-                       const igmc_extract_ws_t* W, const float* class_values,
+                       const igmc_extract_ws_t* W, const float* class_values, int num_classes, int max_row_deg,
                        const igmc_batch_out_t* O, int* err, void* stream);
 
 /* Device-resident store of pre-extracted subgraphs: the reference's static `MyDataset` keeps

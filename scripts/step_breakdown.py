@@ -29,8 +29,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
 
 def model_only():
-    loss = m.fused_step(eng.batches[0], ARR=0.001, global_num_graphs=B, seed_dev=buf[B + 1:B + 2])
-    opt.step(lr_dev=eng.lr_dev, loss_in=loss, loss_acc=eng.loss_acc, loss_weight=float(B))
+    eng._model_step(eng.batches[0], B, B, buf[B + 1:B + 2])
 
 
 def extract_only():
@@ -45,6 +44,46 @@ def both():
         extract_only()
     model_only()
     main.wait_stream(side)
+
+
+lo_side = torch.cuda.Stream(priority=0)
+hi_main = torch.cuda.Stream(priority=-1)
+
+
+def variant(delay_after, prio):
+    """delay_after: None | 'prep' | 'fwd'  (the extraction branch starts after that model kernel has finished);
+    prio: run the model branch on a high-priority stream"""
+    def fn():
+        outer = torch.cuda.current_stream()
+        ms = hi_main if prio else outer
+        ss = lo_side if prio else side
+        if prio:
+            ms.wait_stream(outer)
+        with torch.cuda.stream(ms):
+            b = eng.batches[0]
+            m._step += 1
+            drop = m.make_dropout(True, seed_dev=buf[B + 1:B + 2])
+            if delay_after is None:
+                ss.wait_stream(ms)
+            import igmc_b200._lib as L, ctypes as C
+            from igmc_b200.util_functions import _stream_ptr
+            ws = m._workspace(b, True)
+            L.check(L.load().igmc_prep_weights(C.byref(m._cmodel), m.flat_params.data_ptr(), m._wprep_buf().data_ptr(),
+                                               _stream_ptr()), "prep")
+            if delay_after == "prep":
+                ss.wait_stream(ms)
+            _, saved = m._launch_forward(b, True, drop, y=b.y, loss_scale=1.0 / B)
+            if delay_after == "fwd":
+                ss.wait_stream(ms)
+            with torch.cuda.stream(ss):
+                extract_only()
+            m._launch_backward(b, drop, saved, saved["ws"]["dpred"])
+            opt.reduce_update(eng.exchange, saved["ws"], B, B * saved["ws"]["cluster"], 1.0 / B, 0.001,
+                              lr_dev=eng.lr_dev, loss_acc=eng.loss_acc, loss_weight=float(B))
+            ms.wait_stream(ss)
+        if prio:
+            outer.wait_stream(ms)
+    return fn
 
 
 def parts():
@@ -98,5 +137,9 @@ def timed(fn, reps=40, flushed=True):
 
 print("workload", wl, "B", B, "plan", m._plan(eng.batches[0]))
 print("eager per-launch (us, L2 flushed):", parts())
-for name, fn in (("model branch", model_only), ("extraction branch", extract_only), ("both branches", both)):
-    print("%-18s graph replay us  flushed median/min %s   warm median/min %s" % (name, timed(fn), timed(fn, flushed=False)))
+cases = [("model branch", model_only), ("extraction branch", extract_only), ("both branches", both)]
+for d_ in (None, "prep", "fwd"):
+    for pr in (False, True):
+        cases.append(("both, extraction after %s%s" % (d_ or "start", ", model high-priority" if pr else ""), variant(d_, pr)))
+for name, fn in cases:
+    print("%-58s graph replay us  flushed median/min %s   warm median/min %s" % (name, timed(fn), timed(fn, flushed=False)))

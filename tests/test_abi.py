@@ -51,7 +51,7 @@ def test_struct_sizes_match_header_layout():
     P = ctypes.sizeof(ctypes.c_void_p)
     assert ctypes.sizeof(_lib.CSR) == 5 * P + 8
     assert ctypes.sizeof(_lib.Pairs) == 5 * P
-    assert ctypes.sizeof(_lib.ExtractWS) == 8 * P
+    assert ctypes.sizeof(_lib.ExtractWS) == 9 * P
     assert ctypes.sizeof(_lib.Adj) == 7 * P + 8
     assert ctypes.sizeof(_lib.Model) == 4 * (4 + 4 * 8 + 4 + 2 + 1 + 1)
     assert ctypes.sizeof(_lib.Stage) == 3 * P + 16

@@ -207,3 +207,53 @@ def test_flixster_real_data():
     bs = st.extract_batch(np.arange(len(idx)))
     res = batch_equal(bs, obt)
     assert all(res.values()), res
+
+
+def _same_everything(a, b, B):
+    """two extracted batches agree on the public arrays AND on the private message-passing adjacency"""
+    a.check(); b.check()
+    ca, cb = a._priv["counts"].cpu().numpy(), b._priv["counts"].cpu().numpy()
+    assert np.array_equal(ca, cb)
+    N, E = int(ca[0]), int(ca[1])
+    for k in ("x", "edge_index", "edge_type", "batch", "node_label", "node_gid", "y"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), k
+    for k in ("node_ptr", "edge_ptr", "graph_nu"):
+        assert torch.equal(a._priv[k][:B + (k != "graph_nu")], b._priv[k][:B + (k != "graph_nu")]), k
+    ta, tb = a._adj[1], b._adj[1]
+    assert torch.equal(ta["adj_in_ptr"][:N + 1], tb["adj_in_ptr"][:N + 1])
+    assert torch.equal(ta["adj_in"][:E], tb["adj_in"][:E])
+    assert torch.equal(ta["adj_eid"][:E], tb["adj_eid"][:E])
+
+
+@pytest.mark.parametrize("group", H1, ids=lambda g: g["tag"])
+def test_one_launch_path_equals_generic_path_golden(group):
+    """h = 1: the one-launch extractor (balanced tile scan, look-back offsets, bitmap / ballot list ranks) and the
+    generic two-launch kernels give identical batches, adjacency lists included - with the hash sampler and with the
+    reference's own draw injected"""
+    from igmc_b200.util_functions import RatingGraph, SubgraphExtractor
+    pu, pv, pl = group["pairs"]
+    G = RatingGraph(group["A"])
+    B = len(group["cases"])
+    exs = [SubgraphExtractor(G, pu, pv, pl, group["cv"], 1, group["ratio"], group["mnph"], seed=99, fast=f)
+           for f in (True, False)]
+    _same_everything(exs[0].extract(idx=np.arange(B)), exs[1].extract(idx=np.arange(B)), B)
+    inj = inject_arrays(group["cases"], exs[0].cap)
+    _same_everything(exs[0].extract(idx=np.arange(B), inject=inj), exs[1].extract(idx=np.arange(B), inject=inj), B)
+    # ragged batch sizes through the same workspace (flag re-arming between launches)
+    for nb in (1, 3, B):
+        _same_everything(exs[0].extract(idx=np.arange(nb)), exs[1].extract(idx=np.arange(nb)), nb)
+
+
+@pytest.mark.parametrize("name,mnph,B", [("ml_100k", 200, 50), ("ml_1m", 100, 50), ("ml_1m_r02", 100, 256),
+                                         ("flixster", 10000, 64), ("tiny", 10, 7)])
+def test_one_launch_path_equals_generic_path_full_size(name, mnph, B):
+    from igmc_b200.data import make_synthetic_dataset
+    from igmc_b200.util_functions import RatingGraph, SubgraphExtractor
+    ds = make_synthetic_dataset(name, seed=0)
+    tu, tv, tl = ds["train"]
+    G = RatingGraph(ds["adj_train"])
+    exs = [SubgraphExtractor(G, tu, tv, tl, ds["class_values"], 1, 1.0, mnph, seed=5, fast=f) for f in (True, False)]
+    rng = np.random.default_rng(3)
+    for _ in range(3):
+        idx = rng.choice(len(tu), B, replace=False)
+        _same_everything(exs[0].extract(idx=idx), exs[1].extract(idx=idx), B)
