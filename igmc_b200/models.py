@@ -610,22 +610,42 @@ class FusedAdam(torch.optim.Optimizer):
 
     def __init__(self, model, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0):
         self.model = model
-        params = [p for (_, _, p) in model._named_order()]
+        # parameter ORDER = model.parameters(), i.e. what the reference's Adam(model.parameters()) (train_eval.py:54)
+        # sees (per conv: basis, att, root, bias): optimizer state_dicts are keyed by position in this list.  The
+        # flat bucket has its own order (model._layout); `_entry` maps a parameter to its slice.
+        params = list(model.parameters())
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False))
         dev = model.flat_params.device
         n = model.flat_params.numel()
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.step_count = torch.zeros(2, dtype=torch.int64, device=dev)   # [step | completion ticket of the kernel]
-        for e, p in zip(model._layout, params):
+        self._entry = {id(p): e for e, (_, _, p) in zip(model._layout, model._named_order())}
+        for p in params:
+            e = self._entry[id(p)]
             self.state[p] = dict(step=self.step_count[0], exp_avg=model._pview(self.exp_avg, e),
                                  exp_avg_sq=model._pview(self.exp_avg_sq, e))
 
+    def state_dict(self):
+        """stock ``torch.optim.Adam`` layout with INDEPENDENT per-parameter tensors: every ``step`` is its own float32
+        scalar (torch's Adam increments each one separately - shared storage would be bumped once per parameter)
+        and the moments are contiguous clones, so the file loads into ``torch.optim.Adam`` of the reference
+        (Main.py:45, train_eval.py:60-62) as well as back into ``FusedAdam``."""
+        sd = super().state_dict()
+        step = float(self.step_count[0].item())
+        out_state = {}
+        for k, st in sd["state"].items():
+            out_state[k] = dict(step=torch.tensor(step, dtype=torch.float32),
+                                exp_avg=st["exp_avg"].detach().clone().contiguous(),
+                                exp_avg_sq=st["exp_avg_sq"].detach().clone().contiguous())
+        return dict(state=out_state, param_groups=sd["param_groups"])
+
     def load_state_dict(self, sd):
         super().load_state_dict(sd)
-        params = [p for (_, _, p) in self.model._named_order()]
+        params = list(self.model.parameters())
         with torch.no_grad():
-            for e, p in zip(self.model._layout, params):
+            for p in params:
+                e = self._entry[id(p)]
                 st = self.state[p]
                 ea, es = self.model._pview(self.exp_avg, e), self.model._pview(self.exp_avg_sq, e)
                 ea.copy_(st["exp_avg"])

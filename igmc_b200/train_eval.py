@@ -278,6 +278,12 @@ def train_multiple_epochs(train_dataset, test_dataset, model, epochs, batch_size
     torch.cuda.synchronize()
     t_start = time.perf_counter()
     gen = torch.Generator().manual_seed(int(seed))
+    if start_epoch > 1:
+        # resumed run: continue the dropout / permutation streams where the checkpointed run left them instead of
+        # replaying epoch 1's (the sampling stream is keyed by the epoch number already)
+        engine.steps = int(optimizer.step_count[0].item())
+        for _ in range(start_epoch - 1):
+            torch.randperm(len(train_dataset), generator=gen)
     for epoch in range(start_epoch, epochs + start_epoch):
         train_loss = train(model, optimizer, train_dataset, device, regression=True, ARR=ARR, epoch=epoch,
                            engine=engine, generator=gen)
@@ -345,9 +351,20 @@ def _eval_sqerr_sum(model, dataset, batch_size):
         batch = dataset.extract_batch(idx)
         _, saved = model._launch_forward(batch, False, drop, y=batch.y, loss_scale=0.0)
         acc += saved["ws"]["sqerr"].sum()
+    _check_dataset(dataset)      # a kernel error during evaluation must not turn into a silent garbage RMSE
     if world > 1:
         dist.all_reduce(acc)
     return acc
+
+
+def _check_dataset(dataset):
+    ex = getattr(dataset, "extractor", None)
+    err = getattr(ex, "err", None)
+    if err is not None:
+        code = int(err.item())
+        if code:
+            from . import _lib
+            raise RuntimeError("igmc_b200 kernel error %d: %s" % (code, _lib.ERR_NAMES.get(code, "?")))
 
 
 def eval_loss(model, loader, device, regression=False, show_progress=False, batch_size=50):
@@ -365,6 +382,10 @@ def eval_rmse(model, loader, device, show_progress=False, batch_size=50):
 def eval_loss_ensemble(model, checkpoints, loader, device, regression=False, show_progress=False, batch_size=50):
     """Reference train_eval.py:208-238: average the predictions of several checkpoints, then MSE."""
     dataset = loader
+    rank, world = _dist_info()
+    dev = model.flat_params.device
+    order = np.arange(len(dataset), dtype=np.int64)
+    shards = [idx for idx, _ in shard_batches(order, batch_size, rank, world) if len(idx)]   # this rank's share
     outs, ys = [], None
     for i, checkpoint in enumerate(checkpoints):
         model.load_state_dict(torch.load(checkpoint))
@@ -372,17 +393,21 @@ def eval_loss_ensemble(model, checkpoints, loader, device, regression=False, sho
         o, y = [], []
         drop = model.make_dropout(False)
         with torch.no_grad():
-            for s in range(0, len(dataset), batch_size):
-                batch = dataset.extract_batch(np.arange(s, min(s + batch_size, len(dataset)), dtype=np.int64))
+            for idx in shards:
+                batch = dataset.extract_batch(idx)
                 pred, _ = model._launch_forward(batch, False, drop)
                 o.append(pred.clone())
                 if i == 0:
                     y.append(batch.y.clone())
-        outs.append(torch.cat(o).view(-1, 1))
+        outs.append(torch.cat(o).view(-1, 1) if o else torch.zeros(0, 1, device=dev))
         if i == 0:
-            ys = torch.cat(y)
+            ys = torch.cat(y) if y else torch.zeros(0, device=dev)
+    _check_dataset(dataset)
     mean = torch.cat(outs, 1).mean(1)
-    return float(((mean - ys) ** 2).sum().item()) / len(dataset)
+    sq = ((mean - ys) ** 2).sum().view(1)
+    if world > 1:
+        dist.all_reduce(sq)
+    return float(sq.item()) / len(dataset)
 
 
 def eval_rmse_ensemble(model, checkpoints, loader, device, show_progress=False, batch_size=50):
@@ -398,9 +423,11 @@ def test_once(test_dataset, model, batch_size, logger=None, ensemble=False, chec
     else:
         rmse = eval_rmse(model, test_dataset, device, batch_size=batch_size)
     duration = time.perf_counter() - t_start
-    print("Test Once RMSE: {:.6f}, Duration: {:.6f}".format(rmse, duration))
+    rank, _ = _dist_info()
+    if rank == 0:
+        print("Test Once RMSE: {:.6f}, Duration: {:.6f}".format(rmse, duration))
     eval_info = {"epoch": "test_once" if not ensemble else "ensemble", "train_loss": 0, "test_rmse": rmse}
-    if logger is not None:
+    if logger is not None and rank == 0:
         logger(eval_info, None, None)
     return rmse
 

@@ -165,3 +165,38 @@ def test_dgcnn_rs_bucket_layout_and_state_dict():
     ds = DS([G(n) for n in (5, 50, 20, 30, 40, 12, 60, 33, 47, 25)])
     m2 = DGCNN_RS(ds, latent_dim=[32, 32, 32, 1], k=0.6, num_relations=5, num_bases=4, regression=True)
     assert m2.k == sorted(g.num_nodes for g in ds)[int(np.ceil(0.6 * len(ds))) - 1]
+
+
+def test_fused_adam_state_dict_loads_into_torch_adam():
+    """an optimizer checkpoint written by FusedAdam must load into the reference's torch.optim.Adam (Main.py:45,
+    train_eval.py:60-62): independent per-parameter `step`s (shared storage would be incremented once per
+    parameter by torch's step()), contiguous moments of the parameters' shapes"""
+    import io
+    from igmc_b200.models import IGMC, FusedAdam
+    torch.manual_seed(0)
+    m = IGMC(4, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True)
+    opt = FusedAdam(m, lr=1e-3)
+    opt.step_count[0] = 7
+    opt.exp_avg.uniform_(-1e-3, 1e-3)
+    opt.exp_avg_sq.uniform_(1e-8, 1e-6)
+    buf = io.BytesIO()
+    torch.save(opt.state_dict(), buf)
+    sd = torch.load(io.BytesIO(buf.getvalue()))
+    steps = [st["step"] for st in sd["state"].values()]
+    assert len(steps) == 20 and len({t.untyped_storage().data_ptr() for t in steps}) == 20
+    params = [torch.nn.Parameter(p.detach().clone()) for p in m.parameters()]
+    ref = torch.optim.Adam(params, lr=1e-3)
+    ref.load_state_dict(sd)
+    for p in params:
+        p.grad = torch.full_like(p, 1e-3)
+    ref.step()
+    assert all(float(ref.state[p]["step"]) == 8.0 for p in params)          # 7 -> 8, not 7 -> 7 + 20
+    for p, q in zip(params, m.parameters()):
+        assert ref.state[p]["exp_avg"].shape == q.shape and ref.state[p]["exp_avg"].is_contiguous()
+    # and back into FusedAdam
+    opt2 = FusedAdam(m, lr=1e-3)
+    opt2.load_state_dict(torch.load(io.BytesIO(buf.getvalue())))   # (torch's Adam stepped the tensors of `sd` in place)
+    assert int(opt2.step_count[0]) == 7
+    for p in m.parameters():   # (the flat buffers also hold alignment padding that is not part of any state entry)
+        assert torch.equal(opt2.state[p]["exp_avg"], opt.state[p]["exp_avg"])
+        assert torch.equal(opt2.state[p]["exp_avg_sq"], opt.state[p]["exp_avg_sq"])
