@@ -98,35 +98,66 @@ class ClockSampler(object):
 _G = {}
 
 
-def _pool_init(adj_blob, cv, mnph):
+def _pool_init(adj_blob, cv, mnph, use_ref):
     import scipy.sparse as ssp
-    from oracle import extract_np
     data, indices, indptr, shape = adj_blob
-    _G["g"] = extract_np.RatingCSR(ssp.csr_matrix((data, indices, indptr), shape=shape))
-    _G["cv"], _G["mnph"] = cv, mnph
+    A = ssp.csr_matrix((data, indices, indptr), shape=shape)
+    _G["cv"], _G["mnph"], _G["ref"] = cv, mnph, None
+    if use_ref:
+        from oracle import ref_shim
+        m = ref_shim.load()                      # the reference's own util_functions.py (oracle/_ref or /root/reference)
+        _G["ref"] = m
+        _G["idx"] = (m.SparseRowIndexer(A), m.SparseColIndexer(A.tocsc()))
+    else:
+        from oracle import extract_np
+        _G["g"] = extract_np.RatingCSR(A)
 
 
 def _pool_extract(args):
-    from oracle import extract_np
     u, v, lab, pid = args
+    m = _G["ref"]
+    if m is not None:   # reference code path: subgraph_extraction_labeling + construct_pyg_graph (util_functions.py:208-297)
+        import random
+        random.seed(pid)
+        out = m.subgraph_extraction_labeling((u, v), _G["idx"][0], _G["idx"][1], 1, 1.0, _G["mnph"], None, None,
+                                             _G["cv"], lab)
+        d = m.construct_pyg_graph(*out)
+        return dict(x=d.x.numpy(), edge_index=d.edge_index.numpy(), edge_type=d.edge_type.numpy(),
+                    y=d.y.numpy().reshape(-1))
+    from oracle import extract_np
     sub = extract_np.extract_subgraph(_G["g"], u, v, 1, 1.0, _G["mnph"], seed=0, pair_id=pid)
     return extract_np.construct_graph(sub, _G["cv"][lab], 1)
 
 
+def _collate(graphs):
+    """PyG Batch.from_data_list of per-graph dicts."""
+    off, xs, eis, ets, ys, bs = 0, [], [], [], [], []
+    for gi, g in enumerate(graphs):
+        n = g["x"].shape[0]
+        xs.append(g["x"]); eis.append(g["edge_index"] + off); ets.append(g["edge_type"]); ys.append(g["y"])
+        bs.append(np.full(n, gi, np.int64))
+        off += n
+    return dict(x=np.concatenate(xs).astype(np.float32), edge_index=np.concatenate(eis, 1).astype(np.int64),
+                edge_type=np.concatenate(ets).astype(np.int64), y=np.concatenate(ys).astype(np.float32),
+                batch=np.concatenate(bs), num_graphs=len(graphs))
+
+
 class CpuReference(object):
-    """The reference's CPU train path: per-pair extraction in a process pool (DataLoader workers,
-    train_eval.py:40-45) + PyG-1.4.2-formulation model step on all host threads."""
+    """The reference's CPU train path: per-pair extraction in a persistent process pool (its DataLoader workers,
+    train_eval.py:40-45) running the reference's OWN extraction code when it is present (oracle/_ref, built by
+    oracle/make_ref.py; else the numpy port), + the PyG-1.4.2-formulation model step on the host threads."""
 
     def __init__(self, ds, batch, cores=None, model_kind="igmc", k=30):
         import multiprocessing as mp
         import torch
-        from oracle import pyg_restated
+        from oracle import pyg_restated, ref_shim
         self.ds, self.B = ds, batch
         self.cores = cores or os.cpu_count()
+        self.use_ref = ref_shim.available()
         A = ds["adj_train"]
         self.pool = mp.get_context("fork").Pool(self.cores, _pool_init,
                                                 ((A.data, A.indices, A.indptr, A.shape), ds["class_values"],
-                                                 ds["max_nodes_per_hop"]))
+                                                 ds["max_nodes_per_hop"], self.use_ref))
         self.threads = min(self.cores, 16)
         torch.set_num_threads(self.threads)
         self.pyg = pyg_restated
@@ -145,12 +176,13 @@ class CpuReference(object):
         self.model_kind = model_kind
         self.opt = torch.optim.Adam(self.model.parameters(), lr=LR)
 
-    def extract(self, idx):
-        from oracle import extract_np
+    def extract_graphs(self, idx):
         tu, tv, tl = self.ds["train"]
-        graphs = self.pool.map(_pool_extract, [(int(tu[i]), int(tv[i]), int(tl[i]), int(i)) for i in idx],
-                               chunksize=max(1, len(idx) // (4 * self.cores)))
-        return extract_np.collate(graphs)
+        return self.pool.map(_pool_extract, [(int(tu[i]), int(tv[i]), int(tl[i]), int(i)) for i in idx],
+                             chunksize=max(1, len(idx) // (8 * self.cores)))
+
+    def extract(self, idx):
+        return _collate(self.extract_graphs(idx))
 
     def model_step(self, nb):
         tb = self.pyg.to_torch_batch(nb)
@@ -163,29 +195,36 @@ class CpuReference(object):
             loss, _ = self.pyg.train_loss(self.model, tb, ARR)
         loss.backward()
         self.opt.step()
-        return float(loss)
-
-    def step(self, idx):
-        return self.model_step(self.extract(idx))
+        return float(loss.detach())
 
     def close(self):
         self.pool.terminate()
 
 
 def run_reference(args, ds, B, rank):
-    """--impl reference: whole steps on the host cores; throughput of the serial pipeline and the
-    overlapped estimate min(extraction, model) are both reported (value = overlapped, as the reference
-    overlaps the two with DataLoader workers)."""
+    """--impl reference / cpu_baseline: the two halves of the reference's CPU step are timed separately - extraction
+    as ONE pool.map over a large set of pairs (>= 1000: steady state of the worker pool, not per-batch fork/IPC jitter)
+    and the model step on pre-extracted batches - and combined as the reference overlaps them (DataLoader workers):
+    value = min(extraction rate, model rate); the serial figure is listed too."""
     import torch
     ref = CpuReference(ds, B, model_kind=getattr(args, "model", "igmc"), k=getattr(args, "k", None) or 30)
     rng = np.random.default_rng(123)
     n = len(ds["train"][0])
-    # give the reference its best thread count for the small per-edge bmm ops (oversubscription hurts it)
-    nb0 = ref.extract(rng.choice(n, B, replace=False))
     static = ds["name"] == "flixster"   # the reference pre-extracts this dataset once (MyDataset): model-bound steps
+    steps = max(1, int(args.steps))
+    ref.extract_graphs(rng.choice(n, min(n, 4 * ref.cores), replace=False))          # warm the workers
+    n_pairs = min(n, max(1000, 4 * B))
+    idx_all = rng.choice(n, n_pairs, replace=False)
+    t = time.perf_counter()
+    graphs = ref.extract_graphs(idx_all)
+    t_ext = time.perf_counter() - t
+    ext_rate = n_pairs / t_ext
+    batches = [_collate(graphs[s * B:(s + 1) * B]) for s in range(min(steps + 1, n_pairs // B))]
+    nb0 = batches[0]
     if getattr(args, "model", "igmc") == "dgcnn_rs" and not getattr(args, "k", None):
         nn_ = np.sort(np.bincount(nb0["batch"], minlength=B))   # percentile rule of models.py:69-73 on one batch
         ref.build_model("dgcnn_rs", max(10, int(nn_[int(np.ceil(0.6 * len(nn_))) - 1])))
+    # the reference's best thread count for the small per-edge bmm ops (oversubscription hurts it)
     best = (1e30, ref.threads)
     for th in sorted({8, 16, 32, 64, ref.cores} & set(range(1, ref.cores + 1))):
         torch.set_num_threads(th)
@@ -195,31 +234,91 @@ def run_reference(args, ds, B, rank):
         best = min(best, (time.perf_counter() - t, th))
     ref.threads = best[1]
     torch.set_num_threads(ref.threads)
-    for _ in range(max(1, min(args.warmup, 2))):
-        ref.step(rng.choice(n, B, replace=False))
-    budget, t_ext, t_mod, steps = 120.0, 0.0, 0.0, 0
+    budget, t_mod, done = 150.0, 0.0, 0
     t0 = time.perf_counter()
-    while steps < args.steps and (time.perf_counter() - t0) < budget:
-        idx = rng.choice(n, B, replace=False)
+    while done < steps and (time.perf_counter() - t0) < budget:
         a = time.perf_counter()
-        nb = ref.extract(idx)
-        b = time.perf_counter()
-        ref.model_step(nb)
-        c = time.perf_counter()
-        t_ext += b - a
-        t_mod += c - b
-        steps += 1
+        ref.model_step(batches[1 + done % (len(batches) - 1)] if len(batches) > 1 else nb0)
+        t_mod += time.perf_counter() - a
+        done += 1
     ref.close()
-    ext_rate, mod_rate = B * steps / t_ext, B * steps / t_mod
+    mod_rate = B * done / t_mod
     value = mod_rate if static else min(ext_rate, mod_rate)
-    return dict(value=value, steps=steps, ms_per_step=1000.0 * B / value, cores=ref.cores,
-                extraction_subgraphs_per_s=ext_rate, model_subgraphs_per_s=mod_rate,
-                serial_subgraphs_per_s=B * steps / (t_ext + t_mod),
-                sample="%d steps of %d subgraphs (extraction in a %d-process pool + PyG-1.4.2-formulation "
-                       "fwd/bwd/Adam on %d torch threads, best of {8,16,32,64,all}); %s"
-                       % (steps, B, ref.cores, ref.threads,
+    ext_kind = "reference" if ref.use_ref else "port"
+    return dict(value=value, steps=done, ms_per_step=1000.0 * B / value, cores=ref.cores,
+                extraction_subgraphs_per_s=ext_rate, model_subgraphs_per_s=mod_rate, extraction_kind=ext_kind,
+                serial_subgraphs_per_s=1.0 / (1.0 / ext_rate + 1.0 / mod_rate),
+                sample="extraction: %d pairs in one map over a %d-process pool (%s); model: %d steps of %d subgraphs, "
+                       "PyG-1.4.2-formulation fwd/bwd/Adam on %d torch threads (best of {8,16,32,64,all}); %s"
+                       % (n_pairs, ref.cores,
+                          "the reference's own subgraph_extraction_labeling + construct_pyg_graph" if ref.use_ref
+                          else "numpy port of the reference's extraction", done, B, ref.threads,
                           "value=model rate: the static dataset is pre-extracted once" if static else
                           "value=min(extraction, model) as the reference overlaps them"))
+
+
+def cpu_baseline_dict(r):
+    # kind: the model half is a restatement (PyG 1.4.2 is not installable here), so the arm as a whole is a port;
+    # the extraction half runs the reference's own code whenever oracle/_ref (or /root/reference) is present
+    return {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
+            "extraction_kind": r["extraction_kind"], "model_kind": "port (PyG 1.4.2 RGCNConv restated)",
+            "sample": r["sample"], "extraction_subgraphs_per_s": r["extraction_subgraphs_per_s"],
+            "model_subgraphs_per_s": r["model_subgraphs_per_s"],
+            "serial_subgraphs_per_s": r["serial_subgraphs_per_s"]}
+
+
+def make_config(desc, G, world, no_graph=False):
+    """identical keys on both arms (the driver compares the dicts); the l2 / graph / pipeline entries describe how
+    OUR arm is timed, the reference arm times whole CPU steps on the same workload"""
+    return {"workload": desc, "global_batch": G, "parallelism": "dp%d" % world,
+            "l2": "flushed between timed steps (256 MiB fill), per-step CUDA events summed",
+            "cuda_graph": not no_graph,
+            "pipeline": "extraction of batch k+1 overlaps the model step of batch k (two graph branches)"}
+
+
+def gpu_baseline(ds, train, steps_idx, B, model_kind="igmc", steps=12):
+    """BASELINE config 2 / SURVEY 8(d): "vs PyG on the same B200".  PyG is not installable, so this is the restated
+    PyG-1.4.2 formulation (index_select of per-edge weights + bmm + scatter-mean, autograd, torch.optim.Adam) run with
+    torch CUDA ops on the same batches - what the reference does when a GPU is present (train_eval.py:20,159-177).
+    The batches come from OUR extractor (collated on the device), so only the model half is the baseline's."""
+    import torch
+    from oracle import pyg_restated
+    dev = torch.device("cuda")
+    torch.manual_seed(1)
+    if model_kind != "igmc":
+        return None
+    ref = pyg_restated.IGMCRef(4, (32, 32, 32, 32), ds["num_relations"], 4, ds["adj_dropout"]).to(dev).train()
+    opt = torch.optim.Adam(ref.parameters(), lr=LR)
+    ex = train.extractor
+    tbs = []
+    for k in range(min(4, len(steps_idx))):
+        b = ex.extract(idx=steps_idx[k])
+        tbs.append(dict(x=b.x.clone(), edge_index=b.edge_index.clone(), edge_type=b.edge_type.clone(), y=b.y.clone()))
+
+    def one(tb):
+        opt.zero_grad()
+        loss, _ = pyg_restated.train_loss(ref, tb, ARR)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for k in range(3):
+        one(tbs[k % len(tbs)])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(steps):
+        one(tbs[k % len(tbs)])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    peak = torch.cuda.max_memory_allocated() / 2 ** 30
+    del ref, opt, tbs
+    torch.cuda.empty_cache()
+    return {"value": B / (ms / 1000.0), "unit": "subgraphs/s", "ms_per_step": ms, "steps": steps,
+            "kind": "port (PyG-1.4.2 formulation: index_select + bmm + scatter-mean, autograd, torch.optim.Adam; "
+                    "torch CUDA ops on the same B200, model half only - batches pre-extracted on the device)",
+            "peak_mem_gib": round(peak, 2)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -417,30 +516,26 @@ def run_ours(args):
         # branch of the step graph and get their own line (`roofline.extract`)
         dom = max(("forward", "backward"), key=lambda n: kern_ms[n])
         peak, peak_src = peaks()
-        traffic = None
+        traffic = None     # DRAM bytes per launch from an `ncu --set full` capture OF THIS workload + model, else null
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             with open(tp) as f:
-                traffic = json.load(f).get(dom)
+                traffic = json.load(f).get("%s/%s" % (args.workload, args.model), {}).get(dom)
         per_launch_bytes = ab[dom] / nb_batches
         achieved = per_launch_bytes / (kern_ms[dom] * 1e-3) / 1e9
         step_bytes = ab["step"] / nb_batches
-        cpu = None
+        cpu, gpub = None, None
         if not args.skip_cpu_baseline:
+            if world == 1 and not static:
+                gpub = gpu_baseline(ds, train, [steps_idx[value_first + k] for k in range(4)], B, args.model)
             ns = argparse.Namespace(steps=args.cpu_steps, warmup=1, model=args.model, k=getattr(args, "k", 30))
-            r = run_reference(ns, ds, B, 0)
-            cpu = {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
-                   "sample": r["sample"], "extraction_subgraphs_per_s": r["extraction_subgraphs_per_s"],
-                   "model_subgraphs_per_s": r["model_subgraphs_per_s"]}
+            cpu = cpu_baseline_dict(run_reference(ns, ds, B, 0))
         out = {
             "metric": "enclosing-subgraphs/sec (train step)", "value": value, "unit": "subgraphs/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "real (tests/golden/flixster_ratings.npz)" if ds.get("real") else "synthetic",
-            "config": {"workload": desc, "global_batch": G, "parallelism": "dp%d" % world,
-                       "l2": "flushed between timed steps (256 MiB fill), per-step CUDA events summed",
-                       "cuda_graph": not args.no_graph,
-                       "pipeline": "extraction of batch k+1 overlaps the model step of batch k (two graph branches)"},
+            "config": make_config(desc, G, world, args.no_graph),
             "clocks": clk,
             "e2e": {"value": G * K / e2e_s, "unit": "subgraphs/s", "h2d_bytes_per_step": (B + 4) * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": 1000.0 * e2e_s / K,
@@ -460,6 +555,7 @@ def run_ours(args):
                                              "kernels of the previous batch"},
                          "step_frac": (step_bytes / (dev_ms / K * 1e-3) / 1e9) / peak},
             "cpu_baseline": cpu,
+            "gpu_baseline": gpub,
             "batch_stats": {k: v / stats["B"] for k, v in stats.items() if k != "B"},
             "wall_s_timed_region": wall,
         }
@@ -503,15 +599,15 @@ def main():
         preset, B, desc = WORKLOADS[args.workload]
         ds = make_synthetic_dataset(preset, seed=0)
         r = run_reference(args, ds, B, rank)
+        world = max(1, int(args.gpus))
         line = {"impl": "reference", "metric": "enclosing-subgraphs/sec (train step)", "value": r["value"],
                 "unit": "subgraphs/s", "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup,
                 "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "real (tests/golden/flixster_ratings.npz)" if ds.get("real") else "synthetic",
-                "config": {"workload": desc, "global_batch": B, "parallelism": "cpu"},
-                "cpu_baseline": {"value": r["value"], "unit": "subgraphs/s", "cores": r["cores"], "kind": "port",
-                                 "sample": r["sample"],
-                                 "extraction_subgraphs_per_s": r["extraction_subgraphs_per_s"],
-                                 "model_subgraphs_per_s": r["model_subgraphs_per_s"]},
+                "config": make_config(desc, B * world, world),
+                "reference_note": "one CPU process on the host cores (the reference has no data parallelism, "
+                                  "train_eval.py:20); `config` is our arm's so that both lines name the same workload",
+                "cpu_baseline": cpu_baseline_dict(r),
                 "e2e": {"value": r["value"], "unit": "subgraphs/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}}
         emit(line)

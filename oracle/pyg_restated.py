@@ -28,8 +28,9 @@ import torch.nn.functional as F
 
 
 def scatter_mean(src, index, dim_size):
-    out = torch.zeros(dim_size, src.shape[1], dtype=src.dtype).index_add_(0, index, src)
-    cnt = torch.zeros(dim_size, dtype=src.dtype).index_add_(0, index, torch.ones_like(index, dtype=src.dtype))
+    out = torch.zeros(dim_size, src.shape[1], dtype=src.dtype, device=src.device).index_add_(0, index, src)
+    cnt = torch.zeros(dim_size, dtype=src.dtype, device=src.device).index_add_(
+        0, index, torch.ones_like(index, dtype=src.dtype))
     return out / cnt.clamp(min=1).unsqueeze(1)
 
 
@@ -39,7 +40,8 @@ def dropout_adj(edge_index, edge_attr, p, training=True, keep_mask=None, generat
     if not training or p == 0.0:
         return edge_index, edge_attr
     if keep_mask is None:
-        keep_mask = torch.bernoulli(torch.full((edge_index.shape[1],), 1 - p), generator=generator).bool()
+        keep_mask = torch.bernoulli(torch.full((edge_index.shape[1],), 1 - p, device=edge_index.device),
+                                    generator=generator).bool()
     return edge_index[:, keep_mask], edge_attr[keep_mask]
 
 
@@ -70,7 +72,7 @@ class RGCNConvRef(nn.Module):
         if self.aggr == "mean_all":
             agg = scatter_mean(msg, dst, n)
         elif self.aggr == "add":
-            agg = torch.zeros(n, msg.shape[1], dtype=msg.dtype).index_add_(0, dst, msg)
+            agg = torch.zeros(n, msg.shape[1], dtype=msg.dtype, device=msg.device).index_add_(0, dst, msg)
         else:
             raise ValueError(self.aggr)
         return agg + x @ self.root + self.bias
@@ -129,15 +131,15 @@ def global_sort_pool(x, batch, k, num_graphs=None):
     counts = torch.bincount(batch, minlength=B)
     nmax = int(counts.max())
     start = torch.cumsum(counts, 0) - counts
-    pos = torch.arange(x.shape[0]) - start[batch]
-    dense = torch.full((B, nmax, D), fill, dtype=x.dtype)
+    pos = torch.arange(x.shape[0], device=x.device) - start[batch]
+    dense = torch.full((B, nmax, D), fill, dtype=x.dtype, device=x.device)
     dense[batch, pos] = x
     _, perm = torch.sort(dense[:, :, -1], dim=-1, descending=True, stable=True)
     dense = torch.gather(dense, 1, perm.unsqueeze(-1).expand(-1, -1, D))
     if nmax >= k:
         dense = dense[:, :k]
     else:
-        dense = torch.cat([dense, torch.full((B, k - nmax, D), fill, dtype=x.dtype)], 1)
+        dense = torch.cat([dense, torch.full((B, k - nmax, D), fill, dtype=x.dtype, device=x.device)], 1)
     dense = torch.where(dense == fill, torch.zeros_like(dense), dense)
     return dense.reshape(B, k * D)
 
@@ -204,9 +206,14 @@ def train_loss(model, batch, ARR=0.001, edge_keep=None, hidden_keep=None):
     return loss, out
 
 
-def to_torch_batch(np_batch, dtype=torch.float32):
-    return dict(x=torch.from_numpy(np_batch["x"]).to(dtype),
-                edge_index=torch.from_numpy(np_batch["edge_index"]),
-                edge_type=torch.from_numpy(np_batch["edge_type"]),
-                y=torch.from_numpy(np_batch["y"]).to(dtype),
-                batch=torch.from_numpy(np_batch["batch"]), num_graphs=np_batch["num_graphs"])
+def to_torch_batch(np_batch, dtype=torch.float32, device=None):
+    """``device``: the restatement is device-agnostic; bench.py's ``gpu_baseline`` runs it with torch CUDA ops (the
+    reference itself puts its model on CUDA when one exists, train_eval.py:20)."""
+    d = dict(x=torch.from_numpy(np_batch["x"]).to(dtype),
+             edge_index=torch.from_numpy(np_batch["edge_index"]),
+             edge_type=torch.from_numpy(np_batch["edge_type"]),
+             y=torch.from_numpy(np_batch["y"]).to(dtype),
+             batch=torch.from_numpy(np_batch["batch"]), num_graphs=np_batch["num_graphs"])
+    if device is not None:
+        d = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in d.items()}
+    return d

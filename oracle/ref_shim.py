@@ -16,7 +16,13 @@ import random
 import sys
 import types
 
+# the reference checkout (this container), else the vendored copy oracle/make_ref.py placed under oracle/_ref/
+# (git-ignored build product that travels to the GPU box with the snapshot)
+_VENDORED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REF_DIR = os.environ.get("IGMC_REFERENCE_DIR", "/root/reference")
+if not os.path.isfile(os.path.join(REF_DIR, "util_functions.py")) and \
+        os.path.isfile(os.path.join(_VENDORED, "util_functions.py")):
+    REF_DIR = _VENDORED
 
 
 def available():
