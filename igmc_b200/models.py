@@ -456,8 +456,8 @@ class DGCNN_RS(IGMC):
     flat bucket: ``convs[-1].basis/root/bias`` are strided views of a 32-wide slot whose other columns are zero and stay
     zero (their gradients are exactly zero).  ``state_dict`` keys and shapes are the reference's.
 
-    ``k < 1`` is the reference's percentile rule (models.py:69-73); for datasets above 2000 graphs the node counts are
-    taken from 2000 evenly spaced graphs instead of all of them (the dynamic dataset extracts on access).
+    ``k < 1`` is the reference's percentile rule over ALL subgraphs (models.py:69-73); the node counts come from
+    ``dataset.node_counts()`` (large GPU batches) instead of a Python loop over ``dataset``.
     """
 
     C1, C2, KW2 = 16, 32, 5   # conv1d_channels and the second kernel width (models.py:75-79)
@@ -484,9 +484,10 @@ class DGCNN_RS(IGMC):
         if k < 1:   # transform percentile to number (models.py:69-73)
             if isinstance(dataset, int):
                 raise ValueError("a percentile k needs the dataset")
-            n = len(dataset)
-            idxs = range(n) if n <= 2000 else [int(round(i * (n - 1) / 1999.0)) for i in range(2000)]
-            node_nums = sorted(int(dataset[i].num_nodes) for i in idxs)
+            if hasattr(dataset, "node_counts"):      # all subgraphs, extracted in large GPU batches
+                node_nums = sorted(int(v) for v in dataset.node_counts())
+            else:
+                node_nums = sorted(int(g.num_nodes) for g in dataset)
             k = node_nums[int(math.ceil(k * len(node_nums))) - 1]
             k = max(10, k)
         self.k = int(k)

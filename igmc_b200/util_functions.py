@@ -430,11 +430,35 @@ class MyDynamicDataset(object):
         return self.extractor.extract(idx=indices)
 
     def get(self, idx):
-        b = self.extractor.extract(idx=np.asarray([idx], dtype=np.int64))
+        b = self.extractor.extract(idx=np.asarray([self._index(idx)], dtype=np.int64))
         return Data(b.x, b.edge_index, edge_type=b.edge_type, y=b.y)
 
+    def _index(self, idx):
+        """PyG ``Dataset.__getitem__`` semantics for an int: negative indices count from the end, anything outside
+        raises IndexError - which is what ends the reference's ``for g in dataset`` loops (models.py:71)."""
+        idx = int(idx)
+        n = len(self)
+        if idx < -n or idx >= n:
+            raise IndexError("index %d out of range for a dataset of %d subgraphs" % (idx, n))
+        return idx + n if idx < 0 else idx
+
     def __getitem__(self, idx):
-        return self.get(int(idx))
+        return self.get(idx)
+
+    def __iter__(self):
+        for k in range(len(self)):
+            yield self.get(k)
+
+    def node_counts(self, chunk=2048):
+        """number of nodes of every subgraph (what ``[g.num_nodes for g in dataset]`` gives, models.py:71), extracted
+        in large batches instead of one by one"""
+        out = []
+        for s0 in range(0, len(self), chunk):
+            idx = np.arange(s0, min(s0 + chunk, len(self)), dtype=np.int64)
+            b = self.extract_batch(idx)
+            b.check()
+            out.append(np.diff(b._priv["node_ptr"][:len(idx) + 1].cpu().numpy()))
+        return np.concatenate(out) if out else np.zeros(0, np.int64)
 
 
 class StaticStore(object):
@@ -579,5 +603,8 @@ class MyDataset(MyDynamicDataset):
         return self.store.extract(idx=indices)
 
     def get(self, idx):
-        b = self.store.extract(idx=np.asarray([idx], dtype=np.int64))
+        b = self.store.extract(idx=np.asarray([self._index(idx)], dtype=np.int64))
         return Data(b.x, b.edge_index, edge_type=b.edge_type, y=b.y)
+
+    def node_counts(self, chunk=2048):
+        return np.diff(self.store.node_off.cpu().numpy()).astype(np.int64)

@@ -62,12 +62,22 @@ class RGCNConvRef(nn.Module):
         for p in (self.basis, self.att, self.root, self.bias):
             p.data.uniform_(-bound, bound)
 
+    # "bmm": the reference-era message function (per-edge weight gather + bmm) - the formulation bench.py times as the
+    # baseline.  "transform": the same sum re-associated (x W_r for every relation first, then a row gather); it avoids
+    # the [E, in, out] tensor so that fp64 parity tests can run BASELINE-size batches (tests/test_oracle_model.py pins
+    # the two against each other).
+    formulation = "bmm"
+
     def forward(self, x, edge_index, edge_type):
         src, dst = edge_index[0], edge_index[1]
         w = torch.matmul(self.att, self.basis.view(self.num_bases, -1))
         w = w.view(self.num_relations, self.in_channels, self.out_channels)
-        w_e = torch.index_select(w, 0, edge_type)                     # [E, in, out]
-        msg = torch.bmm(x[src].unsqueeze(1), w_e).squeeze(1)          # [E, out]
+        if self.formulation == "transform":
+            y = torch.einsum("ni,rio->nro", x, w)                        # [N, R, out]
+            msg = y[src, edge_type]                                       # [E, out]
+        else:
+            w_e = torch.index_select(w, 0, edge_type)                     # [E, in, out]
+            msg = torch.bmm(x[src].unsqueeze(1), w_e).squeeze(1)          # [E, out]
         n = x.shape[0]
         if self.aggr == "mean_all":
             agg = scatter_mean(msg, dst, n)
@@ -186,6 +196,13 @@ class DGCNN_RSRef(nn.Module):
                 z = F.dropout(z, p=0.5, training=True)
         out = self.lin2(z)[:, 0]
         return (out, cs) if return_states else out
+
+
+def set_formulation(model, formulation):
+    """switch every conv of a restated model between the "bmm" and "transform" message formulations"""
+    for c in model.convs:
+        c.formulation = formulation
+    return model
 
 
 def arr_regulariser(model):
