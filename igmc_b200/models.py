@@ -316,6 +316,14 @@ class IGMC(nn.Module):
                           _lib.ptr(self._wprep_buf()) if ws["cluster"] > 0 else None,
                           _lib.ptr(getattr(self, "_prof_buf", None)))
 
+    def prep_weights(self, mark=False):
+        """launch igmc_prep_weights on the current stream; ``mark`` lets the next forward skip its own launch (the
+        train engine issues it early so that the extraction branch of the step can be ordered after it)."""
+        _lib.check(_lib.load().igmc_prep_weights(C.byref(self._cmodel), self.flat_params.data_ptr(),
+                                                 self._wprep_buf().data_ptr(), _stream_ptr()), "igmc_prep_weights")
+        if mark:
+            self._prepped = True
+
     def _wprep_buf(self):
         if self._wprep is None or self._wprep.device != self.flat_params.device:
             n = len(self.convs) * 2 * HID * ((self.num_relations + 1) * HID + 4)
@@ -351,9 +359,9 @@ class IGMC(nn.Module):
         ws = self._workspace(batch, training)
         S = self._saved_struct(ws, p["node_cap"])
         d, keep = drop
-        if ws["cluster"] > 0:   # W_r / W_r^T of the current parameters (one tiny launch per step)
-            _lib.check(lib.igmc_prep_weights(C.byref(self._cmodel), self.flat_params.data_ptr(),
-                                             self._wprep_buf().data_ptr(), _stream_ptr()), "igmc_prep_weights")
+        if ws["cluster"] > 0 and not self.__dict__.pop("_prepped", False):
+            # W_r / W_r^T of the current parameters (one tiny launch per step, unless prep_weights() just ran)
+            self.prep_weights()
         _lib.check(lib.igmc_forward(C.byref(self._cmodel), self.flat_params.data_ptr(), p["node_label"].data_ptr(),
                                     p["node_ptr"].data_ptr(), p["edge_ptr"].data_ptr(), C.byref(adj_c),
                                     batch.num_graphs, p["n_cap"], C.byref(d), int(training), C.byref(S),

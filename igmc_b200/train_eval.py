@@ -195,6 +195,12 @@ class TrainEngine(object):
     def _launch_pipe(self, nb, G, slot, nb_next):
         B, buf = self.B, self.stepbuf_dev
         main = torch.cuda.current_stream()
+        if nb > 0 and self.model._plans and max(self.model._plans.values()) > 0:
+            # the weight-prep launch goes first and the extraction branch is ordered AFTER it: forward and extraction
+            # then become runnable together and the forward's one-per-SM clusters are placed before the extraction
+            # CTAs, which pack two per SM on what is left.  Extraction first spreads over 50 SMs and leaves fewer
+            # than the 100 free SMs the forward needs (measured: 235 us per step instead of 180, profiles/README.md)
+            self.model.prep_weights(mark=True)
         if nb_next > 0:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
