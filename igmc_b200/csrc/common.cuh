@@ -145,6 +145,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                : "memory");
 }
 
+__device__ __forceinline__ long long igmc_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int igmc_smid() {
+  int s;
+  asm volatile("mov.u32 %0, %smid;" : "=r"(s));
+  return s;
+}
+
 #define IGMC_CUDA_CHECK_LAUNCH()                      \
   do {                                                \
     cudaError_t e__ = cudaGetLastError();             \

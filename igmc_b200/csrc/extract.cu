@@ -558,6 +558,11 @@ k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint
   const unsigned lt_mask = (1u << lane) - 1u;
   const uint64_t seed = seed_dev ? *seed_dev : seed_val;
   int* flags = W.sync;   // [B] "counts published" flags + [1] completion ticket (all zero between launches)
+  // debug aid (the hop table is unused for h = 1): low 32 bits of the CTA's start / end wall clock and its SM
+  if (tid == 0 && W.hop_off) {
+    W.hop_off[(size_t)g * 2 * (IGMC_MAX_HOP + 1) + 5] = (int)(igmc_globaltimer() & 0x7fffffff);
+    W.hop_off[(size_t)g * 2 * (IGMC_MAX_HOP + 1) + 7] = igmc_smid();
+  }
   int i, j, lab;
   int64_t pid;
   resolve_pair(P, g, &i, &j, &lab, &pid);
@@ -841,6 +846,7 @@ k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint
   // the last CTA to finish re-arms the flags for the next launch
   __syncthreads();
   if (tid == 0) {
+    if (W.hop_off) W.hop_off[(size_t)g * 2 * (IGMC_MAX_HOP + 1) + 6] = (int)(igmc_globaltimer() & 0x7fffffff);
     __threadfence();
     if (atomicAdd(&flags[B], 1) == B - 1) {
       for (int q = 0; q <= B; ++q) flags[q] = 0;

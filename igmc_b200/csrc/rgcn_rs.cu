@@ -394,6 +394,9 @@ __device__ __forceinline__ Split own_range(int n, int rank, int CL) {
 __host__ __device__ __forceinline__ int own_cap_of(int n_cap, int CL) { return ((n_cap + CL - 1) / CL + GN - 1) / GN * GN; }
 
 #define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
+// debug: wall-clock (globaltimer, ns) of a CTA's start / end and the SM it ran on - slots 50..52 of its prof row
+#define IGMC_WALL(i_) do { if (S.prof && threadIdx.x == 0) { S.prof[(size_t)blockIdx.x * 64 + (i_)] = igmc_globaltimer(); \
+                                                              S.prof[(size_t)blockIdx.x * 64 + 52] = igmc_smid(); } } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // per-step weight preparation.  slab(l, dir) = Bn[n][KS]  (n = output channel, KS = Ktot + 4):
@@ -484,6 +487,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const Split own = own_range(n, rank, CL);
   const int n_own = own.hi - own.lo;
   IGMC_STAMP(0);
+  IGMC_WALL(50);
 
   // weights of a layer: the [W_r ; root] slab prepared by igmc_prep_weights, one bulk (TMA) copy issued by a single
   // thread; every thread waits on mbar[1] (phase = layer parity) right before the layer's tensor-core tiles, so the
@@ -671,7 +675,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     }
   }
 
-  if (rank != 0 || ext) return;
+  if (rank != 0 || ext) { IGMC_WALL(51); return; }
   // ---- readout (models.py:205-215), one CTA of the cluster ----
   __syncthreads();
   for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
@@ -727,6 +731,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     }
   }
   IGMC_STAMP(2 + 6 * L);
+  IGMC_WALL(51);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -807,6 +812,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
   float* gp = gpart + ((size_t)g * CL + rank) * (size_t)igmc_raw_count(R, in0, L);
   IGMC_STAMP(0);
+  IGMC_WALL(50);
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -1172,6 +1178,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     if (CL > 1 && l > 0) cluster_wait();   // nothing is exchanged after layer 0
     IGMC_STAMP(sb + 4);
   }
+  IGMC_WALL(51);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -33,7 +33,11 @@ def test_reference_main_runs_on_the_drop_in_modules(tmp_path, extra):
     env["PYTHONPATH"] = os.pathsep.join([os.path.join(ROOT, "tests", "main_stubs"), os.path.join(ROOT, "shims"), ROOT,
                                          env.get("PYTHONPATH", "")])
     env["MPLBACKEND"] = "Agg"
-    cmd = [sys.executable, _main_py(), "--data-name", "ml_1m", "--testing", "--epochs", "20", "--save-interval", "5",
+    # the script's own directory leads sys.path: run a copy from the (otherwise empty) working directory so that
+    # `from util_functions import *` resolves to shims/, not to the reference file that sits next to Main.py
+    import shutil
+    shutil.copyfile(_main_py(), str(tmp_path / "Main.py"))
+    cmd = [sys.executable, "Main.py", "--data-name", "ml_1m", "--testing", "--epochs", "20", "--save-interval", "5",
            "--ensemble", "--keep-old", "--max-nodes-per-hop", "10", "--batch-size", "50", "--lr-decay-step-size", "8",
            "--save-appendix", "_t"] + extra
     r = subprocess.run(cmd, cwd=str(tmp_path), env=env, capture_output=True, text=True, timeout=600)
