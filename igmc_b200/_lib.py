@@ -77,7 +77,8 @@ class Dropout(C.Structure):
 
 class Saved(C.Structure):
     _fields_ = [("states", vp), ("zsave", vp), ("inv_deg", vp), ("feat", vp), ("hid", vp),
-                ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp), ("wprep", vp), ("prof", vp)]
+                ("hid_gscale", vp), ("pred", vp), ("target", vp), ("node_cap", C.c_int32), ("dstate", vp), ("wprep", vp), ("prof", vp),
+                ("gate", vp)]
 
 
 class Stage(C.Structure):
@@ -130,6 +131,7 @@ _SIGS = {
     "igmc_comm_close": [vp],
     "igmc_comm_free": [vp],
     "igmc_prep_weights": [C.POINTER(Model), vp, vp, vp],
+    "igmc_gate_wait": [vp, C.c_int, C.c_int, vp],
     "igmc_build_info": [],
     "igmc_model_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int],
     "igmc_sortpool_plan": [C.POINTER(SortPool), C.c_int, C.c_int],

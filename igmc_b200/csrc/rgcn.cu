@@ -602,6 +602,12 @@ int rs_stage_lists(const igmc_model_t* M, const int32_t* node_ptr, const int32_t
                    cudaStream_t st);
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st);
+int rs_gate_wait(int* gate, int target, int timeout_us, cudaStream_t st);
+
+extern "C" int igmc_gate_wait(int32_t* gate, int target, int timeout_us, void* stream) {
+  if (!gate || target < 0 || timeout_us < 0) return -21;
+  return rs_gate_wait(gate, target, timeout_us, (cudaStream_t)stream);
+}
 
 extern "C" int igmc_prep_weights(const igmc_model_t* M, const float* params, float* wprep, void* stream) {
   int rc = check_model(M);

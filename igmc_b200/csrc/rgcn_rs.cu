@@ -488,6 +488,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const int n_own = own.hi - own.lo;
   IGMC_STAMP(0);
   IGMC_WALL(50);
+  if (S.gate && tid == 0) atomicAdd(S.gate, 1);   // "this CTA is resident" (igmc_gate_wait)
 
   // weights of a layer: the [W_r ; root] slab prepared by igmc_prep_weights, one bulk (TMA) copy issued by a single
   // thread; every thread waits on mbar[1] (phase = layer parity) right before the layer's tensor-core tiles, so the
@@ -1388,6 +1389,22 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
                           node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, img, err);
   return launch_cluster(rs::k_backward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
                         edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, img, err);
+}
+
+namespace rs {
+__global__ void k_gate_wait(int* gate, int target, long long timeout_ns) {
+  if (threadIdx.x == 0) {
+    const long long t0 = igmc_globaltimer();
+    while (*reinterpret_cast<volatile int*>(gate) < target && igmc_globaltimer() - t0 < timeout_ns) __nanosleep(100);
+    *gate = 0;
+  }
+}
+}  // namespace rs
+
+int rs_gate_wait(int* gate, int target, int timeout_us, cudaStream_t st) {
+  rs::k_gate_wait<<<1, 32, 0, st>>>(gate, target, (long long)timeout_us * 1000);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e + 1000;
 }
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st) {

@@ -314,7 +314,8 @@ class IGMC(nn.Module):
                           ws["feat"].data_ptr(), ws["hid"].data_ptr(), ws["hid_gscale"].data_ptr(),
                           ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap, _lib.ptr(ws.get("dstate")),
                           _lib.ptr(self._wprep_buf()) if ws["cluster"] > 0 else None,
-                          _lib.ptr(getattr(self, "_prof_buf", None)))
+                          _lib.ptr(getattr(self, "_prof_buf", None)),
+                          _lib.ptr(self.__dict__.get("_gate")) if ws["cluster"] > 0 else None)
 
     def prep_weights(self, mark=False):
         """launch igmc_prep_weights on the current stream; ``mark`` lets the next forward skip its own launch (the
@@ -323,6 +324,18 @@ class IGMC(nn.Module):
                                                  self._wprep_buf().data_ptr(), _stream_ptr()), "igmc_prep_weights")
         if mark:
             self._prepped = True
+
+    def gate_wait(self, batch, timeout_us=300):
+        """enqueue (on the CURRENT stream) a one-warp kernel that returns when every CTA of the next cluster-plan
+        forward of ``batch``'s shape is resident: work queued behind it runs BESIDE that forward instead of in front
+        of it (igmc_gate_wait).  The forward must be launched after this call (the gate pointer is armed here)."""
+        cl = self._plan(batch)
+        if cl <= 0:
+            return
+        if self.__dict__.get("_gate") is None:
+            self._gate = torch.zeros(1, dtype=torch.int32, device=self.flat_params.device)
+        _lib.check(_lib.load().igmc_gate_wait(self._gate.data_ptr(), batch.num_graphs * cl, int(timeout_us),
+                                              _stream_ptr()), "igmc_gate_wait")
 
     def _wprep_buf(self):
         if self._wprep is None or self._wprep.device != self.flat_params.device:

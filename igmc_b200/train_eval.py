@@ -195,15 +195,16 @@ class TrainEngine(object):
     def _launch_pipe(self, nb, G, slot, nb_next):
         B, buf = self.B, self.stepbuf_dev
         main = torch.cuda.current_stream()
-        if nb > 0 and self.model._plans and max(self.model._plans.values()) > 0:
-            # the weight-prep launch goes first and the extraction branch is ordered AFTER it: forward and extraction
-            # then become runnable together and the forward's one-per-SM clusters are placed before the extraction
-            # CTAs, which pack two per SM on what is left.  Extraction first spreads over 50 SMs and leaves fewer
-            # than the 100 free SMs the forward needs (measured: 235 us per step instead of 180, profiles/README.md)
-            self.model.prep_weights(mark=True)
         if nb_next > 0:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
+                if nb > 0:
+                    # hold the extraction back until every cluster of this step's forward is resident: the forward
+                    # needs 100 SMs to itself (one CTA per SM); extraction CTAs that start first spread one per SM over
+                    # 50 SMs, leave room for 49 of the 50 clusters and cost the forward a second wave (measured: 235
+                    # us per step instead of 180, profiles/README.md).  Started behind it they pack two per SM on the
+                    # 48 SMs that are left.
+                    self.model.gate_wait(self.batches[slot])
                 self.batches[slot ^ 1] = self.dataset.extractor.extract(idx=buf[:nb_next], seed_dev=buf[B:B + 1],
                                                                         reuse=True, slot=slot ^ 1)
                 # the next step's edge lists (after its dropout draws), staged for the model kernels' bulk loads

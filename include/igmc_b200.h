@@ -193,8 +193,16 @@ typedef struct {
   float* dstate;    /* [node_cap * 32*L] d loss / d concat_states written by an external readout; read by
                      * igmc_backward when readout = 1, unused otherwise */
   const float* wprep; /* [L * 2 * 32*((R+1)*32+4)] per-step prepared weights (igmc_prep_weights), cluster plans only */
-  long long* prof;    /* optional debug: [grid][32] clock64() stamps of the kernel phases (cluster plans), or NULL */
+  long long* prof;    /* optional debug: [grid][64] clock64() stamps of the kernel phases (cluster plans), or NULL */
+  int32_t* gate;      /* optional: every CTA of igmc_forward (cluster plans) adds 1 when it starts, see igmc_gate_wait */
 } igmc_saved_t;
+
+/* Launch-order gate for work that should run BESIDE the forward kernel without taking SMs from it (the extraction of
+ * the next batch on a second stream): a one-warp kernel that returns once `gate` has reached `target` (= the forward's
+ * grid size: all of its one-per-SM clusters are resident) or after `timeout_us`, and resets the counter.  Enqueue it
+ * on the second stream in front of the work to be held back; the forward of the same step must be given the same
+ * `gate` through igmc_saved_t. */
+int igmc_gate_wait(int32_t* gate, int target, int timeout_us, void* stream);
 
 /* Pre-staged edge lists of one batch for the cluster plans (igmc_stage_lists): per (graph, cluster rank) the
  * compacted, kept (after this step's dropout_adj draws, models.py:193-198), pre-swizzled list entries of the rank's
