@@ -144,9 +144,10 @@ def test_full_batch_dgcnn_rs_ml_1m():
         table.append((names[id(p)], float((ggpu - gref).abs().max()), float(gref.abs().max())))
     gmax = max(t[2] for t in table)
     for name, err, scale in table:
-        # relative to the tensor's own largest entry; tensors whose whole gradient is tiny next to the model's largest
-        # (here: first-layer att / root, five orders of magnitude below lin1) are held to the fp32 noise floor instead
-        assert err <= 3e-4 * scale + 1e-7 * gmax, (name, err, scale, gmax, table)
+        # relative to the tensor's own largest entry, plus an fp32 noise floor: the first-layer att gradient is a sum of
+        # O(1) products that cancel to 1e-3 of the model's largest gradient (measured: |att grad| 7e-3 next to 7.1),
+        # so its attainable accuracy is a few ulp of the SUMMANDS, i.e. ~1e-6 of the largest gradient
+        assert err <= 3e-4 * scale + 2e-6 * gmax, (name, err, scale, gmax, table)
 
 
 def test_dataset_iteration_idiom_and_bounds():
