@@ -402,7 +402,8 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
                         float* __restrict__ exp_avg_sq, int64_t* __restrict__ step_count, float lr_val,
                         const float* __restrict__ lr_dev, float b1, float b2, double log_b1, double log_b2, float eps,
                         float wd, float grad_mul, float* __restrict__ loss_out, float* __restrict__ loss_acc,
-                        float loss_weight, float* __restrict__ reg_ws, float* __restrict__ grad_copy) {
+                        float loss_weight, float* __restrict__ reg_ws, float* __restrict__ grad_copy,
+                        float* __restrict__ loss_ring, int ring_mask) {
   const int tid = threadIdx.x;
   const int64_t t64 = C.state[0] + 1;               // the exchange step this launch executes
   const int t = (int)t64;
@@ -449,7 +450,12 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
     const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
     params[i] = p - (lr / bc1) * (mi / denom);
   }
-  if (blockIdx.x == 0 && tid == 0 && loss_acc && loss_out) loss_acc[0] += __ldcg(loss_out) * loss_weight;
+  if (blockIdx.x == 0 && tid == 0 && loss_out) {
+    const float lv = __ldcg(loss_out);
+    if (loss_acc) loss_acc[0] += lv * loss_weight;
+    // the step's result for the host: slot (step number mod ring size) of a mapped pinned-host ring, no copy launch
+    if (loss_ring) loss_ring[(int)(step_i & (int64_t)ring_mask)] = lv;
+  }
   __syncthreads();
   if (tid == 0) {
     __threadfence();
@@ -550,7 +556,8 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
                                   float* exp_avg, float* exp_avg_sq, int64_t* step_count, float lr, const float* lr_dev,
                                   float beta1, float beta2, float eps, float weight_decay, float grad_mul,
                                   float* loss_out, float* loss_acc, float loss_weight, float* reg_ws, float* grad_copy,
-                                  void* stream) {
+                                  float* loss_ring, int ring_size, void* stream) {
+  if (loss_ring && (ring_size < 1 || (ring_size & (ring_size - 1)))) return -20;   // power of two
   if (!comm || !reg_ws || comm->world < 1 || comm->world > IGMC_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
     return -20;
   if (comm->stride < M->param_count || !comm->state) return -20;
@@ -563,7 +570,7 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
   k_reduce_allreduce_adam<<<NA + PBr, 256, 0, (cudaStream_t)stream>>>(
       *M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, *comm, exp_avg, exp_avg_sq,
       step_count, lr, lr_dev, beta1, beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,
-      loss_out, loss_acc, loss_weight, reg_ws, grad_copy);
+      loss_out, loss_acc, loss_weight, reg_ws, grad_copy, loss_ring, ring_size - 1);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
 }

@@ -690,7 +690,7 @@ class FusedAdam(torch.optim.Optimizer):
 
     @torch.no_grad()
     def reduce_update(self, exchange, ws, B, rows, loss_scale, arr, lr_dev=None, loss_acc=None, loss_weight=0.0,
-                      grad_copy=None):
+                      grad_copy=None, loss_ring=None):
         """gradient assembly (+ARR) -> one-shot all-reduce over the ranks of ``exchange`` -> Adam, ONE kernel
         (igmc_reduce_update).  ``ws`` is the model workspace ``forward_backward`` filled (``B`` graphs, ``rows`` raw
         partial rows; both 0 for a rank that holds no graph of a short tail batch)."""
@@ -706,6 +706,7 @@ class FusedAdam(torch.optim.Optimizer):
                                           float(g["betas"][0]), float(g["betas"][1]), float(g["eps"]),
                                           float(g["weight_decay"]), 1.0, ws["loss"].data_ptr(), _lib.ptr(loss_acc),
                                           float(loss_weight), ws["reg_ws"].data_ptr(), _lib.ptr(grad_copy),
+                                          _lib.ptr(loss_ring), int(loss_ring.numel()) if loss_ring is not None else 0,
                                           _stream_ptr()), "igmc_reduce_update")
         return ws["loss"]
 

@@ -67,6 +67,7 @@ class TrainEngine(object):
     """One training step as a replayable CUDA graph (see module docstring)."""
 
     RING = 16
+    LOSS_RING = 1024          # per-step losses the host can read back late (power of two)
 
     def __init__(self, dataset, model, optimizer, batch_size, ARR=0.0, use_graph=True, sample_seed=0):
         self.dataset, self.model, self.opt = dataset, model, optimizer
@@ -90,6 +91,21 @@ class TrainEngine(object):
         self.loss_acc = torch.zeros(1, dtype=torch.float32, device=self.dev)   # sum_steps loss*G (this rank)
         self.last_loss = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self.steps = 0
+        # zero-copy step I/O (pipelined engine): the kernels of a step read its inputs straight out of one of two
+        # pinned host buffers and the update kernel stores the step's loss into a pinned host ring - no copy-engine
+        # operation between two graph replays (the two per-step memcpys cost ~45 us of serialisation per 180 us step)
+        self.zero_copy = self.dev.type == "cuda" and os.environ.get("IGMC_ZERO_COPY", "1") != "0"
+        if self.zero_copy:
+            from .util_functions import mapped_view
+            self.hostbuf = [torch.zeros(self.B + 4, dtype=torch.int64).pin_memory() for _ in range(2)]
+            self.hostbuf_np = [t.numpy() for t in self.hostbuf]
+            self.hostview = [mapped_view(t) for t in self.hostbuf]
+            self.slot_ev = [torch.cuda.Event() for _ in range(2)]
+            self.slot_used = [False, False]
+            self.loss_ring = torch.zeros(self.LOSS_RING, dtype=torch.float32).pin_memory()
+            self.loss_ring_view = mapped_view(self.loss_ring)
+        self._adam_base = None    # Adam step number before this engine's first update (index base of the loss ring)
+        self._updates = 0
         self.exchange = None      # peer-mapped gradient buffers of the fused update kernel (created on first use)
         self.fused_update = os.environ.get("IGMC_FUSED_UPDATE", "1") != "0"
         self.sync_lr()
@@ -124,7 +140,8 @@ class TrainEngine(object):
             else:   # no graph of a short tail batch on this rank: it still takes part in the exchange (zero rows)
                 ws, rows = self._last_ws, 0
             loss = self.opt.reduce_update(self.exchange, ws, nb, rows, 1.0 / max(G, 1), self.arr_local,
-                                          lr_dev=self.lr_dev, loss_acc=self.loss_acc, loss_weight=float(G))
+                                          lr_dev=self.lr_dev, loss_acc=self.loss_acc, loss_weight=float(G),
+                                          loss_ring=self.loss_ring_view if self.zero_copy else None)
         else:
             if nb > 0:
                 loss = m.fused_step(batch, ARR=self.arr_local, global_num_graphs=G, seed_dev=seed_dev)
@@ -161,20 +178,7 @@ class TrainEngine(object):
         ev = self.ring_ev[slot]
         if self.ring_used[slot]:
             ev.synchronize()                   # the copy that last used this slot has finished
-        h = self.ring_np[slot]
-        nb = len(idx)
-        h[:nb] = idx
-        B = self.B
-        ss = self._seed_cache.get(epoch)
-        if ss is None:
-            ss = self._seed_cache[epoch] = _u64_as_i64(splitmix64(self.sample_seed + epoch))
-        h[B] = ss
-        nxt = _u64_as_i64(self.drop_seed(self.steps + 1))
-        cur = self._next_seed if getattr(self, "_next_step", None) == self.steps else _u64_as_i64(self.drop_seed(self.steps))
-        self._next_seed, self._next_step = nxt, self.steps + 1
-        h[B + 1] = cur
-        h[B + 2] = G
-        h[B + 3] = nxt
+        nb = self._fill(self.ring_np[slot], idx, epoch, G)
         self.stepbuf_dev.copy_(self.ring[slot], non_blocking=True)
         ev.record()
         self.ring_used[slot] = True
@@ -205,8 +209,31 @@ class TrainEngine(object):
     def pipelined(self):
         return hasattr(self.dataset, "extractor") and not hasattr(self.dataset, "slices")
 
-    def _launch_pipe(self, nb, G, slot, nb_next):
-        B, buf = self.B, self.stepbuf_dev
+    def loss_of_update(self, k):
+        """loss of this engine's k-th update (0-based) read from the pinned ring; valid after the step has finished
+        (any stream / device sync) and for ``LOSS_RING`` further steps."""
+        return float(self.loss_ring[(self._adam_base + 1 + k) & (self.LOSS_RING - 1)])
+
+    def _fill(self, h, idx, epoch, G):
+        """[idx | sample seed | dropout seed of this step | global batch | dropout seed of the next step] -> ``h``"""
+        nb = len(idx)
+        h[:nb] = idx
+        B = self.B
+        ss = self._seed_cache.get(epoch)
+        if ss is None:
+            ss = self._seed_cache[epoch] = _u64_as_i64(splitmix64(self.sample_seed + epoch))
+        h[B] = ss
+        nxt = _u64_as_i64(self.drop_seed(self.steps + 1))
+        cur = self._next_seed if getattr(self, "_next_step", None) == self.steps else _u64_as_i64(self.drop_seed(self.steps))
+        self._next_seed, self._next_step = nxt, self.steps + 1
+        h[B + 1] = cur
+        h[B + 2] = G
+        h[B + 3] = nxt
+        return nb
+
+    def _launch_pipe(self, nb, G, slot, nb_next, buf=None):
+        B = self.B
+        buf = self.stepbuf_dev if buf is None else buf
         main = torch.cuda.current_stream()
         if nb_next > 0:
             self.side.wait_stream(main)
@@ -249,24 +276,41 @@ class TrainEngine(object):
         One H2D copy of the next indices + one graph replay."""
         nb, G = self.cur
         self.steps += 1
+        if self._adam_base is None:
+            self._adam_base = int(self.opt.step_count[0].item())      # one sync, before the first step only
         nb_next = 0
         if next_idx is not None:
             next_G = len(next_idx) * self.world if next_G is None else int(next_G)
-            nb_next = len(next_idx) if staged else self.stage(next_idx, epoch, next_G)
+        zc = self.zero_copy and not staged
+        buf = None
+        if staged:                 # bench.py's device-resident inputs: stepbuf_dev was filled by the caller
+            nb_next = len(next_idx) if next_idx is not None else 0
+        elif zc:                   # this step's inputs go into the pinned buffer its graph variant reads
+            if self.slot_used[self.slot]:
+                self.slot_ev[self.slot].synchronize()    # the replay that last read this buffer has finished
+            nb_next = self._fill(self.hostbuf_np[self.slot], next_idx if next_idx is not None else (), epoch,
+                                 next_G if next_idx is not None else 0)
+            buf = self.hostview[self.slot]
+        elif next_idx is not None:
+            nb_next = self.stage(next_idx, epoch, next_G)
         else:
             self.stage(np.zeros(0, np.int64), epoch, 0)    # still refresh the dropout seed of this step
-        key = (nb, G, self.slot, nb_next)
+        key = (nb, G, self.slot, nb_next, zc)
         if self.use_graph and key in self.graphs:
             self.graphs[key].replay()
         elif self.use_graph and key in self.eager_done:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._launch_pipe(nb, G, self.slot, nb_next)
+                self._launch_pipe(nb, G, self.slot, nb_next, buf)
             self.graphs[key] = g
             g.replay()
         else:
-            self._launch_pipe(nb, G, self.slot, nb_next)
+            self._launch_pipe(nb, G, self.slot, nb_next, buf)
             self.eager_done.add(key)
+        if zc:
+            self.slot_ev[self.slot].record()
+            self.slot_used[self.slot] = True
+        self._updates += 1
         self.slot ^= 1
         self.cur = (nb_next, next_G if next_idx is not None else 0)
 

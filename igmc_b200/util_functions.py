@@ -29,6 +29,37 @@ def _stream_ptr():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class DevView(object):
+    """Device-visible window of a PINNED host tensor: ``data_ptr()`` is the address the kernels use (under unified
+    addressing a cudaHostAlloc'd buffer has the same address on the host and on the device), so they read / write the
+    host memory directly and no copy is ever launched.  Carries just what the launch code needs (``data_ptr``,
+    ``numel``, slicing).  Used for the per-step inputs (a few hundred bytes of indices and seeds) and the per-step
+    loss read-back of the train engine."""
+
+    def __init__(self, pinned, off=0, n=None):
+        assert pinned.is_pinned() and pinned.is_contiguous() and pinned.dim() == 1
+        self.pinned, self.off = pinned, int(off)
+        self.n = int(pinned.numel() - off if n is None else n)
+
+    def data_ptr(self):
+        return self.pinned.data_ptr() + self.off * self.pinned.element_size()
+
+    def numel(self):
+        return self.n
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, sl):
+        assert isinstance(sl, slice) and sl.step in (None, 1)
+        lo, hi, _ = sl.indices(self.n)
+        return DevView(self.pinned, self.off + lo, max(0, hi - lo))
+
+
+def mapped_view(pinned):
+    return DevView(pinned)
+
+
 class RatingGraph(object):
     """Flat device CSR + CSC of ``adj_train`` (scipy CSR, stored value = rating label + 1,
     preprocessing.py:190-197).  Replaces SparseRowIndexer/SparseColIndexer (util_functions.py:20-66)."""
@@ -347,9 +378,10 @@ class SubgraphExtractor(object):
             P = _lib.Pairs(None, pu.data_ptr(), pv.data_ptr(), pl.data_ptr(), _lib.ptr(pid))
             keep += [pu, pv, pl, pid]
         else:
-            if not torch.is_tensor(idx):
-                idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
-            idx = idx.to(device=dev, dtype=torch.int64)
+            if not isinstance(idx, DevView):     # (a DevView is int64 indices in mapped host memory: used as is)
+                if not torch.is_tensor(idx):
+                    idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+                idx = idx.to(device=dev, dtype=torch.int64)
             B = int(idx.numel())
             P = _lib.Pairs(idx.data_ptr(), self.links_u.data_ptr(), self.links_v.data_ptr(),
                            self.links_label.data_ptr(), None)
@@ -551,9 +583,10 @@ class StaticStore(object):
 
     def extract(self, idx=None, seed_dev=None, reuse=False, slot=0, **unused):
         dev = self.device
-        if not torch.is_tensor(idx):
-            idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
-        idx = idx.to(device=dev, dtype=torch.int64)
+        if not isinstance(idx, DevView):
+            if not torch.is_tensor(idx):
+                idx = torch.as_tensor(np.asarray(idx), dtype=torch.int64)
+            idx = idx.to(device=dev, dtype=torch.int64)
         B = int(idx.numel())
         o = self._alloc_out(B, reuse, slot)
         ncap, ecap = o["_caps"]

@@ -313,14 +313,17 @@ int igmc_comm_free(void* dev_ptr);
  * arrival flags, and every thread sums its elements straight out of the peers' memory (NVLink, fixed rank order ->
  * bit-identical parameters on all ranks) before applying Adam.  Replaces `loss.backward()`'s accumulation +
  * `optimizer.step()` (train_eval.py:175-177) and the ncclAllReduce a DDP port would put between them.
- * `grad_copy` (optional) receives the reduced gradient.  IGMC readout only (readout = 0), cluster plans only. */
+ * `grad_copy` (optional) receives the reduced gradient.  `loss_ring` (optional; `ring_size` a power of two): the
+ * step's loss is also stored at loss_ring[step number % ring_size] - pass mapped pinned HOST memory and the host reads
+ * every step's loss (`loss.item()`, train_eval.py:176) without a copy launch or a sync.
+ * IGMC readout only (readout = 0), cluster plans only. */
 int igmc_reduce_update(const igmc_model_t* M, float* params, int B, int gpart_rows, const float* gpart,
                        const float* dhid, const float* feat, const float* hid, const float* dpred,
                        const float* sqerr, float loss_scale, float arr, const igmc_comm_t* comm,
                        float* exp_avg, float* exp_avg_sq, int64_t* step_count, float lr, const float* lr_dev,
                        float beta1, float beta2, float eps, float weight_decay, float grad_mul,
                        float* loss_out, float* loss_acc, float loss_weight, float* reg_ws, float* grad_copy,
-                       void* stream);
+                       float* loss_ring, int ring_size, void* stream);
 
 /* ---- SortPooling + 1-D convolution readout of DGCNN_RS (models.py:123-167 over DGCNN.__init__ models.py:65-85) ----
  * Consumes the concat_states a readout=1 igmc_forward produced.  latent_dim = [32,...,32,1] is run by the conv
