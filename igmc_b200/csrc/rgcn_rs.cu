@@ -396,7 +396,7 @@ __host__ __device__ __forceinline__ int own_cap_of(int n_cap, int CL) { return (
 #define IGMC_STAMP(i_) do { if (S.prof && threadIdx.x == 0) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
 // debug: wall-clock (globaltimer, ns) of a CTA's start / end and the SM it ran on - slots 50..52 of its prof row
 #define IGMC_WALL(i_) do { if (S.prof && threadIdx.x == 0) { S.prof[(size_t)blockIdx.x * 64 + (i_)] = igmc_globaltimer(); \
-                                                              S.prof[(size_t)blockIdx.x * 64 + 52] = igmc_smid(); } } while (0)
+                                                              S.prof[(size_t)blockIdx.x * 64 + ((i_) < 53 ? 52 : 55)] = igmc_smid(); } } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // per-step weight preparation.  slab(l, dir) = Bn[n][KS]  (n = output channel, KS = Ktot + 4):
@@ -813,7 +813,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
   float* gp = gpart + ((size_t)g * CL + rank) * (size_t)igmc_raw_count(R, in0, L);
   IGMC_STAMP(0);
-  IGMC_WALL(50);
+  IGMC_WALL(53);   // (the backward's wall-clock stamps use slots 53..55 so that one buffer holds both kernels')
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -1179,7 +1179,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     if (CL > 1 && l > 0) cluster_wait();   // nothing is exchanged after layer 0
     IGMC_STAMP(sb + 4);
   }
-  IGMC_WALL(51);
+  IGMC_WALL(54);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1392,11 +1392,16 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
 }
 
 namespace rs {
+// gate[0]: CTAs of gated forwards that have started, ever (never reset); gate[1]: the total this and all earlier gates
+// expect.  Every gate is followed by exactly one forward that was handed the gate (the host arms it per launch), so
+// the count catches up with the expectation once that forward is resident; un-gated forwards do not touch the counter
+// and a timed-out gate does not desynchronise the pair (late arrivals still count towards the same total).
 __global__ void k_gate_wait(int* gate, int target, long long timeout_ns) {
   if (threadIdx.x == 0) {
+    const int expect = gate[1] + target;
+    gate[1] = expect;
     const long long t0 = igmc_globaltimer();
-    while (*reinterpret_cast<volatile int*>(gate) < target && igmc_globaltimer() - t0 < timeout_ns) __nanosleep(100);
-    *gate = 0;
+    while (*reinterpret_cast<volatile int*>(gate) - expect < 0 && igmc_globaltimer() - t0 < timeout_ns) __nanosleep(64);
   }
 }
 }  // namespace rs

@@ -315,7 +315,8 @@ class IGMC(nn.Module):
                           ws["pred"].data_ptr(), ws["target"].data_ptr(), ncap, _lib.ptr(ws.get("dstate")),
                           _lib.ptr(self._wprep_buf()) if ws["cluster"] > 0 else None,
                           _lib.ptr(getattr(self, "_prof_buf", None)),
-                          _lib.ptr(self.__dict__.get("_gate")) if ws["cluster"] > 0 else None)
+                          _lib.ptr(self._gate) if (ws["cluster"] > 0 and self.__dict__.pop("_gate_armed", False))
+                          else None)
 
     def prep_weights(self, mark=False):
         """launch igmc_prep_weights on the current stream; ``mark`` lets the next forward skip its own launch (the
@@ -333,9 +334,10 @@ class IGMC(nn.Module):
         if cl <= 0:
             return
         if self.__dict__.get("_gate") is None:
-            self._gate = torch.zeros(1, dtype=torch.int32, device=self.flat_params.device)
+            self._gate = torch.zeros(2, dtype=torch.int32, device=self.flat_params.device)
         _lib.check(_lib.load().igmc_gate_wait(self._gate.data_ptr(), batch.num_graphs * cl, int(timeout_us),
                                               _stream_ptr()), "igmc_gate_wait")
+        self._gate_armed = True      # the next forward launch (and only that one) counts its CTAs into the gate
 
     def _wprep_buf(self):
         if self._wprep is None or self._wprep.device != self.flat_params.device:

@@ -198,10 +198,11 @@ typedef struct {
 } igmc_saved_t;
 
 /* Launch-order gate for work that should run BESIDE the forward kernel without taking SMs from it (the extraction of
- * the next batch on a second stream): a one-warp kernel that returns once `gate` has reached `target` (= the forward's
- * grid size: all of its one-per-SM clusters are resident) or after `timeout_us`, and resets the counter.  Enqueue it
- * on the second stream in front of the work to be held back; the forward of the same step must be given the same
- * `gate` through igmc_saved_t. */
+ * the next batch on a second stream): a one-warp kernel that returns once `target` more CTAs (= the forward's grid
+ * size: all of its one-per-SM clusters are resident) have counted in, or after `timeout_us`.  `gate` = two zero-
+ * initialised int32 words (started-CTA count, expected total; never reset).  Enqueue it on the second stream in front
+ * of the work to be held back; exactly ONE forward per gate - the one of the same step - must be given `gate` through
+ * igmc_saved_t (other forwards pass NULL). */
 int igmc_gate_wait(int32_t* gate, int target, int timeout_us, void* stream);
 
 /* Pre-staged edge lists of one batch for the cluster plans (igmc_stage_lists): per (graph, cluster rank) the

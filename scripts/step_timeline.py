@@ -27,24 +27,25 @@ for s in range(12):
     eng.step_pipe(idx[s + 1], epoch=1)
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for rep in range(3):
-    flush.fill_(rep)
-    prof.zero_()
-    eng.step_pipe(idx[20 + rep], epoch=1)
-    torch.cuda.synchronize()
-    p = prof.view(-1, 64)[:100].cpu().numpy()
-    ho = d.extractor.ws["hop_off"].view(-1, 8)[:B].cpu().numpy()
-    # the backward wrote last into the shared rows: its start/end; the forward's are lost in this replay
-    bs, be, bsm = p[:, 50] & 0x7fffffff, p[:, 51] & 0x7fffffff, p[:, 52]
-    es, ee, esm = ho[:, 5].astype(np.int64), ho[:, 6].astype(np.int64), ho[:, 7]
-    t0 = min(bs.min(), es.min())
-    print("replay %d  (us relative to the earliest stamp)" % rep)
-    print("  backward   CTA start min/median/max %.1f %.1f %.1f   end max %.1f   SMs used %d" % (
-        (bs.min() - t0) / 1e3, (np.median(bs) - t0) / 1e3, (bs.max() - t0) / 1e3, (be.max() - t0) / 1e3, len(set(bsm.tolist()))))
-    print("  extraction CTA start min/median/max %.1f %.1f %.1f   end min/median/max %.1f %.1f %.1f   SMs used %d   "
-          "per-CTA duration median %.1f max %.1f" % (
-              (es.min() - t0) / 1e3, (np.median(es) - t0) / 1e3, (es.max() - t0) / 1e3, (ee.min() - t0) / 1e3,
-              (np.median(ee) - t0) / 1e3, (ee.max() - t0) / 1e3, len(set(esm.tolist())), np.median(ee - es) / 1e3,
-              (ee - es).max() / 1e3))
-    late = np.sort(bs - bs.min())[-6:] / 1e3
-    print("  backward latest CTA starts (us after the first):", np.round(late, 1), " shared SMs:", len(set(bsm.tolist()) & set(esm.tolist())))
+M31 = 0x7fffffff
+for mode in ("flushed", "back-to-back"):
+    for rep in range(4):
+        if mode == "flushed":
+            flush.fill_(rep)
+        prof.zero_()
+        for _ in range(1 if mode == "flushed" else 3):      # back-to-back: stamps of the LAST of three replays
+            eng.step_pipe(idx[20 + rep], epoch=1)
+        torch.cuda.synchronize()
+        p = prof.view(-1, 64)[:100].cpu().numpy()
+        ho = d.extractor.ws["hop_off"].view(-1, 8)[:B].cpu().numpy()
+        fs, fe, fsm = p[:, 50] & M31, p[:, 51] & M31, p[:, 52]
+        bs, be, bsm = p[:, 53] & M31, p[:, 54] & M31, p[:, 55]
+        es, ee, esm = ho[:, 5].astype(np.int64), ho[:, 6].astype(np.int64), ho[:, 7]
+        t0 = fs.min()
+        u = lambda a: np.round((a - t0) / 1e3, 1)
+        print("%s replay %d (us after the first forward CTA started)" % (mode, rep))
+        print("  forward    start min/med/max %s %s %s  end med/max %s %s  SMs %d" % (u(fs.min()), u(np.median(fs)), u(fs.max()), u(np.median(fe)), u(fe.max()), len(set(fsm.tolist()))))
+        print("  extraction start min/med/max %s %s %s  end med/max %s %s  SMs %d" % (u(es.min()), u(np.median(es)), u(es.max()), u(np.median(ee)), u(ee.max()), len(set(esm.tolist()))))
+        print("  backward   start min/med/max %s %s %s  end med/max %s %s  SMs %d  (SMs shared with extraction %d)" % (u(bs.min()), u(np.median(bs)), u(bs.max()), u(np.median(be)), u(be.max()), len(set(bsm.tolist())), len(set(bsm.tolist()) & set(esm.tolist()))))
+        late = np.sort(fs)[-4:]
+        print("  latest forward CTA starts:", u(late), " latest backward CTA starts:", u(np.sort(bs)[-4:]))
