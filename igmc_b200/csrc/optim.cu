@@ -417,17 +417,22 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
   reduce_raw_block(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, 1.0f, gl, loss_out,
                    reg_ws);
   int* tick = reinterpret_cast<int*>(C.state + 1);  // [0] phase-1 ticket, [1] phase-3 ticket
+  __shared__ int s_pub;
   __syncthreads();
   if (tid == 0) {
     __threadfence_system();
-    if (atomicAdd(&tick[0], 1) == (int)gridDim.x - 1) {
-      tick[0] = 0;
-      __threadfence_system();
-      for (int r = 0; r < C.world; ++r) st_release_sys(C.flag[r] + C.rank, t);   // includes the own flag
-    }
-    for (int r = 0; r < C.world; ++r)
-      while (ld_acquire_sys(C.flag[C.rank] + r) - t < 0) {}
+    s_pub = (atomicAdd(&tick[0], 1) == (int)gridDim.x - 1);
+    if (s_pub) tick[0] = 0;
   }
+  __syncthreads();
+  // the last block publishes "step t ready", one thread per destination rank (the stores travel in parallel)
+  if (s_pub && tid < C.world) {
+    __threadfence_system();
+    st_release_sys(C.flag[tid] + C.rank, t);   // includes the own flag
+  }
+  // every block: one thread per source rank polls its arrival flag
+  if (tid < C.world)
+    while (ld_acquire_sys(C.flag[C.rank] + tid) - t < 0) {}
   __syncthreads();
   const float lr = lr_dev ? *lr_dev : lr_val;
   const float bc1 = s_bc[0], bc2 = s_bc[1];
