@@ -67,7 +67,7 @@ class Model(C.Structure):
                 ("off_root", C.c_int32 * MAX_LAYERS), ("off_bias", C.c_int32 * MAX_LAYERS),
                 ("off_lin1_w", C.c_int32), ("off_lin1_b", C.c_int32), ("off_lin2_w", C.c_int32),
                 ("off_lin2_b", C.c_int32), ("conv_param_count", C.c_int32), ("param_count", C.c_int32),
-                ("multiply_by", C.c_float), ("readout", C.c_int32)]
+                ("multiply_by", C.c_float), ("readout", C.c_int32), ("list_hint", C.c_int32)]
 
 
 class Dropout(C.Structure):

@@ -1257,9 +1257,16 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
   size_t rows = (limit - base - 4096) / (rowfl * 4);
   rows &= ~(size_t)15;
   if (rows > (size_t)own16) rows = own16;
-  // the layer-0 aggregate tile of the backward reuses the staging rows: it must hold at least 8 node rows
   size_t left = limit - base - rows * rowfl * 4;
   size_t lc = (left / 4) & ~(size_t)3;
+  // a list that does not fit is gathered through global memory (3-4x slower per layer): trade staging rows for list
+  // capacity down to 32 rows when the caller knows how long the lists get
+  const size_t hint = M->list_hint > 0 ? (size_t)(M->list_hint > 16384 ? 16384 : M->list_hint) : 0;
+  while (lc < hint && rows > 32) {
+    rows -= 16;
+    left = limit - base - rows * rowfl * 4;
+    lc = (left / 4) & ~(size_t)3;
+  }
   if (lc > 16384) lc = 16384;
   {
     // 1024 threads (64 registers) or 512 threads (128 registers: no address rematerialisation, fewer instructions)

@@ -12,6 +12,7 @@ Adam updates.  ``forward`` is autograd-capable (custom Function over the C-ABI);
 """
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -219,8 +220,18 @@ class IGMC(nn.Module):
         lib = _lib.load()
         n_cap, B = p["n_cap"], batch.num_graphs
         want = self.kernel_plan
+        env = os.environ.get("IGMC_PLAN")
+        if want == "auto" and env:
+            want = int(env)
+        if self.num_relations <= 12 and n_cap > 256 and self._cmodel.list_hint == 0:
+            # large subgraphs: size the shared-memory list buffers from the data (longest per-graph edge list of
+            # this first batch, one host sync per model; the lists of one CTA hold its share of the directed edges)
+            ep = p["edge_ptr"][:B + 1].cpu()
+            self._max_edges = int((ep[1:] - ep[:-1]).max())
         cands = [want] if want != "auto" else [cl for cl in (4, 2, 1) if B * cl <= self.NUM_SMS or cl == 1] + [0]
         for cl in cands:
+            if self.__dict__.get("_max_edges") and int(cl) > 0:
+                self._cmodel.list_hint = int(1.25 * self._max_edges / int(cl)) + 256
             f = lib.igmc_model_plan(C.byref(self._cmodel), n_cap, int(cl), 0)
             b = lib.igmc_model_plan(C.byref(self._cmodel), n_cap, int(cl), 1)
             if f > 0 and b > 0:

@@ -163,6 +163,10 @@ typedef struct {
   int32_t readout;           /* 0: IGMC target-row readout inside igmc_forward/igmc_backward (models.py:203-215);
                               * 1: none - igmc_forward stops at concat_states, igmc_backward takes S.dstate =
                               *    d loss / d concat_states from an external readout (igmc_sortpool_*) */
+  int32_t list_hint;         /* 0 = unknown, else the number of edge-list entries one CTA should be able to stage in
+                              * shared memory (largest per-CTA list seen + margin): the cluster plans then give up
+                              * staging rows (more, smaller chunks) until the list buffer holds that many - large
+                              * subgraphs (ml_100k, 402 nodes) otherwise gather through global memory */
 } igmc_model_t;
 
 /* Dropout draws of one step.  edge_keep/hidden_keep (uint8, 1 = keep) inject explicit draws

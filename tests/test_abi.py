@@ -53,7 +53,7 @@ def test_struct_sizes_match_header_layout():
     assert ctypes.sizeof(_lib.Pairs) == 5 * P
     assert ctypes.sizeof(_lib.ExtractWS) == 9 * P
     assert ctypes.sizeof(_lib.Adj) == 7 * P + 8
-    assert ctypes.sizeof(_lib.Model) == 4 * (4 + 4 * 8 + 4 + 2 + 1 + 1)
+    assert ctypes.sizeof(_lib.Model) == 4 * (4 + 4 * 8 + 4 + 2 + 1 + 1 + 1)
     assert ctypes.sizeof(_lib.Stage) == 3 * P + 16
     assert ctypes.sizeof(_lib.SortPool) == 4 * 19
     assert ctypes.sizeof(_lib.SortPoolSaved) == 10 * P
