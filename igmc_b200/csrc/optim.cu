@@ -403,7 +403,7 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
                         const float* __restrict__ lr_dev, float b1, float b2, double log_b1, double log_b2, float eps,
                         float wd, float grad_mul, float* __restrict__ loss_out, float* __restrict__ loss_acc,
                         float loss_weight, float* __restrict__ reg_ws, float* __restrict__ grad_copy,
-                        float* __restrict__ loss_ring, int ring_mask) {
+                        float* __restrict__ loss_ring, int ring_mask, float* __restrict__ wprep) {
   const int tid = threadIdx.x;
   const int64_t t64 = C.state[0] + 1;               // the exchange step this launch executes
   const int t = (int)t64;
@@ -468,6 +468,45 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
       tick[1] = 0;
       step_count[0] = step_i;
       C.state[0] = t64;
+      if (wprep) {   // second grid barrier: every block's parameter slice is written - release the weight preparation
+        __threadfence();
+        *reinterpret_cast<volatile int*>(&tick[2]) = t;
+      }
+    }
+    if (wprep)
+      while (*reinterpret_cast<volatile int*>(&tick[2]) - t < 0) {}
+    __threadfence();
+  }
+  if (!wprep) return;
+  __syncthreads();
+  // ---- phase 4: W_r = sum_b att[r,b] basis[b] and its transpose for the NEXT step's kernels (what
+  //      igmc_prep_weights launches; same layout: slab(l, dir) = 32 rows of KS floats) ----
+  {
+    const int R = M.num_relations, NB = M.num_bases;
+    const size_t slab = (size_t)HID * ((size_t)(R + 1) * HID + 4);
+    for (int row = blockIdx.x; row < M.num_layers * 2 * 32; row += gridDim.x) {
+      const int n = row & 31, ld = row >> 5, l = ld >> 1, dir = ld & 1;
+      if (dir == 1 && l == 0) continue;
+      const int in = l == 0 ? M.in_dim0 : HID, inp = (in + 3) & ~3;
+      const int K1 = R * inp, K1p = (K1 + 7) & ~7, inpp = (inp + 7) & ~7, KS = K1p + inpp + 4;
+      const float* bs = params + M.off_basis[l];
+      const float* at = params + M.off_att[l];
+      const float* rt = params + M.off_root[l];
+      float* out = wprep + ((size_t)l * 2 + dir) * slab + (size_t)n * KS;
+      for (int kk = tid; kk < KS; kk += 256) {
+        float w = 0.f;
+        if (kk < K1) {
+          const int r = kk / inp, q = kk - r * inp;
+          if (q < in) {
+            const int k = dir == 0 ? q : n, j = dir == 0 ? n : q;
+            for (int b = 0; b < NB; ++b) w = fmaf(__ldcg(at + r * NB + b), __ldcg(bs + (b * in + k) * HID + j), w);
+          }
+        } else if (kk >= K1p && kk < K1p + inp) {
+          const int q = kk - K1p;
+          if (q < in) w = dir == 0 ? __ldcg(rt + q * HID + n) : __ldcg(rt + n * HID + q);
+        }
+        out[kk] = w;
+      }
     }
   }
 }
@@ -561,7 +600,7 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
                                   float* exp_avg, float* exp_avg_sq, int64_t* step_count, float lr, const float* lr_dev,
                                   float beta1, float beta2, float eps, float weight_decay, float grad_mul,
                                   float* loss_out, float* loss_acc, float loss_weight, float* reg_ws, float* grad_copy,
-                                  float* loss_ring, int ring_size, void* stream) {
+                                  float* loss_ring, int ring_size, float* wprep, void* stream) {
   if (loss_ring && (ring_size < 1 || (ring_size & (ring_size - 1)))) return -20;   // power of two
   if (!comm || !reg_ws || comm->world < 1 || comm->world > IGMC_MAX_RANKS || comm->rank < 0 || comm->rank >= comm->world)
     return -20;
@@ -575,7 +614,7 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
   k_reduce_allreduce_adam<<<NA + PBr, 256, 0, (cudaStream_t)stream>>>(
       *M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, *comm, exp_avg, exp_avg_sq,
       step_count, lr, lr_dev, beta1, beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,
-      loss_out, loss_acc, loss_weight, reg_ws, grad_copy, loss_ring, ring_size - 1);
+      loss_out, loss_acc, loss_weight, reg_ws, grad_copy, loss_ring, ring_size - 1, wprep);
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
 }

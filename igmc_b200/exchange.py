@@ -28,7 +28,7 @@ class Exchange(object):
         self.stride = (int(param_count) + 31) & ~31
         self.bytes = 2 * self.stride * 4 + self.FLAG_BYTES
         self.device = torch.device(device)
-        self.state = torch.zeros(2, dtype=torch.int64, device=self.device)
+        self.state = torch.zeros(4, dtype=torch.int64, device=self.device)   # step counter, tickets [3 x int32 + pad]
         self.peers = {}
         self.local = None
         with torch.cuda.device(self.device):

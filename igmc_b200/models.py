@@ -184,6 +184,7 @@ class IGMC(nn.Module):
                 p.grad = None
         self.flat_params, self.flat_grad = flat, grad
         self._layout, self._cmodel, self._offs = layout, m, offs
+        self._prepped = False
         self._ws = {}
         self._plans = {}
         self._wprep = None
@@ -197,6 +198,10 @@ class IGMC(nn.Module):
         out = super()._apply(fn, *a, **kw)
         self._flatten()
         return out
+
+    def load_state_dict(self, *a, **kw):
+        self._prepped = False         # prepared weights (igmc_prep_weights) belong to the old parameters
+        return super().load_state_dict(*a, **kw)
 
     def reset_parameters(self):
         for c in self.convs:
@@ -228,7 +233,16 @@ class IGMC(nn.Module):
             # this first batch, one host sync per model; the lists of one CTA hold its share of the directed edges)
             ep = p["edge_ptr"][:B + 1].cpu()
             self._max_edges = int((ep[1:] - ep[:-1]).max())
-        cands = [want] if want != "auto" else [cl for cl in (4, 2, 1) if B * cl <= self.NUM_SMS or cl == 1] + [0]
+        if want != "auto":
+            cands = [want]
+        elif n_cap > 256 and self.num_relations <= 12:
+            # large subgraphs (ml_100k*: up to 402 nodes): four CTAs per subgraph even when that is more than one wave
+            # of the SMs - node features of the whole subgraph take 100 KB of every CTA's shared memory, and only with
+            # a quarter of the nodes per CTA do the edge lists still fit next to them.  Measured at batch 50
+            # (profiles/README.md): 143 k subgraphs/s with 4 CTAs, 136 k with 3, 67 k with 2.
+            cands = [4, 3, 2, 1, 0]
+        else:
+            cands = [cl for cl in (4, 2, 1) if B * cl <= self.NUM_SMS or cl == 1] + [0]
         for cl in cands:
             if self.__dict__.get("_max_edges") and int(cl) > 0:
                 self._cmodel.list_hint = int(1.25 * self._max_edges / int(cl)) + 256
@@ -691,6 +705,7 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, grad_mul=1.0, lr_dev=None, loss_in=None, loss_acc=None, loss_weight=0.0):
         lib = _lib.load()
+        self.model._prepped = False   # parameters change: the prepared weights are stale
         g = self.param_groups[0]
         m = self.model
         _lib.check(lib.igmc_adam_step(m.flat_params.data_ptr(), m.flat_grad.data_ptr(), self.exp_avg.data_ptr(),
@@ -720,7 +735,8 @@ class FusedAdam(torch.optim.Optimizer):
                                           float(g["weight_decay"]), 1.0, ws["loss"].data_ptr(), _lib.ptr(loss_acc),
                                           float(loss_weight), ws["reg_ws"].data_ptr(), _lib.ptr(grad_copy),
                                           _lib.ptr(loss_ring), int(loss_ring.numel()) if loss_ring is not None else 0,
-                                          _stream_ptr()), "igmc_reduce_update")
+                                          m._wprep_buf().data_ptr(), _stream_ptr()), "igmc_reduce_update")
+        m._prepped = True     # the update kernel re-prepared W_r / W_r^T from the new parameters (next forward skips it)
         return ws["loss"]
 
     def zero_grad(self, set_to_none=False):

@@ -303,7 +303,7 @@ int igmc_adam_step(float* params, const float* grad, float* exp_avg, float* exp_
 typedef struct {
   float* grad[IGMC_MAX_RANKS];    /* grad[r]: rank r's [2][stride] gradient buffers (r = rank: local memory) */
   int32_t* flag[IGMC_MAX_RANKS];  /* flag[r]: rank r's [IGMC_MAX_RANKS] arrival flags, flag[r][src] = last step src published */
-  int64_t* state;                 /* local [2]: exchange step counter, two int32 tickets (zero-initialised) */
+  int64_t* state;                 /* local [4], zero-initialised: exchange step counter, then three int32 tickets */
   int32_t world, rank, stride, pad_;
 } igmc_comm_t;
 
@@ -320,7 +320,9 @@ int igmc_comm_free(void* dev_ptr);
  * `optimizer.step()` (train_eval.py:175-177) and the ncclAllReduce a DDP port would put between them.
  * `grad_copy` (optional) receives the reduced gradient.  `loss_ring` (optional; `ring_size` a power of two): the
  * step's loss is also stored at loss_ring[step number % ring_size] - pass mapped pinned HOST memory and the host reads
- * every step's loss (`loss.item()`, train_eval.py:176) without a copy launch or a sync.
+ * every step's loss (`loss.item()`, train_eval.py:176) without a copy launch or a sync.  `wprep` (optional): after
+ * the update (second grid barrier) the kernel also rebuilds the prepared weights of igmc_prep_weights from the NEW
+ * parameters, so that the next step's forward needs no separate preparation launch.
  * IGMC readout only (readout = 0), cluster plans only. */
 int igmc_reduce_update(const igmc_model_t* M, float* params, int B, int gpart_rows, const float* gpart,
                        const float* dhid, const float* feat, const float* hid, const float* dpred,
@@ -328,7 +330,7 @@ int igmc_reduce_update(const igmc_model_t* M, float* params, int B, int gpart_ro
                        float* exp_avg, float* exp_avg_sq, int64_t* step_count, float lr, const float* lr_dev,
                        float beta1, float beta2, float eps, float weight_decay, float grad_mul,
                        float* loss_out, float* loss_acc, float loss_weight, float* reg_ws, float* grad_copy,
-                       float* loss_ring, int ring_size, void* stream);
+                       float* loss_ring, int ring_size, float* wprep, void* stream);
 
 /* ---- SortPooling + 1-D convolution readout of DGCNN_RS (models.py:123-167 over DGCNN.__init__ models.py:65-85) ----
  * Consumes the concat_states a readout=1 igmc_forward produced.  latent_dim = [32,...,32,1] is run by the conv
