@@ -63,7 +63,9 @@ def test_full_batch_train_step_parity_dynamic(name, mnph, B, plan):
     hk = torch.rand(B, 128, generator=torch.Generator().manual_seed(2)) > 0.5
     _check_step(m, ref, b, ob, 0.001, ds["adj_dropout"], hk)
     if plan == "auto":
-        assert m._plan(b) == 2            # batch 50 -> two CTAs per subgraph
+        # batch 50: two CTAs per subgraph; four for the 402-node subgraphs of ml_100k* (edge lists must fit in shared
+        # memory next to the node features)
+        assert m._plan(b) == (4 if b._priv["n_cap"] > 256 else 2)
     # the same step with the list images of the pipelined engine: bit-identical gradient
     g0 = m.flat_grad.clone()
     m._step = 31
