@@ -156,6 +156,13 @@ __device__ __forceinline__ int igmc_smid() {
   return s;
 }
 
+// ---- programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream still runs; pdl_wait() blocks until the predecessor has completed and its
+// writes are visible, pdl_trigger() lets the successor's CTAs be scheduled as soon as SMs free up.  Both are no-ops
+// for launches without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 #define IGMC_CUDA_CHECK_LAUNCH()                      \
   do {                                                \
     cudaError_t e__ = cudaGetLastError();             \

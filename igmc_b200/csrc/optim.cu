@@ -4,6 +4,7 @@
 // + `torch.optim.Adam.step` (train_eval.py:54,177) with TWO launches on the flat parameter bucket, which is
 // also what the one NCCL all-reduce per step operates on.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -405,6 +406,7 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
                         float loss_weight, float* __restrict__ reg_ws, float* __restrict__ grad_copy,
                         float* __restrict__ loss_ring, int ring_mask, float* __restrict__ wprep) {
   const int tid = threadIdx.x;
+  pdl_wait();   // launched as a programmatic dependent of the backward: its partial rows are complete from here on
   const int64_t t64 = C.state[0] + 1;               // the exchange step this launch executes
   const int t = (int)t64;
   const int64_t step_i = step_count[0] + 1;
@@ -611,11 +613,25 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
   if (M->readout != 0) return -16;   // external readouts write their own gradient slice: use the separate kernels
   const int NA = M->in_dim0 + (M->num_layers - 1) * HID;
   const int PBr = (M->param_count - M->conv_param_count + 255) / 256;
-  k_reduce_allreduce_adam<<<NA + PBr, 256, 0, (cudaStream_t)stream>>>(
-      *M, params, B, gpart_rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, *comm, exp_avg, exp_avg_sq,
-      step_count, lr, lr_dev, beta1, beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,
-      loss_out, loss_acc, loss_weight, reg_ws, grad_copy, loss_ring, ring_size - 1, wprep);
-  IGMC_CUDA_CHECK_LAUNCH();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(NA + PBr);
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // scheduled under the backward's tail (pdl_wait)
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  static int pdl = -1;
+  if (pdl < 0) {
+    const char* e = getenv("IGMC_PDL");
+    pdl = e ? atoi(e) : 1;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduce_allreduce_adam, *M, params, B, gpart_rows, NA, gpart, dhid, feat, hid,
+                                     dpred, sqerr, loss_scale, arr, *comm, exp_avg, exp_avg_sq, step_count, lr, lr_dev,
+                                     beta1, beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,
+                                     loss_out, loss_acc, loss_weight, reg_ws, grad_copy, loss_ring, ring_size - 1, wprep);
+  if (e != cudaSuccess) return (int)e + 1000;
   return 0;
 }
 

@@ -489,6 +489,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   IGMC_STAMP(0);
   IGMC_WALL(50);
   if (S.gate && tid == 0) atomicAdd(S.gate, 1);   // "this CTA is resident" (igmc_gate_wait)
+  pdl_trigger();   // a backward launched behind this kernel may take the SMs the first finished clusters free
 
   // weights of a layer: the [W_r ; root] slab prepared by igmc_prep_weights, one bulk (TMA) copy issued by a single
   // thread; every thread waits on mbar[1] (phase = layer parity) right before the layer's tensor-core tiles, so the
@@ -810,10 +811,8 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   const Split own = own_range(n, rank, CL);
   const int n_own = own.hi - own.lo;
   const bool ext = M.readout != 0;   // d concat_states comes from an external readout (S.dstate)
-  const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
   float* gp = gpart + ((size_t)g * CL + rank) * (size_t)igmc_raw_count(R, in0, L);
-  IGMC_STAMP(0);
-  IGMC_WALL(53);   // (the backward's wall-clock stamps use slots 53..55 so that one buffer holds both kernels')
+  pdl_trigger();   // the gradient-assembly kernel behind this one may be scheduled as SMs free up
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -854,6 +853,12 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
   if (!use_img)
     Ls = stage_lists(sym ? A.in_adj : A.out_adj, sym ? A.in_eid : A.out_eid, sym ? A.in_ptr : A.out_ptr, nb, own.lo,
                      own.hi, K, sym, eb, m_half, lbuf, lcap, ibuf, own_cap, chunk, ws, nullptr, nullptr);
+  // everything above only touches what existed before the forward ran (batch, list images, prepared weights): under
+  // a programmatic dependent launch it overlaps the forward's tail.  From here on the forward's results are read.
+  pdl_wait();
+  IGMC_STAMP(0);
+  IGMC_WALL(53);   // (the backward's wall-clock stamps use slots 53..55 so that one buffer holds both kernels')
+  const int tu = ext ? -1 : S.target[2 * g] - nb, ti = ext ? -1 : S.target[2 * g + 1] - nb;
 
   // ---- readout backward (every CTA needs d feat to seed its target rows) ----
   if (!ext) {
@@ -1287,21 +1292,36 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
   return 0;
 }
 
+static int pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("IGMC_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+
 template <class Kern, class... Args>
-static int launch_cluster(Kern kern, int grid, int threads, size_t smem, int cluster, cudaStream_t st, Args... args) {
+static int launch_cluster(Kern kern, int grid, int threads, size_t smem, int cluster, bool pdl, cudaStream_t st,
+                          Args... args) {
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = cluster;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
+  if (pdl && pdl_enabled()) {   // may start under the tail of the previous kernel of the stream (pdl_wait inside)
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
   if (e != cudaSuccess) return (int)e + 1000;
   return 0;
@@ -1373,10 +1393,10 @@ int rs_forward(const igmc_model_t* M, const float* params, const uint8_t* node_l
   if (rc) return rc;
   if (img.tab && !img.inv_deg) return -19;
   if (threads == 512)
-    return launch_cluster(rs::k_forward_rs<512>, B * cluster, threads, smem, cluster, st, *M, params, node_label,
+    return launch_cluster(rs::k_forward_rs<512>, B * cluster, threads, smem, cluster, false, st, *M, params, node_label,
                           node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, img,
                           err);
-  return launch_cluster(rs::k_forward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
+  return launch_cluster(rs::k_forward_rs<1024>, B * cluster, threads, smem, cluster, false, st, *M, params, node_label, node_ptr,
                         edge_ptr, *A, n_cap, lcap, chunk, *D, training, *S, y, loss_scale, dpred, sqerr, img, err);
 }
 
@@ -1392,9 +1412,9 @@ int rs_backward(const igmc_model_t* M, const float* params, const uint8_t* node_
   rc = check_image(stage, n_cap, cluster, lcap, chunk, &img);
   if (rc) return rc;
   if (threads == 512)
-    return launch_cluster(rs::k_backward_rs<512>, B * cluster, threads, smem, cluster, st, *M, params, node_label,
+    return launch_cluster(rs::k_backward_rs<512>, B * cluster, threads, smem, cluster, true, st, *M, params, node_label,
                           node_ptr, edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, img, err);
-  return launch_cluster(rs::k_backward_rs<1024>, B * cluster, threads, smem, cluster, st, *M, params, node_label, node_ptr,
+  return launch_cluster(rs::k_backward_rs<1024>, B * cluster, threads, smem, cluster, true, st, *M, params, node_label, node_ptr,
                         edge_ptr, *A, n_cap, lcap, chunk, *D, *S, dpred, gpart, dhid, img, err);
 }
 
