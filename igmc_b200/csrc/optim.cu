@@ -623,7 +623,7 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
   static int pdl = -1;
   if (pdl < 0) {
     const char* e = getenv("IGMC_PDL");
-    pdl = e ? atoi(e) : 1;
+    pdl = e ? atoi(e) : 0;   // off by default (same reason as the backward, csrc/rgcn_rs.cu)
   }
   cfg.attrs = at;
   cfg.numAttrs = pdl ? 1 : 0;

@@ -257,11 +257,7 @@ class TrainEngine(object):
     def prime(self, idx, epoch=0, G=None):
         """extract the first batch of a pipelined sequence (no model work)."""
         if not hasattr(self, "side"):
-            # higher priority than the model stream: the backward is launched as a programmatic dependent and sits in
-            # the work distributor's queue while the forward runs; at equal priority the extraction kernel, launched
-            # after it, is not dispatched until that queue entry has been placed (measured: extraction starts 67 us into
-            # the step instead of 2.5 us).  Its CTAs only ever take SMs the model kernels cannot use.
-            self.side = torch.cuda.Stream(priority=-1)
+            self.side = torch.cuda.Stream()
             self.batches = [None, None]
         G = len(idx) * self.world if G is None else int(G)
         nb = self.stage(idx, epoch, G)
