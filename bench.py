@@ -392,7 +392,14 @@ def run_ours(args):
     G = B * world
     rng = np.random.default_rng(1000)
     perm = rng.permutation(len(tu))
-    steps_idx = [perm[(s * G + rank * B + np.arange(B)) % len(perm)] for s in range(W + 4 * K + 32)]   # wraps on small sets
+    # every step: one global batch of G pairs of the permutation, dealt to the ranks balanced by the pairs' degree
+    # estimate (train_eval.deal_balanced, what `train()` does under data parallelism); wraps on small sets
+    from igmc_b200.train_eval import deal_balanced
+    cost = train.pair_cost()
+    steps_idx = []
+    for s in range(W + 4 * K + 32):
+        chunk = perm[(s * G + np.arange(G)) % len(perm)]
+        steps_idx.append(deal_balanced(chunk, cost[chunk], world)[rank] if world > 1 else chunk)
     cursor = [0]
 
     def next_idx():

@@ -99,22 +99,45 @@ __device__ void select_side(const int32_t* __restrict__ nbr, int len, int target
     __syncthreads();
   }
   const uint32_t tau = prefix;  // keys < tau are all taken; `remaining` ties (key == tau) are taken
-  int run_strict = 0, run_tie = 0;
-  for (int base = 0; base < len; base += nt) {
-    const int p = base + tid;
-    int strict = 0, tie = 0, node = 0;
-    if (p < len && p != pos) {
-      node = nbr[p];
-      uint32_t key = sample_key(state, node);
-      strict = key < tau;
-      tie = key == tau;
+  // ordered compaction with two barriers: every warp owns one contiguous range of the list (a multiple of 32 entries),
+  // counts its (strict | tie << 16) selections, all warps scan the <= 32 per-warp totals, then each warp writes its
+  // range with ballot ranks.  (A block scan per 1024-entry chunk cost 3 barriers per chunk: 17 % of the kernel.)
+  {
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const int chunks = (len + 31) >> 5, per = (chunks + nw - 1) / nw;
+    const int c0 = warp * per, c1 = min(chunks, c0 + per);
+    int cs = 0, ct = 0;
+    for (int c = c0; c < c1; ++c) {
+      const int p = (c << 5) + lane;
+      int strict = 0, tie = 0;
+      if (p < len && p != pos) {
+        const uint32_t key = sample_key(state, nbr[p]);
+        strict = key < tau;
+        tie = key == tau;
+      }
+      cs += __popc(__ballot_sync(IGMC_FULL, strict));
+      ct += __popc(__ballot_sync(IGMC_FULL, tie));
     }
-    int tot;
-    int ex = block_excl_scan_i(strict | (tie << 16), ws, &tot);
-    const int sb = run_strict + (ex & 0xFFFF), tb = run_tie + (ex >> 16);
-    if (strict || (tie && tb < remaining)) out[1 + sb + min(tb, remaining)] = node;
-    run_strict += tot & 0xFFFF;
-    run_tie += tot >> 16;
+    if (lane == 0) { hist[warp] = cs; hist[32 + warp] = ct; }   // (the radix histogram is free again)
+    __syncthreads();
+    int sb = 0, tb = 0;
+    for (int w = 0; w < warp; ++w) { sb += hist[w]; tb += hist[32 + w]; }
+    const unsigned lt = (1u << lane) - 1u;
+    for (int c = c0; c < c1; ++c) {
+      const int p = (c << 5) + lane;
+      int strict = 0, tie = 0, node = 0;
+      if (p < len && p != pos) {
+        node = nbr[p];
+        const uint32_t key = sample_key(state, node);
+        strict = key < tau;
+        tie = key == tau;
+      }
+      const unsigned bs = __ballot_sync(IGMC_FULL, strict), bt = __ballot_sync(IGMC_FULL, tie);
+      const int s_here = sb + __popc(bs & lt), t_here = tb + __popc(bt & lt);
+      if (strict || (tie && t_here < remaining)) out[1 + s_here + min(t_here, remaining)] = node;
+      sb += __popc(bs);
+      tb += __popc(bt);
+    }
   }
   __syncthreads();
 }
@@ -628,17 +651,19 @@ k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint
         const int mid = (lo + hi + 1) >> 1;
         if (S.rowstart[mid] <= q0) lo = mid; else hi = mid - 1;
       }
-      int ar[4], pr[4], col[4];
+      int ar[4], col[4];
+      uint32_t rat[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int q = q0 + 32 * u + lane;
         int a = lo;
         col[u] = -1;
-        pr[u] = 0;
+        rat[u] = 0;
         if (q < D) {
           while (q >= S.rowstart[a + 1]) ++a;
-          pr[u] = S.rp[a] + (q - S.rowstart[a]);
-          col[u] = __ldg(G.col_idx + pr[u]);
+          const int p = S.rp[a] + (q - S.rowstart[a]);
+          col[u] = __ldg(G.col_idx + p);
+          rat[u] = __ldg(G.rating + p);     // fetched with the index (1 B per entry): no second dependent L2 latency
         }
         ar[u] = a;
       }
@@ -652,7 +677,7 @@ k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint
         const bool match = (b != NONE16) && !(ar[u] == 0 && b == 0);   // (target user, target item): removed (ref :238)
         uint32_t r = 0;
         if (match) {
-          r = G.rating[pr[u]];
+          r = rat[u];
           if ((int)r >= R) { igmc_set_err(err, IGMC_ERR_BAD_BATCH); r = 0; }   // label outside class_values
           atomicAdd(&S.rowcnt[ar[u]], 1);
           atomicOr(&S.bm[((size_t)b * R + r) * words + (ar[u] >> 5)], 1u << (ar[u] & 31));
@@ -682,6 +707,40 @@ k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint
   __syncthreads();
 
   // ---- C: prefixes ----
+  const int TTc = T > FX_TCAP ? 0 : T;
+  if (nu <= nt && nv <= nt && TTc <= nt) {
+    // the common case (every table fits one value per thread): the three exclusive scans share one set of barriers
+    int v0 = tid < nu ? (S.rowcnt[tid] | ((S.hj[tid] & 1) << 20)) : 0;     // row edges | target-item edge << 20
+    int v1 = tid < TTc ? S.tilebase[tid] : 0;                              // staged entries of tile tid
+    int v2 = 0;                                                            // list length of item tid (from the bitmaps)
+    if (tid < nv) {
+      for (int r = 0; r < R; ++r) {
+        S.cur[tid * R + r] = v2;
+        const uint32_t* w = S.bm + ((size_t)tid * R + r) * words;
+        for (int x = 0; x < words; ++x) v2 += __popc(w[x]);
+      }
+      S.colcnt[tid] = v2;
+    }
+    int i0 = warp_incl_scan_i(v0, lane), i1 = warp_incl_scan_i(v1, lane), i2 = warp_incl_scan_i(v2, lane);
+    if (lane == 31) { hist[warp] = i0; hist[32 + warp] = i1; hist[64 + warp] = i2; }
+    __syncthreads();
+    if (warp < 3) {
+      const int sv = lane < nwarps ? hist[32 * warp + lane] : 0;
+      const int inc = warp_incl_scan_i(sv, lane);
+      hist[96 + 32 * warp + lane] = inc - sv;
+      if (lane == 31) hist[192 + warp] = inc;
+    }
+    __syncthreads();
+    const int e0 = hist[96 + warp] + i0 - v0, e1 = hist[128 + warp] + i1 - v1, e2 = hist[160 + warp] + i2 - v2;
+    if (tid < nu) { S.rowoff[tid] = e0 & 0xFFFFF; S.jbefore[tid] = e0 >> 20; }
+    if (tid < TTc) S.tilebase[tid] = e1;
+    if (tid < nv) S.coloff[tid] = e2;
+    if (tid == 0) {
+      S.rowoff[nu] = hist[192] & 0xFFFFF; S.jbefore[nu] = hist[192] >> 20;
+      S.tilebase[TTc] = hist[193];
+    }
+    __syncthreads();
+  } else {
   {   // rows: edge offsets and the number of target-item edges in earlier rows, one packed scan (counts < 2^20)
     int running = 0;
     for (int base = 0; base < nu; base += nt) {
@@ -731,6 +790,7 @@ k_extract_fast(igmc_csr_t G, igmc_pairs_t P, int B, int mnph, double ratio, uint
       if (b < nv) S.coloff[b] = running + ex;
       running += tot;
     }
+  }
   }
   const int m = S.rowoff[nu];
   // publish this graph's counts, then sum the predecessors' (they run at the same time; lower block ids are

@@ -37,18 +37,37 @@ def _dist_info():
     return 0, 1
 
 
-def shard_batches(perm, batch_size, rank, world):
+def deal_balanced(chunk, cost, world):
+    """Partition one global batch over ``world`` ranks so that every rank gets the same number of pairs (+-1) and a
+    similar mix of expensive and cheap ones: pairs sorted by ``cost`` (descending, ties by position) are dealt in
+    snake order 0..w-1, w-1..0, ...  A step ends when the slowest rank's largest subgraph is done, so what matters
+    is that no rank collects the big ones.  Returns a list of index arrays (positions into ``chunk`` kept in their
+    original relative order).  Pure host logic."""
+    g = len(chunk)
+    order = np.argsort(-np.asarray(cost, dtype=np.float64), kind="stable")
+    owner = np.empty(g, dtype=np.int64)
+    pos = np.arange(g)
+    lap, k = pos // world, pos % world
+    owner[order] = np.where(lap % 2 == 0, k, world - 1 - k)
+    return [np.asarray(chunk)[owner == r] for r in range(world)]
+
+
+def shard_batches(perm, batch_size, rank, world, cost=None):
     """Split an epoch permutation into global batches of ``batch_size*world`` and return, per step,
     (this rank's indices, global batch size).  The last global batch may be short (the reference's
     DataLoader keeps the partial batch, drop_last=False); it is split as evenly as possible and a rank
-    may then receive an empty slice.  Pure host logic (covered by CPU tests)."""
+    may then receive an empty slice.  ``cost`` (optional, one value per dataset index): deal every global batch
+    balanced by it (``deal_balanced``) instead of in contiguous slices - the global batches, and therefore the
+    optimisation trajectory up to summation order, are the same.  Pure host logic (covered by CPU tests)."""
     n = len(perm)
     gb = batch_size * world
     out = []
     for s in range(0, n, gb):
         chunk = perm[s:s + gb]
         g = len(chunk)
-        if g == gb:
+        if cost is not None and world > 1:
+            mine = deal_balanced(chunk, np.asarray(cost)[chunk], world)[rank]
+        elif g == gb:
             mine = chunk[rank * batch_size:(rank + 1) * batch_size]
         else:
             base, extra = divmod(g, world)
@@ -384,7 +403,8 @@ def train(model, optimizer, loader, device, regression=False, ARR=0, show_progre
     perm = torch.randperm(len(dataset), generator=generator).numpy()
     engine.loss_acc.zero_()
     ep = 0 if epoch is None else int(epoch)
-    batches = shard_batches(perm, engine.B, rank, world)
+    cost = dataset.pair_cost() if world > 1 and hasattr(dataset, "pair_cost") else None
+    batches = shard_batches(perm, engine.B, rank, world, cost)
     if engine.pipelined() and len(batches) > 0:
         engine.prime(batches[0][0], ep, batches[0][1])
         for k in range(len(batches)):

@@ -481,6 +481,19 @@ class MyDynamicDataset(object):
         for k in range(len(self)):
             yield self.get(k)
 
+    def pair_cost(self):
+        """a-priori size estimate of every pair's subgraph from the matrix degrees alone (hop 1: raters of the item
+        + items of the user, each capped by max_nodes_per_hop): what the data-parallel sharding balances the ranks'
+        batches by (train_eval.deal_balanced).  Host arrays, computed once."""
+        c = getattr(self, "_pair_cost", None)
+        if c is None:
+            h = self.graph.host
+            du, dv = np.diff(h["row_ptr"]), np.diff(h["col_ptr"])
+            cap = self.max_nodes_per_hop if self.max_nodes_per_hop is not None else (1 << 30)
+            c = np.minimum(du[self.links[0]], cap) + np.minimum(dv[self.links[1]], cap)
+            self._pair_cost = c = c.astype(np.float64)
+        return c
+
     def node_counts(self, chunk=2048):
         """number of nodes of every subgraph (what ``[g.num_nodes for g in dataset]`` gives, models.py:71), extracted
         in large batches instead of one by one"""

@@ -200,3 +200,28 @@ def test_fused_adam_state_dict_loads_into_torch_adam():
     for p in m.parameters():   # (the flat buffers also hold alignment padding that is not part of any state entry)
         assert torch.equal(opt2.state[p]["exp_avg"], opt.state[p]["exp_avg"])
         assert torch.equal(opt2.state[p]["exp_avg_sq"], opt.state[p]["exp_avg_sq"])
+
+
+def test_balanced_dealing_partitions_and_balances():
+    """deal_balanced / shard_batches(cost=...): every pair of every global batch goes to exactly one rank, rank sizes
+    differ by at most one, the same global batches as the contiguous split, and the ranks' largest costs are close"""
+    from igmc_b200.train_eval import deal_balanced
+    rng = np.random.default_rng(0)
+    n, B = 1003, 50
+    perm = rng.permutation(n)
+    cost = rng.lognormal(0, 1, n)
+    for world in (2, 4, 8):
+        per_rank = [shard_batches(perm, B, r, world, cost) for r in range(world)]
+        plain = [shard_batches(perm, B, r, world) for r in range(world)]
+        for step in range(len(per_rank[0])):
+            got = np.concatenate([per_rank[r][step][0] for r in range(world)])
+            want = np.concatenate([plain[r][step][0] for r in range(world)])
+            assert sorted(got.tolist()) == sorted(want.tolist())
+            sizes = [len(per_rank[r][step][0]) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1 and per_rank[0][step][1] == plain[0][step][1]
+            if sizes[0] == B:
+                tops = [cost[per_rank[r][step][0]].max() for r in range(world)]
+                srt = np.sort(cost[got])[::-1]
+                assert min(tops) >= srt[world - 1] - 1e-12          # each rank holds one of the `world` largest
+    parts = deal_balanced(np.arange(7), np.array([5, 1, 4, 2, 3, 0, 6.0]), 3)
+    assert sorted(np.concatenate(parts).tolist()) == list(range(7)) and [len(p) for p in parts] == [3, 2, 2]
