@@ -549,6 +549,68 @@ class StaticStore(object):
             parts["ncnt"].append(cnt_n)
             parts["ecnt"].append(ends)
         cat = {k: torch.cat(v) for k, v in parts.items()}
+        self._finish(cat, num_graphs)
+
+    @classmethod
+    def from_arrays(cls, device, feat_dim, x, edge_index, edge_type, y, node_off, edge_off, emit_x=True):
+        """Build the store from collated per-graph-LOCAL arrays (the content of the reference's ``data.pt``,
+        pyg_cache.load_processed) instead of extracting: labels from the one-hot ``x``, message-passing lists by one
+        device-wide sort of the edges by (destination node, rating, source).  The edge layout must be the reference's
+        ``[u | v ; v | u]`` per graph (construct_pyg_graph, util_functions.py:283-285): the kernels find an edge's
+        reverse at +-half the graph's edge count."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self.device = dev = torch.device(device)
+        self.feat_dim, self.emit_x = int(feat_dim), emit_x
+        x, y = x.to(dev), y.to(dev).float().view(-1)
+        ei, et = edge_index.to(dev).long(), edge_type.to(dev).long()
+        noff, eoff = node_off.to(dev).long(), edge_off.to(dev).long()
+        G = int(y.numel())
+        if int(x.shape[1]) != self.feat_dim:
+            raise ValueError("cached node features have width %d, expected %d (hop mismatch)" % (x.shape[1], feat_dim))
+        ncnt, ecnt = noff[1:] - noff[:-1], eoff[1:] - eoff[:-1]
+        E, N = int(eoff[-1]), int(noff[-1])
+        ge = torch.repeat_interleave(torch.arange(G, device=dev), ecnt)          # graph of every edge
+        gn = torch.repeat_interleave(torch.arange(G, device=dev), ncnt)
+        if E:
+            half = (ecnt // 2)[ge]
+            k = torch.arange(E, device=dev) - eoff[ge]
+            mirror = torch.where(k < half, torch.arange(E, device=dev) + half, torch.arange(E, device=dev) - half)
+            if bool((ecnt % 2 != 0).any()) or not torch.equal(ei[0], ei[1][mirror]) or not torch.equal(et, et[mirror]) \
+                    or int(ei.max()) >= int(ncnt.max()) or bool((ei >= ncnt[ge].unsqueeze(0)).any()):
+                raise ValueError("the cache is not in the reference's [u|v ; v|u] per-graph edge layout")
+        label = torch.argmax(x, 1)
+        gnu = torch.zeros(G, dtype=torch.int64, device=dev).index_add_(0, gn, (label % 2 == 0).long())
+        # in-lists: edges sorted by (global destination node, rating, local source); graphs stay contiguous
+        gdst = noff[ge] + ei[1]
+        key = (gdst * 256 + et) * 65536 + ei[0]
+        order = torch.argsort(key)
+        deg = torch.zeros(N, dtype=torch.int64, device=dev).index_add_(0, gdst, torch.ones(E, dtype=torch.int64, device=dev))
+        start = torch.cumsum(deg, 0) - deg                                         # first list slot of every node
+        adj_ptr = torch.empty(N + G, dtype=torch.int32, device=dev)
+        adj_ptr[torch.arange(N, device=dev) + gn] = (start - eoff[gn]).int()
+        adj_ptr[noff[1:] + torch.arange(G, device=dev)] = ecnt.int()
+        cat = dict(node_label=label.to(torch.uint8), node_gid=torch.zeros(N, dtype=torch.int32, device=dev),
+                   edge_src=ei[0].int(), edge_dst=ei[1].int(), edge_type=et.to(torch.uint8), y=y, graph_nu=gnu.int(),
+                   adj_ptr=adj_ptr, adj_in=(ei[0][order] | (et[order] << 16)).int(),
+                   adj_eid=(order - eoff[ge[order]]).int(), ncnt=ncnt, ecnt=ecnt)
+        self._finish(cat, G)
+        return self
+
+    def arrays(self):
+        """collated per-graph-local arrays of the store: (x one-hot, edge_index, edge_type, y, node_off, edge_off)"""
+        lab = self.t["node_label"].long()
+        n = int(self.node_off[-1])
+        x = torch.zeros(n, self.feat_dim, dtype=torch.float32, device=self.device)
+        if n:
+            x[torch.arange(n, device=self.device), lab[:n]] = 1.0
+        e = int(self.edge_off[-1])
+        ei = torch.stack([self.t["edge_src"][:e].long(), self.t["edge_dst"][:e].long()])
+        return x, ei, self.t["edge_type"][:e].long(), self.t["y"][:self.num_graphs], self.node_off.long(), \
+            self.edge_off.long()
+
+    def _finish(self, cat, num_graphs):
+        dev = self.device
         z = torch.zeros(1, dtype=torch.int64, device=dev)
         self.node_off = torch.cat([z, torch.cumsum(cat["ncnt"], 0)]).int()
         self.edge_off = torch.cat([z, torch.cumsum(cat["ecnt"], 0)]).int()
@@ -634,14 +696,32 @@ class MyDataset(MyDynamicDataset):
         super().__init__(root, A, links, labels, h, sample_ratio, max_nodes_per_hop, u_features, v_features,
                          class_values, max_num, seed)
         self.parallel = parallel
-        self.process(chunk)
+        self.max_num = max_num
+        self.dynamic_extractor = self.extractor
+        # the reference's cache contract (util_functions.py:91-99,108-109): <root>/processed/data.pt (data_<max_num>.pt)
+        # holding (data, slices) is used when present, written otherwise - files interchange with the reference's
+        from . import pyg_cache
+        path = pyg_cache.processed_path(root, max_num) if root else None
+        if path is not None and os.path.isfile(path):
+            c = pyg_cache.load_processed(path)
+            if int(c["y"].numel()) != len(self):
+                raise ValueError("%s holds %d subgraphs, the dataset has %d pairs (stale cache: delete it or pass "
+                                 "--reprocess)" % (path, int(c["y"].numel()), len(self)))
+            self.store = StaticStore.from_arrays(self.dynamic_extractor.device, self.num_features, c["x"],
+                                                 c["edge_index"], c["edge_type"], c["y"], c["node_off"], c["edge_off"])
+            self.extractor = self.store
+            self.loaded_from = path
+        else:
+            self.process(chunk)
+            self.loaded_from = None
+            if path is not None:
+                pyg_cache.save_processed(path, *self.store.arrays())
 
     @property
     def processed_file_names(self):
-        return ["data.pt"]
+        return ["data.pt"] if self.max_num is None else ["data_{}.pt".format(self.max_num)]
 
     def process(self, chunk=512):
-        self.dynamic_extractor = self.extractor
         self.store = StaticStore(self.dynamic_extractor, len(self), chunk)
         self.extractor = self.store          # the train / eval loops batch through the store from now on
 

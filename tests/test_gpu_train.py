@@ -286,3 +286,56 @@ def test_dp2_peer_exchange_equals_single_gpu_global_batch():
     assert diff <= 1e-6 and moved > 1e-5, (diff, moved)
     assert abs(float(eng.loss_acc) - (got[0][2] + got[1][2])) <= 1e-3 * abs(float(eng.loss_acc))
     eng.exchange.close()
+
+
+def test_static_dataset_cache_file_interchange(tmp_path):
+    """MyDataset(root=...) keeps the reference's cache contract (util_functions.py:91-110): the first construction
+    extracts and writes <root>/processed/data.pt as (data, slices); the second loads the FILE (no extraction) and
+    serves bit-identical batches - message-passing lists, predictions and gradients included - and a file written the
+    reference's way (plain Data + slices pickled by hand) loads too."""
+    from igmc_b200 import pyg_cache
+    from igmc_b200.models import IGMC
+    from igmc_b200.util_functions import MyDataset
+    ds = _tiny()
+    tu, tv, tl = ds["train"]
+    n = 120
+    args = (ds["adj_train"], (tu[:n], tv[:n]), tl[:n], 1, 1.0, 10, None, None, ds["class_values"])
+    root = str(tmp_path / "data" / "tiny" / "train")
+    a = MyDataset(root, *args)
+    assert a.loaded_from is None and os.path.isfile(os.path.join(root, "processed", "data.pt"))
+    b = MyDataset(root, *args)
+    assert b.loaded_from is not None
+    idx = np.array([5, 0, 77, 119, 33, 34, 35])
+    ba, bb = a.extract_batch(idx), b.extract_batch(idx)
+    for k in ("x", "edge_index", "edge_type", "batch", "y"):
+        assert torch.equal(getattr(ba, k), getattr(bb, k)), k
+    E = int(ba._priv["counts"][1])
+    N = int(ba._priv["counts"][0])
+    for k in ("adj_in_ptr", "adj_in", "adj_eid"):
+        lim = N + 1 if k == "adj_in_ptr" else E
+        assert torch.equal(ba._adj[1][k][:lim], bb._adj[1][k][:lim]), k
+    torch.manual_seed(0)
+    m = IGMC(a, latent_dim=[32] * 4, num_relations=5, num_bases=4, regression=True, adj_dropout=0.2).cuda().train()
+    hk = torch.rand(len(idx), 128, generator=torch.Generator().manual_seed(1)) > 0.5
+    m._step = 3
+    la = float(m.fused_step(ba, ARR=0.001, hidden_keep=hk)); ga = m.flat_grad.clone()
+    m._step = 3
+    lb = float(m.fused_step(bb, ARR=0.001, hidden_keep=hk))
+    assert la == lb and torch.equal(ga, m.flat_grad)
+    # single graphs through the reference's indexing idiom
+    assert torch.equal(a[7].edge_index, b[7].edge_index) and torch.equal(a[7].x, b[7].x)
+    # a cache pickled "by the reference": same arrays, its own Data object
+    x, ei, et, y, noff, eoff = [t.cpu() for t in a.store.arrays()]
+    root2 = str(tmp_path / "data" / "tiny" / "ref_written")
+    os.makedirs(os.path.join(root2, "processed"))
+    Data = pyg_cache._data_class()
+    torch.save((Data(x=x, edge_index=ei, y=y, edge_type=et),
+                {"x": noff, "edge_index": eoff, "y": torch.arange(n + 1), "edge_type": eoff}),
+               os.path.join(root2, "processed", "data.pt"))
+    c = MyDataset(root2, *args)
+    assert c.loaded_from is not None
+    bc = c.extract_batch(idx)
+    assert torch.equal(bc.edge_index, ba.edge_index) and torch.equal(bc._adj[1]["adj_in"][:E], ba._adj[1]["adj_in"][:E])
+    # a stale cache (different number of pairs) is refused, not silently used
+    with pytest.raises(ValueError):
+        MyDataset(root, ds["adj_train"], (tu[:50], tv[:50]), tl[:50], 1, 1.0, 10, None, None, ds["class_values"])
