@@ -42,9 +42,19 @@ def main(verbose=True):
         eng.step(np.arange(s * 8, s * 8 + 8), epoch=1)
     eng.check()
     loss = float(eng.last_loss.item())
+    # the production path: pipelined engine (extraction of the next batch + list images on the side branch behind the
+    # launch-order gate, TMA-staged model kernels, one fused reduce -> exchange -> Adam kernel, zero-copy step I/O),
+    # first eager, then as replayed CUDA graphs
+    eng.prime(np.arange(32, 40), epoch=1)
+    for s in range(6):
+        eng.step_pipe(np.arange(40 + s * 8, 48 + s * 8) if s < 5 else None, epoch=1)
+    eng.check()
     torch.cuda.synchronize()
+    loss_pipe = eng.loss_of_update(eng._updates - 1) if eng.zero_copy and eng.exchange is not None else float(eng.last_loss)
+    assert np.isfinite(loss_pipe) and bool(torch.isfinite(m.flat_params).all())
     if verbose:
-        print("smoke: extract_exact=%s forward_rmse=%.3e train_loss=%.4f" % (ok_extract, rmse, loss))
+        print("smoke: extract_exact=%s forward_rmse=%.3e train_loss=%.4f pipelined_loss=%.4f" % (
+            ok_extract, rmse, loss, loss_pipe))
     assert ok_extract, "extraction differs from the oracle"
     assert rmse <= 1e-4, "forward differs from the oracle: %g" % rmse
     assert np.isfinite(loss)
