@@ -333,6 +333,15 @@ class TrainEngine(object):
         self.slot ^= 1
         self.cur = (nb_next, next_G if next_idx is not None else 0)
 
+    def close(self):
+        """drop the captured graphs and release the peer-mapped exchange buffers (collective under data parallelism:
+        every rank calls it, nobody may still be reading a buffer that is being freed)"""
+        torch.cuda.synchronize()
+        self.graphs.clear()
+        if self.exchange is not None:
+            self.exchange.close()
+            self.exchange = None
+
     def check(self):
         code = int(self.dataset.extractor.err.item()) if hasattr(self.dataset, "extractor") else 0
         if code:
@@ -387,6 +396,7 @@ def train_multiple_epochs(train_dataset, test_dataset, model, epochs, batch_size
     duration = time.perf_counter() - t_start
     if rank == 0:
         print("Final Test RMSE: {:.6f}, Duration: {:.6f}".format(rmses[-1], duration))
+    engine.close()
     return rmses[-1]
 
 

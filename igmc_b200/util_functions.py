@@ -314,6 +314,11 @@ class SubgraphExtractor(object):
         if B <= self.max_batch:
             return
         dev, cap, g = self.device, self.cap, self.graph
+        if self.max_batch:
+            # captured CUDA graphs hold raw pointers into the workspace of the batch sizes seen so far: keep the old
+            # buffers alive instead of handing them back to the allocator
+            self.__dict__.setdefault("_retired_ws", []).append((self.ws, self._out_cache))
+            self._out_cache = {}
         self.max_batch = B
         per_graph_edges = 2 * min(cap * min(cap, max(g.max_row_deg, 1)), max(g.nnz, 1))
         self.node_cap = B * 2 * cap
