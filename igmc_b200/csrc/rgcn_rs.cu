@@ -344,26 +344,6 @@ __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, 
   }
 }
 
-// Layer 0 of an h = 1 model: the input rows are one-hot over 4 labels, so a segment's relation-space aggregate is a
-// table of (rating, label) COUNTS.  One thread per segment walks its <= 32 staged entries (label = position of the 1
-// in the neighbour's 4-float row, one LDS.128) instead of eight lanes moving float4s of which seven carry nothing:
-// 5.3 -> ~1.5 us per forward.  Same values as gather_segments (sums of exact 1.0s), staged lists only.
-__device__ __forceinline__ void gather_l0_counts(const Lists& Ls, int sg0, int sg1, const float* __restrict__ feat,
-                                                 float* __restrict__ stage, int SS, int R) {
-  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int sg = sg0 + (int)threadIdx.x; sg < sg1; sg += (int)blockDim.x) {
-    float* row = stage + (size_t)Ls.seg_row[sg] * SS;
-    for (int c = 0; c < SS; c += 4) *reinterpret_cast<float4*>(row + c) = z4;   // incl. the K padding the tiles read
-    const int p1 = Ls.seg_p1[sg];
-    for (int p = Ls.seg_p0[sg]; p < p1; ++p) {
-      const uint32_t e = Ls.lst[p];
-      const float4 hv = *reinterpret_cast<const float4*>(feat + (e & 0xffffffu));
-      const int lab = (int)(hv.y + 2.f * hv.z + 3.f * hv.w);
-      row[(e >> 24) * 4 + lab] += 1.f;
-    }
-  }
-}
-
 // ---- tensor-core tiles: mma.sync m16n8k8 TF32 with 3xTF32 error compensation (fp32-level accuracy) ----------
 // D(16x8) += A(16x8, row) * B(8x8, col).  lane: g = lane>>2, t = lane&3
 //   A: a0=(g,t) a1=(g+8,t) a2=(g,t+4) a3=(g+8,t+4)   B: b0=(k=t,n=g) b1=(k=t+4,n=g)   D: d0=(g,2t) d1=(g,2t+1) d2=(g+8,2t) d3=(g+8,2t+1)
@@ -580,28 +560,6 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   const int gq = lane >> 2, tq = lane & 3;
   IGMC_STAMP(1);
-  // readout lin1 (models.py:211), pipelined: hid_s accumulates lin1.bias + the contribution of every layer's slice of
-  // the two target rows; layer l's slice is added while layer l+1 waits at its cluster barrier (thread = output o x one
-  // 16-column quarter of the 64 inputs of a slice, four-lane shuffle sum).  Only the last slice is left for the end.
-  const bool do_readout = rank == 0 && !ext;
-  if (do_readout && tid < L1O) hid_s[tid] = __ldg(params + M.off_lin1_b + tid);
-  auto readout_partial = [&](int ll) {
-    if (tid < 4 * L1O) {
-      const int o = tid >> 2, part = tid & 3;
-      const int col = (part >> 1) * CW + ll * HID + (part & 1) * 16;        // user | item half, 16 columns
-      const float4* w4 = reinterpret_cast<const float4*>(params + M.off_lin1_w + (size_t)o * F + col);
-      const float4* f4 = reinterpret_cast<const float4*>(feat_s + col);
-      float s = 0.f;
-#pragma unroll
-      for (int q4 = 0; q4 < 4; ++q4) {
-        const float4 w = __ldg(w4 + q4), f = f4[q4];
-        s = fmaf(w.x, f.x, s); s = fmaf(w.y, f.y, s); s = fmaf(w.z, f.z, s); s = fmaf(w.w, f.w, s);
-      }
-      s += __shfl_xor_sync(IGMC_FULL, s, 1);
-      s += __shfl_xor_sync(IGMC_FULL, s, 2);
-      if (part == 0) hid_s[o] += s;
-    }
-  };
   for (int l = 0; l < L; ++l) {
     const int inp = l == 0 ? in0p : HID;
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), SS = K1p + 4, KS = K1p + inpp + 4;
@@ -612,10 +570,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       // ---- aggregate: one 8-lane group per list segment ----
 #define IGMC_STAMP_T(t_, i_) do { if (S.prof && l == 1 && threadIdx.x == (t_)) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
       IGMC_STAMP_T(0, 39); IGMC_STAMP_T(992, 49);
-      if (l == 0 && inp == 4 && in0 == 4 && Ls.lst)
-        gather_l0_counts(Ls, Ls.segbase[c0], Ls.segbase[c0 + crow], H, stage, SS, R);
-      else
-        gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, H, stage, SS, inp, &ws[33]);
+      gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, H, stage, SS, inp, &ws[33]);
       IGMC_STAMP_T(0, 40); IGMC_STAMP_T(992, 43); IGMC_STAMP_T(480, 46);
       __syncthreads();
       if (tid == 0) ws[33] = 0;   // re-arm the segment ticket (the next gather is several barriers away)
@@ -705,7 +660,6 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     // the next layer's weights do not depend on the peers: load them while the row pushes of the cluster land
     if (CL > 1) cluster_arrive();
     if (l + 1 < L) load_weights(l + 1);
-    if (do_readout && l >= 1) readout_partial(l - 1);   // the previous layer's slice, inside the barrier window
     if (CL > 1) cluster_wait();
     IGMC_STAMP(7 + 6 * l);
     float* t = H; H = Hn; Hn = t;
@@ -724,30 +678,43 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
 
   if (rank != 0 || ext) { IGMC_WALL(51); return; }
-  // ---- readout (models.py:205-215), one CTA of the cluster: last slice of lin1, ReLU, Dropout(0.5), lin2 ----
+  // ---- readout (models.py:205-215), one CTA of the cluster ----
   __syncthreads();
   for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
   if (tid == 0) { S.target[2 * g] = nb + tu; S.target[2 * g + 1] = nb + ti; }
-  readout_partial(L - 1);
-  __syncthreads();
-  if (tid < L1O) {
-    const int o = tid;
-    const float h = fmaxf(hid_s[o], 0.f);
-    float scale = 1.f;
-    if (training && (D.hidden_dropout > 0.f || D.hidden_keep)) {
-      bool keep;
-      if (D.hidden_keep) keep = D.hidden_keep[(size_t)g * L1O + o] != 0;
-      else {
-        double t = (double)D.hidden_dropout * 4294967296.0;
-        keep = edge_keep(K.seed ^ 0x5bd1e995a5a5a5a5ull, (uint32_t)(g * L1O + o),
-                         t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t);
-      }
-      const float p = D.hidden_keep ? 0.5f : D.hidden_dropout;
-      scale = keep ? 1.f / (1.f - p) : 0.f;
+  const float* W1 = params + M.off_lin1_w;
+  for (int ob = warp * 4; ob < L1O; ob += nwarps * 4) {   // 4 outputs per warp with independent load streams
+    float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    const float bias_o = lane < 4 ? __ldg(params + M.off_lin1_b + ob + lane) : 0.f;   // independent of the dot products
+#pragma unroll 8   // 32 independent L2 loads in flight per lane (the loop is latency bound)
+    for (int i = lane; i < F; i += 32) {
+      const float f = feat_s[i];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) s4[u] = fmaf(__ldg(W1 + (size_t)(ob + u) * F + i), f, s4[u]);
     }
-    hid_s[o] = h * scale;
-    S.hid[(size_t)g * L1O + o] = h * scale;
-    S.hid_gscale[(size_t)g * L1O + o] = h > 0.f ? scale : 0.f;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) s4[u] = warp_sum_f(s4[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) if (lane == u) {
+      const int o = ob + u;
+      const float s = s4[u];
+      float h = fmaxf(s + bias_o, 0.f);
+      float scale = 1.f;
+      if (training && (D.hidden_dropout > 0.f || D.hidden_keep)) {
+        bool keep;
+        if (D.hidden_keep) keep = D.hidden_keep[(size_t)g * L1O + o] != 0;
+        else {
+          double t = (double)D.hidden_dropout * 4294967296.0;
+          keep = edge_keep(K.seed ^ 0x5bd1e995a5a5a5a5ull, (uint32_t)(g * L1O + o),
+                           t >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)t);
+        }
+        const float p = D.hidden_keep ? 0.5f : D.hidden_dropout;
+        scale = keep ? 1.f / (1.f - p) : 0.f;
+      }
+      hid_s[o] = h * scale;
+      S.hid[(size_t)g * L1O + o] = h * scale;
+      S.hid_gscale[(size_t)g * L1O + o] = h > 0.f ? scale : 0.f;
+    }
   }
   __syncthreads();
   if (warp == 0) {
