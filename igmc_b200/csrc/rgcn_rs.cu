@@ -1049,9 +1049,10 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         // (2) weight gradients over the chunk's rows:  D[k][(r,j) | j'] += sum_u h_{l-1}[u][k] [Q[u] | dpre[u]]
         //     M = 32 (k, two 16-row tiles), N = (R+1)*32, K = crow nodes; warp = (m tile, every (nwarps/2)-th n tile)
         mbar_wait(&mbar[2], huse & 1u); ++huse;            // the chunk's h_{l-1} rows have landed
-        {
+        // a warp owns up to MAXI column tiles per pass; more (R > 7 at 16 warps) take further passes over the nodes
+        for (int jp = warp >> 1; jp < NTN; jp += 4 * (nwarps >> 1)) {
           constexpr int MAXI = 4;
-          const int m0 = (warp & 1) << 4, jn0 = warp >> 1, jstep = nwarps >> 1;
+          const int m0 = (warp & 1) << 4, jn0 = jp, jstep = nwarps >> 1;
           float acc[MAXI][4], acs[MAXI][4];
 #pragma unroll
           for (int i = 0; i < MAXI; ++i)
@@ -1256,7 +1257,6 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
   const int own16 = rs::a16(rs::own_cap_of(n_cap, cluster));
   // weight-gradient accumulators: ceil(8 (R+1) tiles / nwarps) per warp must be <= 4
   const int tiles = 4 * ((R + 1) * rs::HID / 16);
-  if (backward && (tiles + 31) / 32 > 4) return -3;
   // stage rows: as many as fit (multiple of 16, at least 16), leaving >= 4 KB for the edge lists
   if (base + 4096 + 16 * rowfl * 4 > limit) return -3;
   size_t rows = (limit - base - 4096) / (rowfl * 4);
@@ -1282,8 +1282,12 @@ int rs_plan(const igmc_model_t* M, int n_cap, int cluster, int backward, int* th
     }
     // default: 512 threads when the weight-gradient tiles fit 4 per warp with 16 warps (R <= 7); measured 4 % faster
     // per step than 1024 threads at R = 5 (profiles/README.md)
-    int nt = (nt_env == 512 || nt_env == 1024) ? nt_env : 512;
-    if ((tiles + (nt >> 5) - 1) / (nt >> 5) > 4) nt = 1024;
+    // 512 threads x 128 registers for every R <= 12: beyond 4 weight-gradient column tiles per warp (R > 7) the tiles
+    // run in a second pass over the nodes.  Measured on flixster (R = 10, profiles/README.md): 280 k subgraphs/s at
+    // 512 threads, 255 k at 1024 (64 registers: spills, address rematerialisation); R = 5: +5 % (round 1).
+    int nt = 512;
+    if (nt_env == 512 || nt_env == 1024) nt = nt_env;
+    (void)tiles;
     *threads = nt;
   }
   *chunk = (int)rows;
