@@ -115,6 +115,9 @@ _SIGS = {
                      C.c_int, C.POINTER(Saved), vp, C.c_float, vp, vp, C.c_int, C.POINTER(Stage), vp, vp],
     "igmc_backward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),
                       C.POINTER(Saved), vp, vp, vp, C.c_int, C.POINTER(Stage), vp, vp],
+    "igmc_forward_backward": [C.POINTER(Model), vp, vp, vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout),
+                              C.POINTER(Saved), vp, C.c_float, vp, vp, vp, vp, C.c_int, C.POINTER(Stage),
+                              C.POINTER(Stage), vp, vp],
     "igmc_raw_grad_count": [C.POINTER(Model)],
     "igmc_stage_plan": [C.POINTER(Model), C.c_int, C.c_int, C.c_int, C.POINTER(Stage)],
     "igmc_stage_lists": [C.POINTER(Model), vp, vp, C.POINTER(Adj), C.c_int, C.c_int, C.POINTER(Dropout), C.c_int,

@@ -602,6 +602,11 @@ int rs_stage_lists(const igmc_model_t* M, const int32_t* node_ptr, const int32_t
                    cudaStream_t st);
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st);
+int rs_train(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
+             const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
+             const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, float* gpart,
+             float* dhid, int cluster, const igmc_stage_t* stage_f, const igmc_stage_t* stage_b, int* err,
+             cudaStream_t st);
 int rs_gate_wait(int* gate, int target, int timeout_us, cudaStream_t st);
 
 extern "C" int igmc_gate_wait(int32_t* gate, int target, int timeout_us, void* stream) {
@@ -685,6 +690,21 @@ extern "C" int igmc_forward(const igmc_model_t* M, const float* params, const ui
   }
   IGMC_CUDA_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" int igmc_forward_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
+                                     const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B,
+                                     int n_cap, const igmc_dropout_t* D, const igmc_saved_t* S, const float* y,
+                                     float loss_scale, float* dpred, float* sqerr, float* gpart, float* dhid,
+                                     int cluster, const igmc_stage_t* stage_fwd, const igmc_stage_t* stage_bwd,
+                                     int* err, void* stream) {
+  if (B <= 0) return 0;
+  int rc = check_model(M);
+  if (rc) return rc;
+  if (cluster <= 0 || M->readout != 0 || !rs_supported(M)) return -16;   // cluster plans, IGMC readout
+  if (!S->wprep || !S->zsave || !y || !dpred) return -17;
+  return rs_train(M, params, node_label, node_ptr, edge_ptr, A, B, n_cap, D, S, y, loss_scale, dpred, sqerr, gpart, dhid,
+                  cluster, stage_fwd, stage_bwd, err, (cudaStream_t)stream);
 }
 
 extern "C" int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,

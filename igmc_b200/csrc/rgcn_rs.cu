@@ -380,6 +380,87 @@ __device__ __forceinline__ void mma_3xtf32(float (&d)[4], float (&dsm)[4], const
   mma_tf32(d, ah, bh);
 }
 
+__device__ __forceinline__ void split_tf32(const float (&f)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    hi[i] = __float_as_uint(f[i]) & 0xffffe000u;
+    lo[i] = __float_as_uint(f[i] - __uint_as_float(hi[i]));
+  }
+}
+__device__ __forceinline__ void mma_3xtf32_a(float (&d)[4], float (&dsm)[4], const uint32_t (&ah)[4],
+                                             const uint32_t (&al)[4], const float (&bf)[2]) {
+  uint32_t bh[2], bl[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
+    bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i]));
+  }
+  mma_tf32(dsm, al, bh);
+  mma_tf32(dsm, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+// ---- NP adjacent 16x8 tiles (columns n0 + 8 i) of one 16-row block per warp: the A fragments are loaded and split
+// ONCE for all of them (the tile loops are issue bound: 4 LDS + 8 ALU for A and 2 LDS + 4 ALU + 3 HMMA per tile and
+// k-step; one tile per warp repeated the A part in the four warps of a row block).  Per output element the sums and
+// their order are those of one tile per warp: (d, e) take the even k-steps of the first span, (d2, e2) the odd ones
+// and the second (root) span; e/e2 hold the 3xTF32 cross terms.
+struct TileAcc { float d[4], d2[4], e[4], e2[4]; };
+__device__ __forceinline__ void tile_zero(TileAcc& t) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { t.d[i] = 0.f; t.d2[i] = 0.f; t.e[i] = 0.f; t.e2[i] = 0.f; }
+}
+// a0p / a1p: rows gq / gq + 8 of the block (+ tq), K-contiguous;  bp: row n0 + gq of the n-major slab (+ tq)
+template <int NP>
+__device__ __forceinline__ void tiles_span(TileAcc (&T)[NP], const float* __restrict__ a0p,
+                                           const float* __restrict__ a1p, const float* __restrict__ bp, int KS, int K) {
+  int k0 = 0;
+  for (; k0 + 16 <= K; k0 += 16) {                  // two independent accumulator sets per iteration
+    const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
+    const float ag[4] = {a0p[k0 + 8], a1p[k0 + 8], a0p[k0 + 12], a1p[k0 + 12]};
+    uint32_t ah[4], al[4], gh[4], gl[4];
+    split_tf32(af, ah, al);
+    split_tf32(ag, gh, gl);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float* b = bp + (size_t)i * 8 * KS + k0;
+      const float bf[2] = {b[0], b[4]}, bg[2] = {b[8], b[12]};
+      mma_3xtf32_a(T[i].d, T[i].e, ah, al, bf);
+      mma_3xtf32_a(T[i].d2, T[i].e2, gh, gl, bg);
+    }
+  }
+  for (; k0 < K; k0 += 8) {
+    const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
+    uint32_t ah[4], al[4];
+    split_tf32(af, ah, al);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float* b = bp + (size_t)i * 8 * KS + k0;
+      const float bf[2] = {b[0], b[4]};
+      mma_3xtf32_a(T[i].d, T[i].e, ah, al, bf);
+    }
+  }
+}
+// the second span (root / d pre rows), into (d2, e2).  pa / pb: the two 16-row-block rows' element pointers for
+// columns tq and tq + 4 (already swizzled), xa / xb: XOR applied to the k offset (hix swizzle bits 3-4; 0 = linear)
+template <int NP>
+__device__ __forceinline__ void tiles_span2(TileAcc (&T)[NP], const float* __restrict__ p0a, const float* __restrict__ p0b,
+                                            const float* __restrict__ p1a, const float* __restrict__ p1b, int x0, int x1,
+                                            const float* __restrict__ bp, int KS, int K) {
+  for (int k0 = 0; k0 < K; k0 += 8) {
+    const int o0 = k0 ^ x0, o1 = k0 ^ x1;
+    const float af[4] = {p0a[o0], p1a[o1], p0b[o0], p1b[o1]};
+    uint32_t ah[4], al[4];
+    split_tf32(af, ah, al);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+      const float* b = bp + (size_t)i * 8 * KS + k0;
+      const float bf[2] = {b[0], b[4]};
+      mma_3xtf32_a(T[i].d2, T[i].e2, ah, al, bf);
+    }
+  }
+}
+
 __host__ __device__ __forceinline__ int a8(int x) { return (x + 7) & ~7; }
 __host__ __device__ __forceinline__ int a16(int x) { return (x + 15) & ~15; }
 
@@ -448,13 +529,17 @@ __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.w
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
+// The forward of one subgraph as a device function (returns false when it bailed out on a data error, uniformly over
+// the cluster): body of k_forward_rs, and first half of the fused train kernel k_train_rs.
 template <int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1)
-k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
-             const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
-             int lcap, int chunk, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y,
-             float loss_scale, float* __restrict__ dpred, float* __restrict__ sqerr, igmc_stage_t IMG, int* err) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ bool forward_body(const igmc_model_t& M, const float* __restrict__ params,
+                                             const uint8_t* __restrict__ node_label,
+                                             const int32_t* __restrict__ node_ptr,
+                                             const int32_t* __restrict__ edge_ptr, const igmc_adj_t& A, int n_cap,
+                                             int lcap, int chunk, const igmc_dropout_t& D, int training,
+                                             const igmc_saved_t& S, const float* __restrict__ y, float loss_scale,
+                                             float* __restrict__ dpred, float* __restrict__ sqerr,
+                                             const igmc_stage_t& IMG, int* err, float* smem) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int g = blockIdx.x / CL;
@@ -481,7 +566,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   const int eb = edge_ptr[g], m_half = (edge_ptr[g + 1] - eb) >> 1;
   if (n > n_cap) {   // uniform over the cluster
     if (tid == 0) igmc_set_err(err, IGMC_ERR_SMEM_NODES);
-    return;
+    return false;
   }
   const Keep K = make_keep(D, training);
   const Split own = own_range(n, rank, CL);
@@ -551,7 +636,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   if (!ext && (tu >= n || ti >= n)) {
     if (tid == 0) igmc_set_err(err, IGMC_ERR_BAD_BATCH);
     mbar_wait(&mbar[1], 0);   // do not exit under an in-flight bulk copy
-    return;
+    return false;
   }
   if (S.prof && tid == 0) {   // debug: staging facts
     long long* pp = S.prof + (size_t)blockIdx.x * 64;
@@ -565,6 +650,9 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     const int K1 = R * inp, K1p = a8(K1), inpp = a8(inp), SS = K1p + 4, KS = K1p + inpp + 4;
     __syncthreads();
     IGMC_STAMP(2 + 6 * l);
+    float* peerH[3];   // this layer's output buffer in the other CTAs of the cluster (mapped once, not per tile)
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) peerH[pr] = pr + 1 < CL ? cluster.map_shared_rank(Hn, (rank + pr + 1) % CL) : Hn;
     for (int c0 = 0; c0 < n_own; c0 += chunk) {
       const int crow = min(chunk, n_own - c0);
       // ---- aggregate: one 8-lane group per list segment ----
@@ -602,52 +690,38 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
       // ---- dense transform on tensor cores: out[16x8 tiles] = [AGG' | h] . [W_r ; root] ----
       if (c0 == 0) mbar_wait(&mbar[1], (uint32_t)(l & 1));   // this layer's weight slab has landed
       const int mt = (crow + 15) >> 4;
-      for (int tile = warp; tile < mt * 4; tile += nwarps) {
-        const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
-        float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-        float e[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};   // cross-term accumulators
+      for (int item = warp; item < mt * 2; item += nwarps) {   // warp = (16-row block, 16-column half)
+        const int m0 = (item >> 1) << 4, nh = (item & 1) << 4;
+        TileAcc T[2];
+        tile_zero(T[0]); tile_zero(T[1]);
         const float* a0p = stage + (size_t)(m0 + gq) * SS + tq;
-        const float* a1p = a0p + 8 * SS;
-        const float* bp = Wn + (size_t)(n0 + gq) * KS + tq;
-        int k0 = 0;
-        for (; k0 + 16 <= K1p; k0 += 16) {                  // two independent accumulator sets per iteration
-          const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
-          const float bf[2] = {bp[k0], bp[k0 + 4]};
-          const float ag[4] = {a0p[k0 + 8], a1p[k0 + 8], a0p[k0 + 12], a1p[k0 + 12]};
-          const float bg[2] = {bp[k0 + 8], bp[k0 + 12]};
-          mma_3xtf32(d, e, af, bf);
-          mma_3xtf32(d2, e2, ag, bg);
-        }
-        for (; k0 < K1p; k0 += 8) {
-          const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
-          const float bf[2] = {bp[k0], bp[k0 + 4]};
-          mma_3xtf32(d, e, af, bf);
-        }
+        const float* bp = Wn + (size_t)(nh + gq) * KS + tq;
+        tiles_span<2>(T, a0p, a0p + 8 * SS, bp, KS, K1p);
         const int r0 = c0 + m0 + gq, r1 = r0 + 8;           // rows relative to the own range
         const int v0 = own.lo + min(r0, n_own - 1), v1 = own.lo + min(r1, n_own - 1);
+        const int sw0 = (v0 & 7) << 2, sw1 = (v1 & 7) << 2;   // hix(): column ^ swizzle, split into its bit 2 and bits 3-4
         const float* h0 = H + (v0 << 5);
         const float* h1 = H + (v1 << 5);
-        const int sw0 = (v0 & 7) << 2, sw1 = (v1 & 7) << 2;
-        for (k0 = 0; k0 < inpp; k0 += 8) {
-          const float af[4] = {h0[(k0 + tq) ^ sw0], h1[(k0 + tq) ^ sw1], h0[(k0 + tq + 4) ^ sw0], h1[(k0 + tq + 4) ^ sw1]};
-          const float bf[2] = {bp[K1p + k0], bp[K1p + k0 + 4]};
-          mma_3xtf32(d2, e2, af, bf);
-        }
+        tiles_span2<2>(T, h0 + (tq | (sw0 & 4)), h0 + (tq | ((sw0 & 4) ^ 4)), h1 + (tq | (sw1 & 4)),
+                       h1 + (tq | ((sw1 & 4) ^ 4)), sw0 & 24, sw1 & 24, bp + K1p, KS, inpp);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) d[i] = (d[i] + d2[i]) + (e[i] + e2[i]);
-        const int cc = n0 + 2 * tq;
-        const float b0 = bias_s[cc], b1 = bias_s[cc + 1];
+        for (int i = 0; i < 2; ++i) {
+          float d[4];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          const int r = half ? r1 : r0;
-          if (r < n_own) {
-            const int v = own.lo + r;
-            const float2 o = make_float2(tanhf(d[2 * half] + b0), tanhf(d[2 * half + 1] + b1));
-            const int off = hix(v, cc);
-            *reinterpret_cast<float2*>(Hn + off) = o;
-            for (int pr = 1; pr < CL; ++pr) {   // push the row slice to the other CTAs of the cluster (DSMEM)
-              float* peer = cluster.map_shared_rank(Hn, (rank + pr) % CL);
-              *reinterpret_cast<float2*>(peer + off) = o;
+          for (int q = 0; q < 4; ++q) d[q] = (T[i].d[q] + T[i].d2[q]) + (T[i].e[q] + T[i].e2[q]);
+          const int cc = nh + 8 * i + 2 * tq;
+          const float b0 = bias_s[cc], b1 = bias_s[cc + 1];
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int r = half ? r1 : r0;
+            if (r < n_own) {
+              const int v = own.lo + r;
+              const float2 o = make_float2(tanhf(d[2 * half] + b0), tanhf(d[2 * half + 1] + b1));
+              const int off = hix(v, cc);
+              *reinterpret_cast<float2*>(Hn + off) = o;
+#pragma unroll
+              for (int pr = 0; pr < 3; ++pr)   // push the row slice to the other CTAs of the cluster (DSMEM)
+                if (pr + 1 < CL) *reinterpret_cast<float2*>(peerH[pr] + off) = o;
             }
           }
         }
@@ -677,7 +751,7 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
     }
   }
 
-  if (rank != 0 || ext) { IGMC_WALL(51); return; }
+  if (rank != 0 || ext) { IGMC_WALL(51); return true; }
   // ---- readout (models.py:205-215), one CTA of the cluster ----
   __syncthreads();
   for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
@@ -734,6 +808,18 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
   }
   IGMC_STAMP(2 + 6 * L);
   IGMC_WALL(51);
+  return true;
+}
+
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
+k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
+             const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
+             int lcap, int chunk, igmc_dropout_t D, int training, igmc_saved_t S, const float* __restrict__ y,
+             float loss_scale, float* __restrict__ dpred, float* __restrict__ sqerr, igmc_stage_t IMG, int* err) {
+  extern __shared__ __align__(16) float smem[];
+  forward_body<NTMAX>(M, params, node_label, node_ptr, edge_ptr, A, n_cap, lcap, chunk, D, training, S, y, loss_scale,
+                      dpred, sqerr, IMG, err, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -742,24 +828,23 @@ k_forward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __
 constexpr int DPS_ = 40;   // row stride of the own-rows dpre / h_{l-1} copies (== 8 mod 32: conflict-free k-major fragments)
 
 // 3xTF32 with the A operand split once (it is reused for several B tiles)
-__device__ __forceinline__ void split_tf32(const float (&f)[4], uint32_t (&hi)[4], uint32_t (&lo)[4]) {
+
+// weight-gradient tiles of one warp over the chunk's nodes: CNT column tiles share the A^T fragment of a k-step
+template <int CNT>
+__device__ __forceinline__ void wgrad_pass(const float* __restrict__ ha, const float* const (&bb)[4], const int (&bst)[4],
+                                           int krows, float (&acc)[4][4], float (&acs)[4][4]) {
+  for (int k0 = 0; k0 < krows; k0 += 8) {
+    const float* a = ha + (size_t)k0 * DPS_;
+    const float af[4] = {a[0], a[8], a[4 * DPS_], a[4 * DPS_ + 8]};
+    uint32_t ah[4], al[4];
+    split_tf32(af, ah, al);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    hi[i] = __float_as_uint(f[i]) & 0xffffe000u;
-    lo[i] = __float_as_uint(f[i] - __uint_as_float(hi[i]));
+    for (int i = 0; i < CNT; ++i) {
+      const float* bp = bb[i] + (size_t)k0 * bst[i];
+      const float bf[2] = {bp[0], bp[4 * bst[i]]};
+      mma_3xtf32_a(acc[i], acs[i], ah, al, bf);
+    }
   }
-}
-__device__ __forceinline__ void mma_3xtf32_a(float (&d)[4], float (&dsm)[4], const uint32_t (&ah)[4],
-                                             const uint32_t (&al)[4], const float (&bf)[2]) {
-  uint32_t bh[2], bl[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    bh[i] = __float_as_uint(bf[i]) & 0xffffe000u;
-    bl[i] = __float_as_uint(bf[i] - __uint_as_float(bh[i]));
-  }
-  mma_tf32(dsm, al, bh);
-  mma_tf32(dsm, ah, bl);
-  mma_tf32(d, ah, bh);
 }
 
 // Per layer l (top down), for the own nodes u of this CTA:
@@ -771,12 +856,15 @@ __device__ __forceinline__ void mma_3xtf32_a(float (&d)[4], float (&dsm)[4], con
 //   Layer 0 has no data gradient; its dW_r come from the saved aggregate of the one-hot input (S.zsave).
 // The (att, basis) chain rule is NOT applied here: it is linear and runs once on the sum (igmc_grad_reduce).
 template <int NTMAX>
-__global__ void __launch_bounds__(NTMAX, 1)
-k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
-              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
-              int lcap, int chunk, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred,
-              float* __restrict__ gpart, float* __restrict__ dhid_out, igmc_stage_t IMG, int* err) {
-  extern __shared__ __align__(16) float smem[];
+__device__ __forceinline__ void backward_body(const igmc_model_t& M, const float* __restrict__ params,
+                                              const uint8_t* __restrict__ node_label,
+                                              const int32_t* __restrict__ node_ptr,
+                                              const int32_t* __restrict__ edge_ptr, const igmc_adj_t& A, int n_cap,
+                                              int lcap, int chunk, const igmc_dropout_t& D, const igmc_saved_t& S,
+                                              const float* dpred /* written by this launch in k_train_rs */,
+                                              float* __restrict__ gpart,
+                                              float* __restrict__ dhid_out, const igmc_stage_t& IMG, int* err,
+                                              float* smem) {
   cg::cluster_group cluster = cg::this_cluster();
   const int CL = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
   const int g = blockIdx.x / CL;
@@ -869,7 +957,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
       if (rank == 0) dhid_out[(size_t)g * L1O + o] = d;
     }
   }
-  for (int v = tid; v < n; v += NT) invdeg[v] = S.inv_deg[nb + v];
+  for (int v = tid; v < n; v += NT) invdeg[v] = __ldcg(S.inv_deg + nb + v);   // (peer rows: L2, see k_train_rs)
   __syncthreads();
   if (!ext) {
     // d feat[i] = sum_o W1[o][i] d hid[o]: thread slice p of NT/F takes every (NT/F)-th o, partials in `stage`
@@ -918,6 +1006,9 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     float* DPS = (l & 1) ? DH1 : DH0;                    // d h_l on entry, dpre/deg after step (0)
     float* DHn = (l & 1) ? DH0 : DH1;                    // d h_{l-1} (written here and by the peers)
     float* gpl = gp + igmc_raw_off(R, in0, l);           // this layer's block of the raw partial row
+    float* peerD[3];   // d h_{l-1} in the other CTAs of the cluster (mapped once per layer, not per tile)
+#pragma unroll
+    for (int pr = 0; pr < 3; ++pr) peerD[pr] = pr + 1 < CL ? cluster.map_shared_rank(DHn, (rank + pr + 1) % CL) : DHn;
     // (0) d pre = d h (1 - h^2);  DPS = d pre / deg (gather source), DP = d pre of the own rows (padded with zeros)
     for (int idx = tid; idx < n * 8; idx += NT) {
       const int v = idx >> 3, c4 = (idx & 7) * 4;
@@ -989,55 +1080,40 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
         IGMC_STAMP(sb + 6);
         if (c0 == 0) { mbar_wait(&mbar[1], wuse & 1u); ++wuse; }   // [W_r^T ; root^T] has landed
         const int mt = (crow + 15) >> 4;
-        for (int tile = warp; tile < mt * 4; tile += nwarps) {
-          const int m0 = (tile >> 2) << 4, n0 = (tile & 3) << 3;
-          float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-          float e[4] = {0.f, 0.f, 0.f, 0.f}, e2[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int item = warp; item < mt * 2; item += nwarps) {   // warp = (16-row block, 16-column half)
+          const int m0 = (item >> 1) << 4, nh = (item & 1) << 4;
+          TileAcc T[2];
+          tile_zero(T[0]); tile_zero(T[1]);
           const float* a0p = stage + (size_t)(m0 + gq) * SS + tq;
-          const float* a1p = a0p + 8 * SS;
-          const float* bp = Wn + (size_t)(n0 + gq) * KS + tq;
-          int k0 = 0;
-          for (; k0 + 16 <= K1p; k0 += 16) {
-            const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
-            const float bf[2] = {bp[k0], bp[k0 + 4]};
-            const float ag[4] = {a0p[k0 + 8], a1p[k0 + 8], a0p[k0 + 12], a1p[k0 + 12]};
-            const float bg[2] = {bp[k0 + 8], bp[k0 + 12]};
-            mma_3xtf32(d, e, af, bf);
-            mma_3xtf32(d2, e2, ag, bg);
-          }
-          for (; k0 < K1p; k0 += 8) {
-            const float af[4] = {a0p[k0], a1p[k0], a0p[k0 + 4], a1p[k0 + 4]};
-            const float bf[2] = {bp[k0], bp[k0 + 4]};
-            mma_3xtf32(d, e, af, bf);
-          }
+          const float* bp = Wn + (size_t)(nh + gq) * KS + tq;
+          tiles_span<2>(T, a0p, a0p + 8 * SS, bp, KS, K1p);
           const int r0 = c0 + m0 + gq, r1 = r0 + 8;
           const float* p0 = DP + (size_t)min(r0, own_cap16 - 1) * DPS_ + tq;
           const float* p1 = DP + (size_t)min(r1, own_cap16 - 1) * DPS_ + tq;
-          for (k0 = 0; k0 < HID; k0 += 8) {
-            const float af[4] = {p0[k0], p1[k0], p0[k0 + 4], p1[k0 + 4]};
-            const float bf[2] = {bp[K1p + k0], bp[K1p + k0 + 4]};
-            mma_3xtf32(d2, e2, af, bf);
-          }
+          tiles_span2<2>(T, p0, p0 + 4, p1, p1 + 4, 0, 0, bp + K1p, KS, HID);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) d[i] = (d[i] + d2[i]) + (e[i] + e2[i]);
-          const int cc = n0 + 2 * tq;
+          for (int i = 0; i < 2; ++i) {
+            float d[4];
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int r = half ? r1 : r0;
-            if (r < n_own) {
-              const int u = own.lo + r;
-              float2 o = make_float2(d[2 * half], d[2 * half + 1]);
-              if (ext) {
-                const float2 sd = __ldg(reinterpret_cast<const float2*>(S.dstate + (size_t)(nb + u) * CW + (l - 1) * HID + cc));
-                o.x += sd.x; o.y += sd.y;
-              }
-              if (u == tu) { o.x += dfeat[(l - 1) * HID + cc]; o.y += dfeat[(l - 1) * HID + cc + 1]; }
-              if (u == ti) { o.x += dfeat[CW + (l - 1) * HID + cc]; o.y += dfeat[CW + (l - 1) * HID + cc + 1]; }
-              const int off = hix(u, cc);
-              *reinterpret_cast<float2*>(DHn + off) = o;
-              for (int pr = 1; pr < CL; ++pr) {
-                float* peer = cluster.map_shared_rank(DHn, (rank + pr) % CL);
-                *reinterpret_cast<float2*>(peer + off) = o;
+            for (int q = 0; q < 4; ++q) d[q] = (T[i].d[q] + T[i].d2[q]) + (T[i].e[q] + T[i].e2[q]);
+            const int cc = nh + 8 * i + 2 * tq;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              const int r = half ? r1 : r0;
+              if (r < n_own) {
+                const int u = own.lo + r;
+                float2 o = make_float2(d[2 * half], d[2 * half + 1]);
+                if (ext) {
+                  const float2 sd = __ldg(reinterpret_cast<const float2*>(S.dstate + (size_t)(nb + u) * CW + (l - 1) * HID + cc));
+                  o.x += sd.x; o.y += sd.y;
+                }
+                if (u == tu) { o.x += dfeat[(l - 1) * HID + cc]; o.y += dfeat[(l - 1) * HID + cc + 1]; }
+                if (u == ti) { o.x += dfeat[CW + (l - 1) * HID + cc]; o.y += dfeat[CW + (l - 1) * HID + cc + 1]; }
+                const int off = hix(u, cc);
+                *reinterpret_cast<float2*>(DHn + off) = o;
+#pragma unroll
+                for (int pr = 0; pr < 3; ++pr)
+                  if (pr + 1 < CL) *reinterpret_cast<float2*>(peerD[pr] + off) = o;
               }
             }
           }
@@ -1059,25 +1135,26 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
 #pragma unroll
             for (int c = 0; c < 4; ++c) { acc[i][c] = 0.f; acs[i][c] = 0.f; }
           const int krows = a8(crow);                       // rows beyond crow: Hs is zero there, stage/DP are finite
-          for (int k0 = 0; k0 < krows; k0 += 8) {
-            // A^T fragment: row = k (m0+g), col = node (k0+t)
-            const float* a = Hs + (size_t)(k0 + tq) * DPS_ + m0 + gq;
-            const float af[4] = {a[0], a[8], a[4 * DPS_], a[4 * DPS_ + 8]};
-            uint32_t ah[4], al[4];
-            split_tf32(af, ah, al);
+          // B fragments (k = node, n = column of [Q | dpre]): base pointer and row stride of each of the warp's column
+          // tiles, fixed over the node loop
+          const float* bb[MAXI];
+          int bst[MAXI];
+          int cnt = 0;
 #pragma unroll
-            for (int i = 0; i < MAXI; ++i) {
-              const int jn = jn0 + i * jstep;
-              if (jn < NTN) {
-                const int n0 = jn << 3;
-                // B fragment: k = node, n = column of [Q | dpre]
-                const float* bp = n0 < K1 ? stage + (size_t)(k0 + tq) * SS + n0 + gq
-                                          : DP + (size_t)(c0 + k0 + tq) * DPS_ + (n0 - K1) + gq;
-                const int bs4 = n0 < K1 ? 4 * SS : 4 * DPS_;
-                const float bf[2] = {bp[0], bp[bs4]};
-                mma_3xtf32_a(acc[i], acs[i], ah, al, bf);
-              }
-            }
+          for (int i = 0; i < MAXI; ++i) {
+            const int jn = jn0 + i * jstep, n0 = jn << 3;
+            if (jn < NTN) cnt = i + 1;
+            const bool q = n0 < K1 || jn >= NTN;
+            bb[i] = jn >= NTN ? stage : q ? stage + (size_t)tq * SS + n0 + gq
+                                          : DP + (size_t)(c0 + tq) * DPS_ + (n0 - K1) + gq;
+            bst[i] = q ? SS : DPS_;
+          }
+          const float* ha = Hs + (size_t)tq * DPS_ + m0 + gq;   // A^T fragment: row = k (m0+g), col = node (k0+t)
+          switch (cnt) {   // (uniform over the warp) one straight-line node loop per tile count
+            case 4: wgrad_pass<4>(ha, bb, bst, krows, acc, acs); break;
+            case 3: wgrad_pass<3>(ha, bb, bst, krows, acc, acs); break;
+            case 2: wgrad_pass<2>(ha, bb, bst, krows, acc, acs); break;
+            default: wgrad_pass<1>(ha, bb, bst, krows, acc, acs); break;
           }
 #pragma unroll
           for (int i = 0; i < MAXI; ++i) {
@@ -1130,7 +1207,7 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
           for (int idx = tid; idx < rows * kq; idx += NT) {
             const int r_ = idx / kq, k4 = idx - r_ * kq;
             float4 val = z4;
-            if (t0 + r_ < n_own) val = __ldg(reinterpret_cast<const float4*>(zbase + (size_t)r_ * K1) + k4);
+            if (t0 + r_ < n_own) val = __ldcg(reinterpret_cast<const float4*>(zbase + (size_t)r_ * K1) + k4);
             t4[r_ * TS4 + k4] = val;
           }
           const int tail = KRp - K1;   // zero padding of the aggregate + the one-hot input columns
@@ -1186,6 +1263,41 @@ k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* _
     IGMC_STAMP(sb + 4);
   }
   IGMC_WALL(54);
+}
+
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
+k_backward_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
+              const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
+              int lcap, int chunk, igmc_dropout_t D, igmc_saved_t S, const float* __restrict__ dpred,
+              float* __restrict__ gpart, float* __restrict__ dhid_out, igmc_stage_t IMG, int* err) {
+  extern __shared__ __align__(16) float smem[];
+  backward_body<NTMAX>(M, params, node_label, node_ptr, edge_ptr, A, n_cap, lcap, chunk, D, S, dpred, gpart, dhid_out,
+                       IMG, err, smem);
+}
+
+// Forward and backward of one subgraph in ONE kernel (training): the loss gradient of a subgraph depends on its own
+// forward only (dpred[g] = 2 (out_g - y_g) / G), so a cluster goes straight from its readout into its backward - no
+// second launch, and the spread of the forward times over the clusters is not paid twice (every cluster used to wait
+// for the slowest forward before any backward could start).  The shared memory is re-carved for the backward; what the
+// backward reads of the forward travels through global memory exactly as between the two separate kernels, ordered
+// by a device fence + cluster barrier (the peer CTA wrote half of the states / inv_deg rows, rank 0 the readout).
+template <int NTMAX>
+__global__ void __launch_bounds__(NTMAX, 1)
+k_train_rs(igmc_model_t M, const float* __restrict__ params, const uint8_t* __restrict__ node_label,
+           const int32_t* __restrict__ node_ptr, const int32_t* __restrict__ edge_ptr, igmc_adj_t A, int n_cap,
+           int lcap_f, int chunk_f, int lcap_b, int chunk_b, igmc_dropout_t D, igmc_saved_t S,
+           const float* __restrict__ y, float loss_scale, float* __restrict__ dpred, float* __restrict__ sqerr,
+           float* __restrict__ gpart, float* __restrict__ dhid_out, igmc_stage_t IMGF, igmc_stage_t IMGB, int* err) {
+  extern __shared__ __align__(16) float smem[];
+  const bool ok = forward_body<NTMAX>(M, params, node_label, node_ptr, edge_ptr, A, n_cap, lcap_f, chunk_f, D, 1, S, y,
+                                      loss_scale, dpred, sqerr, IMGF, err, smem);
+  if (!ok) return;   // uniform over the cluster
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");   // the backward's bulk copies read state rows written above
+  cg::this_cluster().sync();   // (a cluster of one CTA: a block barrier)
+  backward_body<NTMAX>(M, params, node_label, node_ptr, edge_ptr, A, n_cap, lcap_b, chunk_b, D, S, dpred, gpart,
+                       dhid_out, IMGB, err, smem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1442,6 +1554,34 @@ int rs_gate_wait(int* gate, int target, int timeout_us, cudaStream_t st) {
   rs::k_gate_wait<<<1, 32, 0, st>>>(gate, target, (long long)timeout_us * 1000);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : (int)e + 1000;
+}
+
+int rs_train(const igmc_model_t* M, const float* params, const uint8_t* node_label, const int32_t* node_ptr,
+             const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap, const igmc_dropout_t* D,
+             const igmc_saved_t* S, const float* y, float loss_scale, float* dpred, float* sqerr, float* gpart,
+             float* dhid, int cluster, const igmc_stage_t* stage_f, const igmc_stage_t* stage_b, int* err,
+             cudaStream_t st) {
+  int tf, tb, lcf, lcb, chf, chb;
+  size_t smf, smb;
+  int rc = rs_plan(M, n_cap, cluster, 0, &tf, &smf, &lcf, &chf);
+  if (rc) return rc;
+  rc = rs_plan(M, n_cap, cluster, 1, &tb, &smb, &lcb, &chb);
+  if (rc) return rc;
+  if (tf != tb) return -3;
+  igmc_stage_t imf, imb;
+  rc = check_image(stage_f, n_cap, cluster, lcf, chf, &imf);
+  if (rc) return rc;
+  if (imf.tab && !imf.inv_deg) return -19;
+  rc = check_image(stage_b, n_cap, cluster, lcb, chb, &imb);
+  if (rc) return rc;
+  const size_t smem = smf > smb ? smf : smb;
+  if (tf == 512)
+    return launch_cluster(rs::k_train_rs<512>, B * cluster, tf, smem, cluster, false, st, *M, params, node_label, node_ptr,
+                          edge_ptr, *A, n_cap, lcf, chf, lcb, chb, *D, *S, y, loss_scale, dpred, sqerr, gpart, dhid, imf,
+                          imb, err);
+  return launch_cluster(rs::k_train_rs<1024>, B * cluster, tf, smem, cluster, false, st, *M, params, node_label, node_ptr,
+                        edge_ptr, *A, n_cap, lcf, chf, lcb, chb, *D, *S, y, loss_scale, dpred, sqerr, gpart, dhid, imf, imb,
+                        err);
 }
 
 int rs_prep_weights(const igmc_model_t* M, const float* params, float* wprep, cudaStream_t st) {

@@ -464,9 +464,31 @@ class IGMC(nn.Module):
         self._step += 1
         drop = self.make_dropout(True, edge_keep, hidden_keep, seed_dev=seed_dev)
         G = batch.num_graphs if global_num_graphs is None else int(global_num_graphs)
+        if self._cmodel.readout == 0 and self._plan(batch) > 0 and os.environ.get("IGMC_FUSED_FB", "1") != "0":
+            return self._launch_train(batch, drop, batch.y, 1.0 / G)
         out, saved = self._launch_forward(batch, True, drop, y=batch.y, loss_scale=1.0 / G)
         self._launch_backward(batch, drop, saved, saved["ws"]["dpred"])
         return saved
+
+    def _launch_train(self, batch, drop, y, loss_scale):
+        """forward + loss + backward as ONE launch (igmc_forward_backward): cluster plans, IGMC readout."""
+        lib = _lib.load()
+        p = batch._priv
+        adj_c, _ = batch.adjacency()
+        ws = self._workspace(batch, True)
+        S = self._saved_struct(ws, p["node_cap"])
+        d, keep = drop
+        if not self.__dict__.pop("_prepped", False):
+            self.prep_weights()
+        _lib.check(lib.igmc_forward_backward(C.byref(self._cmodel), self.flat_params.data_ptr(),
+                                             p["node_label"].data_ptr(), p["node_ptr"].data_ptr(),
+                                             p["edge_ptr"].data_ptr(), C.byref(adj_c), batch.num_graphs, p["n_cap"],
+                                             C.byref(d), C.byref(S), y.data_ptr(), float(loss_scale),
+                                             ws["dpred"].data_ptr(), ws["sqerr"].data_ptr(), ws["gpart"].data_ptr(),
+                                             ws["dhid"].data_ptr(), ws["cluster"], self._stage_arg(batch, "fwd"),
+                                             self._stage_arg(batch, "bwd"), batch._err.data_ptr(), _stream_ptr()),
+                   "igmc_forward_backward")
+        return dict(ws=ws, S=S, train=True, dpred_used=ws["dpred"])
 
     def fused_update_ok(self, batch):
         """the one-kernel reduce -> all-reduce -> Adam path needs raw partial rows (cluster plans) and the IGMC

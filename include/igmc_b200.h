@@ -268,6 +268,16 @@ int igmc_backward(const igmc_model_t* M, const float* params, const uint8_t* nod
                   const igmc_dropout_t* D, const igmc_saved_t* S, const float* dpred,
                   float* gpart, float* dhid, int cluster, const igmc_stage_t* stage, int* err, void* stream);
 
+/* igmc_forward (training, with the loss) immediately followed by igmc_backward for the same batch, as ONE launch: a
+ * cluster goes from its subgraph's readout straight into its backward (d loss / d pred of a subgraph depends on that
+ * subgraph's forward only).  Same arguments, same results bit for bit as the two calls; cluster plans with the IGMC
+ * readout only.  What `loss = mse_loss(model(data), y); loss.backward()` spans in train_eval.py:160-175. */
+int igmc_forward_backward(const igmc_model_t* M, const float* params, const uint8_t* node_label,
+                          const int32_t* node_ptr, const int32_t* edge_ptr, const igmc_adj_t* A, int B, int n_cap,
+                          const igmc_dropout_t* D, const igmc_saved_t* S, const float* y, float loss_scale,
+                          float* dpred, float* sqerr, float* gpart, float* dhid, int cluster,
+                          const igmc_stage_t* stage_fwd, const igmc_stage_t* stage_bwd, int* err, void* stream);
+
 /* floats per raw gradient row of the cluster plans (see igmc_backward) */
 int igmc_raw_grad_count(const igmc_model_t* M);
 

@@ -276,3 +276,39 @@ def test_staged_list_images_equal_self_staged(plan, adj_dropout, symmetric):
     assert torch.equal(m.flat_grad, g0)
     assert float(g0.abs().max()) > 0
     b._stage = None
+
+
+@pytest.mark.parametrize("plan,staged", [(1, False), (2, False), (2, True), (3, True), (4, True), (4, False)])
+def test_one_launch_forward_backward_equals_two_launches(plan, staged, monkeypatch):
+    """igmc_forward_backward (a cluster runs its subgraph's forward, loss and backward in ONE launch) against
+    igmc_forward + igmc_backward on the same batch and dropout draws: predictions, raw gradient rows, readout
+    factors and the assembled gradient are BIT-identical."""
+    from igmc_b200.util_functions import MyDynamicDataset
+    A, (u, v, lab), cv, ob = _oracle_batch(B=12)
+    ref, m = _models(adj_dropout=0.2, plan=plan)
+    m.train()
+    ds = MyDynamicDataset(None, A, (u, v), lab, 1, 1.0, 30, None, None, cv, seed=5)
+    b = ds.extract_batch(np.arange(12))
+    hk = torch.rand(12, 128, generator=torch.Generator().manual_seed(2)) > 0.5
+    got = []
+    for fused in ("0", "1", "1"):
+        monkeypatch.setenv("IGMC_FUSED_FB", fused)
+        m._step = 30
+        if staged:
+            m._step = 31
+            assert m.stage_batch(b, True, m.make_dropout(True)) is not None
+            m._step = 30
+        m.flat_grad.zero_()
+        saved = m.forward_backward(b, hidden_keep=hk)
+        ws = saved["ws"]
+        ws["gpart_copy"] = ws["gpart"].clone()
+        m._launch_grad_reduce(b, saved, loss_scale=1.0 / 12, arr=0.001)
+        b.check()
+        got.append((ws["pred"].clone(), ws["gpart_copy"], ws["dhid"].clone(), ws["dpred"].clone(),
+                    m.flat_grad.clone(), float(ws["loss"])))
+        b._stage = None
+    for a, c in ((got[0], got[1]), (got[1], got[2])):
+        for x, y in zip(a[:5], c[:5]):
+            assert torch.equal(x, y)
+        assert a[5] == c[5]
+    assert float(got[0][4].abs().max()) > 0
