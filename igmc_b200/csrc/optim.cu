@@ -626,7 +626,7 @@ extern "C" int igmc_reduce_update(const igmc_model_t* M, float* params, int B, i
     pdl = e ? atoi(e) : 0;   // off by default (same reason as the backward, csrc/rgcn_rs.cu)
   }
   cfg.attrs = at;
-  cfg.numAttrs = pdl ? 1 : 0;
+  cfg.numAttrs = (pdl & 2) ? 1 : 0;   // IGMC_PDL bit 1 (bit 0: the backward, csrc/rgcn_rs.cu)
   cudaError_t e = cudaLaunchKernelEx(&cfg, k_reduce_allreduce_adam, *M, params, B, gpart_rows, NA, gpart, dhid, feat, hid,
                                      dpred, sqerr, loss_scale, arr, *comm, exp_avg, exp_avg_sq, step_count, lr, lr_dev,
                                      beta1, beta2, log((double)beta1), log((double)beta2), eps, weight_decay, grad_mul,

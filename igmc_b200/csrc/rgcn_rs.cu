@@ -264,16 +264,19 @@ __device__ __forceinline__ Lists stage_lists(const uint32_t* adj, const int32_t*
 // segments of similar length taken at the same time keep their lanes busy (a warp-instruction of the edge loop had
 // 14 of 32 lanes active with the node-order assignment, profiles/README.md).  Which group computes a segment does
 // not change its result (own staging row, fixed summation order): the output stays bitwise deterministic.
+// GL = lanes per segment (one float4 each): 8 for the 32-wide layers; 1 for a 4-wide input layer (one-hot labels) -
+// there seven of the eight lanes of a group had nothing to do, now a warp works on 32 segments at a time.
+template <int GL>
 __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, int sg0, int sg1, int lane,
                                                 const float* __restrict__ feat, float* __restrict__ stage, int SS,
                                                 int inp, int* ticket) {
-  const int q = lane & 7;
+  const int q = lane & (GL - 1);
   const int fo = 4 * q;
   const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
   for (;;) {
     int t = 0;
-    if (q == 0) t = sg0 + atomicAdd(ticket, 1);
-    t = __shfl_sync(IGMC_FULL, t, lane & ~7);
+    if (lane == 0) t = atomicAdd(ticket, 32 / GL);   // 32 / GL consecutive segments (similar lengths) per warp
+    t = sg0 + __shfl_sync(IGMC_FULL, t, 0) + lane / GL;
     const bool valid = t < sg1;
     if (!__any_sync(IGMC_FULL, valid)) break;
     const int sg = valid ? Ls.seg_ord[t] : 0;
@@ -281,7 +284,7 @@ __device__ __forceinline__ void gather_segments(const Lists& Ls, const Keep& K, 
     int p = 0, p1 = 0;
     if (valid) {
       rowb = stage + (size_t)Ls.seg_row[sg] * SS;
-      for (int i = q * 4; i < SS; i += 32) *reinterpret_cast<float4*>(rowb + i) = z4;
+      for (int i = q * 4; i < SS; i += 4 * GL) *reinterpret_cast<float4*>(rowb + i) = z4;
       if (fo < inp) { p = Ls.seg_p0[sg]; p1 = Ls.seg_p1[sg]; }
     }
     __syncwarp();
@@ -658,17 +661,23 @@ __device__ __forceinline__ bool forward_body(const igmc_model_t& M, const float*
       // ---- aggregate: one 8-lane group per list segment ----
 #define IGMC_STAMP_T(t_, i_) do { if (S.prof && l == 1 && threadIdx.x == (t_)) S.prof[(size_t)blockIdx.x * 64 + (i_)] = clock64(); } while (0)
       IGMC_STAMP_T(0, 39); IGMC_STAMP_T(992, 49);
-      gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, H, stage, SS, inp, &ws[33]);
+      if (inp == 4) gather_segments<1>(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, H, stage, SS, inp, &ws[33]);
+      else gather_segments<8>(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, H, stage, SS, inp, &ws[33]);
       IGMC_STAMP_T(0, 40); IGMC_STAMP_T(992, 43); IGMC_STAMP_T(480, 46);
+      if (l == 0) IGMC_STAMP(32);
       __syncthreads();
+      if (l == 0) IGMC_STAMP(33);
       if (tid == 0) ws[33] = 0;   // re-arm the segment ticket (the next gather is several barriers away)
       IGMC_STAMP_T(0, 41); IGMC_STAMP_T(992, 44);
       // ---- fold the extra segments of long lists into their node row, scale by 1/deg, keep a copy for backward ----
       {
         const int kq = K1 >> 2, SS4 = SS >> 2;
         float4* st4 = reinterpret_cast<float4*>(stage);
-        for (int idx = tid; idx < crow * kq; idx += NT) {   // flat over (row, float4): independent iterations
-          const int r = idx / kq, k4 = idx - r * kq;
+        // flat over (row, float4): independent iterations; (r, k4) advance by NT = dr * kq + dk without a division
+        const int dr = NT / kq, dk = NT - dr * kq;
+        int r = tid / kq, k4 = tid - r * kq;
+        for (int idx = tid; idx < crow * kq; idx += NT, r += dr, k4 += dk) {
+          if (k4 >= kq) { k4 -= kq; ++r; }
           const int v = own.lo + c0 + r;
           const float id2 = invdeg[v];
           const int e = Ls.ex[c0 + r], x0 = e & 0xffff, nex = e >> 16;
@@ -754,22 +763,26 @@ __device__ __forceinline__ bool forward_body(const igmc_model_t& M, const float*
   if (rank != 0 || ext) { IGMC_WALL(51); return true; }
   // ---- readout (models.py:205-215), one CTA of the cluster ----
   __syncthreads();
+  IGMC_STAMP(27);
   for (int c = tid; c < F; c += NT) S.feat[(size_t)g * F + c] = feat_s[c];
   if (tid == 0) { S.target[2 * g] = nb + tu; S.target[2 * g + 1] = nb + ti; }
   const float* W1 = params + M.off_lin1_w;
-  for (int ob = warp * 4; ob < L1O; ob += nwarps * 4) {   // 4 outputs per warp with independent load streams
-    float s4[4] = {0.f, 0.f, 0.f, 0.f};
-    const float bias_o = lane < 4 ? __ldg(params + M.off_lin1_b + ob + lane) : 0.f;   // independent of the dot products
-#pragma unroll 8   // 32 independent L2 loads in flight per lane (the loop is latency bound)
+  constexpr int OW = 8;   // outputs per warp and pass: 16 warps x 8 = all 128 in one pass of L2 latency
+  for (int ob = warp * OW; ob < L1O; ob += nwarps * OW) {
+    float s4[OW];
+#pragma unroll
+    for (int u = 0; u < OW; ++u) s4[u] = 0.f;
+    const float bias_o = lane < OW ? __ldg(params + M.off_lin1_b + ob + lane) : 0.f;   // independent of the dot products
+#pragma unroll 4   // 32 independent L2 loads in flight per lane (the loop is latency bound)
     for (int i = lane; i < F; i += 32) {
       const float f = feat_s[i];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) s4[u] = fmaf(__ldg(W1 + (size_t)(ob + u) * F + i), f, s4[u]);
+      for (int u = 0; u < OW; ++u) s4[u] = fmaf(__ldg(W1 + (size_t)(ob + u) * F + i), f, s4[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) s4[u] = warp_sum_f(s4[u]);
+    for (int u = 0; u < OW; ++u) s4[u] = warp_sum_f(s4[u]);
 #pragma unroll
-    for (int u = 0; u < 4; ++u) if (lane == u) {
+    for (int u = 0; u < OW; ++u) if (lane == u) {
       const int o = ob + u;
       const float s = s4[u];
       float h = fmaxf(s + bias_o, 0.f);
@@ -790,7 +803,9 @@ __device__ __forceinline__ bool forward_body(const igmc_model_t& M, const float*
       S.hid_gscale[(size_t)g * L1O + o] = h > 0.f ? scale : 0.f;
     }
   }
+  IGMC_STAMP(28);
   __syncthreads();
+  IGMC_STAMP(29);
   if (warp == 0) {
     float s = 0.f;
     const float b2 = __ldg(params + M.off_lin2_b), yg = y ? __ldg(y + g) : 0.f;   // issued with the weight loads
@@ -966,7 +981,7 @@ __device__ __forceinline__ void backward_body(const igmc_model_t& M, const float
     const int i = tid % F, part = tid / F;
     if (part < parts) {
       float s = 0.f;
-#pragma unroll 16
+#pragma unroll 32   // independent L2 loads in flight (latency bound)
       for (int o = part; o < L1O; o += parts) s = fmaf(__ldg(W1 + (size_t)o * F + i), dhid_s[o], s);
       stage[part * F + i] = s;
     }
@@ -1050,7 +1065,7 @@ __device__ __forceinline__ void backward_body(const igmc_model_t& M, const float
         }
         // (1) data gradient of the own nodes:  d h_{l-1}[u] = [Q[u] | dpre[u]] . [W_r^T ; root^T],
         //     Q[u,r,:] = sum_{(u->d) of type r, kept} dpre[d,:]/deg(d)         -> pushed to every CTA's DH
-        gather_segments(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, DPS, stage, SS, HID, &ws[33]);
+        gather_segments<8>(Ls, K, Ls.segbase[c0], Ls.segbase[c0 + crow], lane, DPS, stage, SS, HID, &ws[33]);
         __syncthreads();
         if (tid == 0) ws[33] = 0;
         {   // fold the extra segments of long lists into their node row
@@ -1434,7 +1449,7 @@ static int launch_cluster(Kern kern, int grid, int threads, size_t smem, int clu
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (pdl && pdl_enabled()) {   // may start under the tail of the previous kernel of the stream (pdl_wait inside)
+  if (pdl && (pdl_enabled() & 1)) {   // IGMC_PDL bit 0: backward behind the forward; bit 1: update kernel (csrc/optim.cu)   // may start under the tail of the previous kernel of the stream (pdl_wait inside)
     at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.numAttrs = 2;

@@ -66,6 +66,8 @@ for plan in (2, 1):
     fl.update({39: "L1 w0 gather start", 49: "L1 w31 gather start", 40: "L1 w0 gather_segments done", 43: "L1 w31 gather_segments done", 46: "L1 w15 gather_segments done",
                41: "L1 w0 after sync", 44: "L1 w31 after sync", 42: "L1 w0 fold done", 45: "L1 w31 fold done"})
     fl[26] = "readout done"
+    fl.update({32: "L0 gather_segments done (warp0)", 33: "L0 after sync", 27: "readout start", 28: "readout lin1 done (warp0)",
+               29: "readout lin1 synced"})
     show2("forward", f, fl)
     print("  staging facts (fwd): staged=%s entries=%s segs=%s lcap=%s chunk=%s n_own=%s" % tuple(
         sorted(set(f[:, c].tolist()))[:6] for c in (60, 61, 62, 63, 59, 58)))
