@@ -524,8 +524,10 @@ def run_ours(args):
         ab = algorithmic_bytes(stats, static=static, keep=1.0 - ds["adj_dropout"])
         nb_batches = min(K, 20)
         names = ("extract", "forward", "backward", "grad_reduce", "adam")
-        acc = {n: 0.0 for n in names}
-        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 1)]
+        # the engine's step runs forward + loss + backward as ONE launch (igmc_forward_backward) when the model allows
+        one_launch = args.model != "dgcnn_rs" and os.environ.get("IGMC_FUSED_FB", "1") != "0"
+        acc = {n: 0.0 for n in names + ("forward_backward",)}
+        evs = [torch.cuda.Event(enable_timing=True) for _ in range(len(names) + 3)]
         ex = train.extractor
         reps = min(K, 50)
         for k in range(reps):
@@ -545,13 +547,26 @@ def run_ours(args):
             evs[4].record()
             opt.step(lr_dev=eng.lr_dev)
             evs[5].record()
+            if one_launch and model.fused_update_ok(b):
+                model.prep_weights(mark=True)      # (its own launch in this eager sequence; the step's update kernel
+                flush.fill_(1)                     #  rebuilds the prepared weights itself)
+                evs[6].record()
+                model._launch_train(b, drop, b.y, 1.0 / G)
+                evs[7].record()
+            else:
+                one_launch = False
             torch.cuda.synchronize()
             for i, n in enumerate(names):
                 acc[n] += evs[i].elapsed_time(evs[i + 1])
+            if one_launch:
+                acc["forward_backward"] += evs[6].elapsed_time(evs[7])
         kern_ms = {n: acc[n] / reps for n in names}
-        # dominant kernel of the step's critical path; the two extraction kernels run under it on the second
+        if one_launch:
+            kern_ms["forward_backward"] = acc["forward_backward"] / reps
+        ab["forward_backward"] = ab["forward"] + ab["backward"]
+        # dominant kernel of the step's critical path; the extraction kernels run under it on the second
         # branch of the step graph and get their own line (`roofline.extract`)
-        dom = max(("forward", "backward"), key=lambda n: kern_ms[n])
+        dom = "forward_backward" if one_launch else max(("forward", "backward"), key=lambda n: kern_ms[n])
         peak, peak_src = peaks()
         traffic = None     # DRAM bytes per launch from an `ncu --set full` capture OF THIS workload + model, else null
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -580,9 +595,10 @@ def run_ours(args):
                                  if zc else "cudaMemcpyAsync H2D + D2H per step",
                     "runs_ms_per_step": [1000.0 * x / K for x in e2e_runs]},
             # our kernels per pipelined step.  IGMC: gate + extraction (one launch; static store: assembly) + list
-            # images + forward + backward + fused reduce/exchange/Adam/weight-prep = 6.  DGCNN_RS (external readout, no
+            # images + forward/loss/backward (one launch; two with IGMC_FUSED_FB=0) + fused
+            # reduce/exchange/Adam/weight-prep = 5 (6).  DGCNN_RS (external readout, no
             # fused update): + weight prep + 3 SortPooling launches + gradient assembly + Adam = 11
-            "gpu_launches": (11 if args.model == "dgcnn_rs" else 6) * K,
+            "gpu_launches": (11 if args.model == "dgcnn_rs" else 5 if one_launch else 6) * K,
             "warm_l2": {"value": G * K / (warm_ms / 1000.0), "ms_per_step": warm_ms / K,
                         "note": "same steps back to back without the L2 flush (informative)"},
             "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",

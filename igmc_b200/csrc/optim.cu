@@ -379,6 +379,16 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// gpu-scope twins for a single-rank exchange (world == 1: the flags only release this GPU's own blocks; a system-scope
+// fence per block costs microseconds on the critical path of every step)
+__device__ __forceinline__ void st_release_dev(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_dev(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
   float v;
   asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
@@ -421,20 +431,28 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
   int* tick = reinterpret_cast<int*>(C.state + 1);  // [0] phase-1 ticket, [1] phase-3 ticket
   __shared__ int s_pub;
   __syncthreads();
+  const bool solo = C.world == 1;   // no peers: device-scope ordering is enough
   if (tid == 0) {
-    __threadfence_system();
+    if (solo) __threadfence(); else __threadfence_system();
     s_pub = (atomicAdd(&tick[0], 1) == (int)gridDim.x - 1);
     if (s_pub) tick[0] = 0;
   }
   __syncthreads();
   // the last block publishes "step t ready", one thread per destination rank (the stores travel in parallel)
   if (s_pub && tid < C.world) {
-    __threadfence_system();
-    st_release_sys(C.flag[tid] + C.rank, t);   // includes the own flag
+    if (solo) {
+      __threadfence();
+      st_release_dev(C.flag[0] + C.rank, t);
+    } else {
+      __threadfence_system();
+      st_release_sys(C.flag[tid] + C.rank, t);   // includes the own flag
+    }
   }
   // every block: one thread per source rank polls its arrival flag
-  if (tid < C.world)
-    while (ld_acquire_sys(C.flag[C.rank] + tid) - t < 0) {}
+  if (tid < C.world) {
+    if (solo) while (ld_acquire_dev(C.flag[C.rank]) - t < 0) {}
+    else while (ld_acquire_sys(C.flag[C.rank] + tid) - t < 0) {}
+  }
   __syncthreads();
   const float lr = lr_dev ? *lr_dev : lr_val;
   const float bc1 = s_bc[0], bc2 = s_bc[1];

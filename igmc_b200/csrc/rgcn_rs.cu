@@ -688,7 +688,7 @@ __device__ __forceinline__ bool forward_body(const igmc_model_t& M, const float*
           }
           t.x *= id2; t.y *= id2; t.z *= id2; t.w *= id2;
           st4[(size_t)r * SS4 + k4] = t;
-          if (S.zsave && l == 0)   // layers >= 1: the backward takes its weight gradients from its own aggregate
+          if (S.zsave && l == 0 && n_own > chunk)   // (one chunk: copied out below, in the cluster-barrier window)
             reinterpret_cast<float4*>(S.zsave + (size_t)(nb + v) * (size_t)K1)[k4] = t;
         }
       }
@@ -743,6 +743,19 @@ __device__ __forceinline__ bool forward_body(const igmc_model_t& M, const float*
     // the next layer's weights do not depend on the peers: load them while the row pushes of the cluster land
     if (CL > 1) cluster_arrive();
     if (l + 1 < L) load_weights(l + 1);
+    if (S.zsave && l == 0 && n_own <= chunk) {
+      // layer 0's scaled aggregate for the backward (layers >= 1: the backward takes its weight gradients from its own
+      // aggregate): the staging rows are untouched until the next gather, so the copy runs while the peers' rows land
+      const int kq = K1 >> 2, SS4 = SS >> 2;
+      const float4* st4 = reinterpret_cast<const float4*>(stage);
+      const int dr = NT / kq, dk = NT - dr * kq;
+      int r = tid / kq, k4 = tid - r * kq;
+      for (int idx = tid; idx < n_own * kq; idx += NT, r += dr, k4 += dk) {
+        if (k4 >= kq) { k4 -= kq; ++r; }
+        reinterpret_cast<float4*>(S.zsave + (size_t)(nb + own.lo + r) * (size_t)K1)[k4] = st4[(size_t)r * SS4 + k4];
+      }
+      IGMC_STAMP(34);
+    }
     if (CL > 1) cluster_wait();
     IGMC_STAMP(7 + 6 * l);
     float* t = H; H = Hn; Hn = t;

@@ -67,7 +67,7 @@ for plan in (2, 1):
                41: "L1 w0 after sync", 44: "L1 w31 after sync", 42: "L1 w0 fold done", 45: "L1 w31 fold done"})
     fl[26] = "readout done"
     fl.update({32: "L0 gather_segments done (warp0)", 33: "L0 after sync", 27: "readout start", 28: "readout lin1 done (warp0)",
-               29: "readout lin1 synced"})
+               29: "readout lin1 synced", 34: "L0 zsave copied (barrier window)"})
     show2("forward", f, fl)
     print("  staging facts (fwd): staged=%s entries=%s segs=%s lcap=%s chunk=%s n_own=%s" % tuple(
         sorted(set(f[:, c].tolist()))[:6] for c in (60, 61, 62, 63, 59, 58)))
