@@ -196,19 +196,33 @@ __device__ __forceinline__ void sum_rows(const float* __restrict__ gp, int rows,
 #pragma unroll
       for (int c = 0; c < NCT; ++c) acc[c] += v[u][c];
   }
-  for (; g0 < rows; g0 += 8) {                        // tail rows
-    float v[NCT];
-    const float* gr = gp + (size_t)g0 * RC;
+  if (g0 < rows) {   // last, partial batch: still ONE round of loads (rows past the end read row g0 and add +0)
+    float v[UR][NCT];
 #pragma unroll
-    for (int c = 0; c < NCT; ++c) v[c] = __ldcg(gr + off[c]);
+    for (int u = 0; u < UR; ++u) {
+      const bool in_range = g0 + 8 * u < rows;
+      const float* gr = gp + (size_t)(in_range ? g0 + 8 * u : g0) * RC;
 #pragma unroll
-    for (int c = 0; c < NCT; ++c) acc[c] += v[c];
+      for (int c = 0; c < NCT; ++c) v[u][c] = __ldcg(gr + off[c]);
+    }
+#pragma unroll
+    for (int u = 0; u < UR; ++u) {
+      const bool in_range = g0 + 8 * u < rows;
+#pragma unroll
+      for (int c = 0; c < NCT; ++c) acc[c] += in_range ? v[u][c] : 0.f;
+    }
   }
 #pragma unroll
   for (int c = 0; c < NCT; ++c)
     if (c < NC) ps[c][warp][lane] = acc[c];
 }
 
+// the step's loss from the per-layer regulariser values and the squared errors (one warp; lane-strided partial sums +
+// shuffle tree: the same bits wherever it is called from)
+__device__ __forceinline__ float loss_from_parts(const float* __restrict__ reg_ws, const float* __restrict__ sqerr, int B,
+                                                 int L, float loss_scale, float arr, int lane);
+
+template <bool LOSS_INSIDE>
 __device__ __forceinline__ void reduce_raw_block(const igmc_model_t& M, const float* __restrict__ params, int B, int rows,
                                                  int NA, const float* __restrict__ gpart, const float* __restrict__ dhid,
                                                  const float* __restrict__ feat, const float* __restrict__ hid,
@@ -225,17 +239,17 @@ __device__ __forceinline__ void reduce_raw_block(const igmc_model_t& M, const fl
     bool write = false;
     if (p >= M.off_lin1_w && p < M.off_lin1_w + L1O * F) {
       const int q = p - M.off_lin1_w, o = q / F, i = q - o * F;      // lin1.weight[o][i]
-#pragma unroll 10
+#pragma unroll 25   // 50 independent L2 loads in flight (latency bound)
       for (int g = 0; g < B; ++g) s = fmaf(dhid[(size_t)g * L1O + o], feat[(size_t)g * F + i], s);
       write = true;
     } else if (p >= M.off_lin1_b && p < M.off_lin1_b + L1O) {
       const int o = p - M.off_lin1_b;
-#pragma unroll 10
+#pragma unroll 25
       for (int g = 0; g < B; ++g) s += dhid[(size_t)g * L1O + o];
       write = true;
     } else if (p >= M.off_lin2_w && p < M.off_lin2_w + L1O) {
       const int o = p - M.off_lin2_w;
-#pragma unroll 10
+#pragma unroll 25
       for (int g = 0; g < B; ++g) s = fmaf(dpred[g], hid[(size_t)g * L1O + o], s);
       write = true;
     } else if (p == M.off_lin2_b) {
@@ -257,17 +271,20 @@ __device__ __forceinline__ void reduce_raw_block(const igmc_model_t& M, const fl
   __shared__ float Wc[12][HID];
   __shared__ float red[8];
   __shared__ int s_last;
-  for (int i = tid; i < R * NB; i += 256) att[i] = params[M.off_att[l] + i];
-  for (int i = tid; i < NB * HID; i += 256) bs[i >> 5][i & 31] = params[M.off_basis[l] + ((i >> 5) * in + k) * HID + (i & 31)];
+  // (R * NB <= 48 and NB * 32 <= 128 values: one per thread; loaded now, parked in registers under the row sums)
+  const float att_v = tid < R * NB ? params[M.off_att[l] + tid] : 0.f;
+  const float bs_v = tid < NB * HID ? params[M.off_basis[l] + ((tid >> 5) * in + k) * HID + (tid & 31)] : 0.f;
   const int NC = R + 1 + (k == 0 ? 1 : 0);
   {
     // column c of this block inside a raw row: c <= R: row k of dW_c / d root; c == R + 1: d bias.
     // warp w sums the partial rows g == w (mod 8); loads are issued in batches (UR rows x NCT columns in flight per
     // thread) BEFORE any of them is consumed - the row sums are L2-latency bound
     const float* gp = gpart + (size_t)igmc_raw_off(R, in0, l) + lane;
-    if (NC <= 7) sum_rows<7, 4>(gp, rows, RC, R, inp, k, NC, warp, lane, ps);
-    else sum_rows<14, 2>(gp, rows, RC, R, inp, k, NC, warp, lane, ps);
+    if (NC <= 7) sum_rows<7, 7>(gp, rows, RC, R, inp, k, NC, warp, lane, ps);   // 100 rows: two rounds of 49 loads
+    else sum_rows<14, 4>(gp, rows, RC, R, inp, k, NC, warp, lane, ps);
   }
+  if (tid < R * NB) att[tid] = att_v;
+  if (tid < NB * HID) bs[tid >> 5][tid & 31] = bs_v;
   __syncthreads();
   for (int t = tid; t < NC * HID; t += 256) {
     const int c = t >> 5, j = t & 31;
@@ -329,16 +346,33 @@ __device__ __forceinline__ void reduce_raw_block(const igmc_model_t& M, const fl
   // ---- last block of layer l: d att[l] and the layer's regulariser value (warp per value, lane = k; the shuffle tree
   //      fixes the order) ----
   __threadfence();
-  for (int pr = warp; pr < R * NB + 1; pr += 8) {
-    const float* src = pr < R * NB ? reg_ws + RW_ATT + (size_t)l * 32 * 64 + pr : reg_ws + RW_REGP + l * 32;
-    const int strd = pr < R * NB ? 64 : 1;
-    const float s = warp_sum_f(lane < in ? __ldcg(src + (size_t)lane * strd) : 0.f);
-    if (lane == 0) {
-      if (pr < R * NB) grad[M.off_att[l] + pr] = s * grad_scale;
-      else reg_ws[RW_REGL + l] = s;
+  {
+    constexpr int MAXV = (12 * IGMC_MAX_BASES + 1 + 7) / 8;   // values per warp at R = 12
+    float pv[MAXV];
+#pragma unroll
+    for (int q = 0; q < MAXV; ++q) {   // one round of L2 latency for all of the warp's values
+      const int pr = warp + 8 * q;
+      const float* src = pr < R * NB ? reg_ws + RW_ATT + (size_t)l * 32 * 64 + pr : reg_ws + RW_REGP + l * 32;
+      const int strd = pr < R * NB ? 64 : 1;
+      pv[q] = (pr < R * NB + 1 && lane < in) ? __ldcg(src + (size_t)lane * strd) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < MAXV; ++q) {
+      const int pr = warp + 8 * q;
+      if (pr < R * NB + 1) {   // (uniform over the warp)
+        const float s = warp_sum_f(pv[q]);
+        if (lane == 0) {
+          if (pr < R * NB) grad[M.off_att[l] + pr] = s * grad_scale;
+          else reg_ws[RW_REGL + l] = s;
+        }
+      }
     }
   }
   __syncthreads();
+  if (!LOSS_INSIDE) {   // the caller computes the loss behind its own grid barrier (k_reduce_allreduce_adam)
+    if (tid == 0) tick[l] = 0;   // re-arm
+    return;
+  }
   if (tid == 0) {
     tick[l] = 0;   // re-arm
     __threadfence();
@@ -346,18 +380,24 @@ __device__ __forceinline__ void reduce_raw_block(const igmc_model_t& M, const fl
   }
   __syncthreads();
   if (!s_last || warp != 0) return;
-  // last layer to finish: the loss (one warp; lane-strided partial sums + shuffle tree)
+  // last layer to finish: the loss
   __threadfence();
-  float reg = lane < L ? __ldcg(reg_ws + RW_REGL + lane) : 0.f;
-  reg = warp_sum_f(reg);
-  float mse = 0.f;
-  if (sqerr)
-    for (int g = lane; g < B; g += 32) mse += sqerr[g];
-  mse = warp_sum_f(mse);
+  const float loss = loss_from_parts(reg_ws, sqerr, B, L, loss_scale, arr, lane);
   if (lane == 0) {
-    if (loss_out) loss_out[0] = mse * loss_scale + arr * reg;
+    if (loss_out) loss_out[0] = loss;
     tick[IGMC_MAX_LAYERS] = 0;
   }
+}
+
+__device__ __forceinline__ float loss_from_parts(const float* __restrict__ reg_ws, const float* __restrict__ sqerr, int B,
+                                                 int L, float loss_scale, float arr, int lane) {
+  float reg = lane < L ? __ldcg(reg_ws + RW_REGL + lane) : 0.f;
+  float mse = 0.f;
+  if (sqerr)
+    for (int g = lane; g < B; g += 32) mse += __ldcg(sqerr + g);
+  reg = warp_sum_f(reg);
+  mse = warp_sum_f(mse);
+  return mse * loss_scale + arr * reg;
 }
 
 __global__ void __launch_bounds__(256)
@@ -366,8 +406,8 @@ k_grad_reduce_raw(igmc_model_t M, const float* __restrict__ params, int B, int r
                   const float* __restrict__ hid, const float* __restrict__ dpred, const float* __restrict__ sqerr,
                   float loss_scale, float arr, float grad_scale, float* __restrict__ grad, float* __restrict__ loss_out,
                   float* __restrict__ reg_ws) {
-  reduce_raw_block(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, grad_scale, grad,
-                   loss_out, reg_ws);
+  reduce_raw_block<true>(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, grad_scale, grad,
+                         loss_out, reg_ws);
 }
 
 // ---- system-scope flags for the peer exchange ----------------------------------------------------------------
@@ -405,7 +445,7 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 // Two parities are enough: a rank overwrites parity p in step t + 2 only after it has seen every peer's flag t + 1,
 // which a peer raises after its step-t kernel (and thus its reads of parity p) has finished.
 // The grid (<= 300 blocks of 256 threads) is always co-resident, so spinning inside the grid is safe.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)   // <= 128 registers: two blocks per SM keep the <= 296-block grid co-resident
 k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int rows, int NA,
                         const float* __restrict__ gpart, const float* __restrict__ dhid, const float* __restrict__ feat,
                         const float* __restrict__ hid, const float* __restrict__ dpred, const float* __restrict__ sqerr,
@@ -426,8 +466,8 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
     s_bc[tid - 254] = (float)(1.0 - exp(step * (tid == 255 ? log_b2 : log_b1)));
   }
   float* gl = C.grad[C.rank] + (size_t)(t & 1) * C.stride;
-  reduce_raw_block(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, 1.0f, gl, loss_out,
-                   reg_ws);
+  reduce_raw_block<false>(M, params, B, rows, NA, gpart, dhid, feat, hid, dpred, sqerr, loss_scale, arr, 1.0f, gl,
+                          loss_out, reg_ws);
   int* tick = reinterpret_cast<int*>(C.state + 1);  // [0] phase-1 ticket, [1] phase-3 ticket
   __shared__ int s_pub;
   __syncthreads();
@@ -475,11 +515,15 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
     const float denom = sqrtf(vi) / sqrtf(bc2) + eps;
     params[i] = p - (lr / bc1) * (mi / denom);
   }
-  if (blockIdx.x == 0 && tid == 0 && loss_out) {
-    const float lv = __ldcg(loss_out);
-    if (loss_acc) loss_acc[0] += lv * loss_weight;
-    // the step's result for the host: slot (step number mod ring size) of a mapped pinned-host ring, no copy launch
-    if (loss_ring) loss_ring[(int)(step_i & (int64_t)ring_mask)] = lv;
+  if (blockIdx.x == 0 && tid < 32 && loss_out) {
+    // the step's loss, off the critical path (every layer's regulariser value is complete behind the grid barrier)
+    const float lv = loss_from_parts(reg_ws, sqerr, B, M.num_layers, loss_scale, arr, tid);
+    if (tid == 0) {
+      loss_out[0] = lv;
+      if (loss_acc) loss_acc[0] += lv * loss_weight;
+      // the step's result for the host: slot (step number mod ring size) of a mapped pinned-host ring, no copy launch
+      if (loss_ring) loss_ring[(int)(step_i & (int64_t)ring_mask)] = lv;
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -504,9 +548,10 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
   {
     const int R = M.num_relations, NB = M.num_bases;
     const size_t slab = (size_t)HID * ((size_t)(R + 1) * HID + 4);
-    for (int row = blockIdx.x; row < M.num_layers * 2 * 32; row += gridDim.x) {
+    // rows of slab (0, 1) do not exist (layer 0 has no data gradient): active row a -> row a (a < 32) / a + 32
+    for (int a = blockIdx.x; a < (M.num_layers * 2 - 1) * 32; a += gridDim.x) {
+      const int row = a < 32 ? a : a + 32;
       const int n = row & 31, ld = row >> 5, l = ld >> 1, dir = ld & 1;
-      if (dir == 1 && l == 0) continue;
       const int in = l == 0 ? M.in_dim0 : HID, inp = (in + 3) & ~3;
       const int K1 = R * inp, K1p = (K1 + 7) & ~7, inpp = (inp + 7) & ~7, KS = K1p + inpp + 4;
       const float* bs = params + M.off_basis[l];
@@ -519,7 +564,15 @@ k_reduce_allreduce_adam(igmc_model_t M, float* __restrict__ params, int B, int r
           const int r = kk / inp, q = kk - r * inp;
           if (q < in) {
             const int k = dir == 0 ? q : n, j = dir == 0 ? n : q;
-            for (int b = 0; b < NB; ++b) w = fmaf(__ldcg(at + r * NB + b), __ldcg(bs + (b * in + k) * HID + j), w);
+            float av[IGMC_MAX_BASES], bv[IGMC_MAX_BASES];
+#pragma unroll
+            for (int b = 0; b < IGMC_MAX_BASES; ++b) {   // all loads in flight before the first fma
+              av[b] = b < NB ? __ldcg(at + r * NB + b) : 0.f;
+              bv[b] = b < NB ? __ldcg(bs + (b * in + k) * HID + j) : 0.f;
+            }
+#pragma unroll
+            for (int b = 0; b < IGMC_MAX_BASES; ++b)
+              if (b < NB) w = fmaf(av[b], bv[b], w);
           }
         } else if (kk >= K1p && kk < K1p + inp) {
           const int q = kk - K1p;
